@@ -1,0 +1,265 @@
+#!/usr/bin/env python3
+"""Headline benchmark: 752x576 frames/sec (and p50 per-frame latency) of the fused pix_shuffle
+forward on B200, next to the reference's CPU forward.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision bf16|fp32]
+
+One "step" = one pass of the hot path over one batch of 64 synthetic RGB444 framebuffers (mixed
+lores / lores-laced / hires / hires-laced pixel modes) per GPU: uint8 RGBA [64,576,752,4] in ->
+gamma -> pix_shuffle-lightweight -> gamma -> uint8 RGBA out (BASELINE.json configs[1]; the deployed
+contract of convertion_tools/torch2onnx.py).  `value` is timed with the frames already in HBM;
+`e2e` goes through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed region).
+N>1 (torchrun): every rank runs the same per-GPU batch on its own GPU, no data-path collective.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAME_H, FRAME_W, BATCH = 576, 752, 64
+GFLOP_PER_FRAME = 29.472          # 2 * 136080 MAC/px * 108288 px, no halo/padding
+BYTES_PER_FRAME_U8 = 2 * FRAME_H * FRAME_W * 4
+WORKLOAD = "pix_shuffle-lightweight, 64 synthetic RGB444 752x576 RGBA framebuffers per GPU (16 each lores/lores_laced/hires/hires_laced), u8 in -> u8 out incl. gamma"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1379.1), d.get("hbm_gbs", 6549.1), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        time.sleep(0.05)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_forward_fps(n_frames: int, batch: int, repeats: int = 1):
+    """The reference's CPU eval forward (oracle port: same torch ops as model_pix_shuffle.py:227-298 +
+    the float glue of train.py:57-73) on the host cores, on a bounded sample of the workload."""
+    import torch
+    from oracle import enhancer_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    spec = O.pix_shuffle_preset("lightweight")
+    sd = O.make_pix_shuffle_state_dict(spec, 7)
+    fb = O.synth_framebuffers(n_frames, seed=100)
+    with torch.no_grad():
+        O.framebuffer_forward(sd, spec, fb[:1])                       # warm-up
+        times = []
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            for i in range(0, n_frames, batch):
+                O.framebuffer_forward(sd, spec, fb[i:i + batch])
+            times.append(time.perf_counter() - t0)
+    return n_frames / statistics.median(times), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = 8
+    vals = []
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_forward_fps(2, 2)
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        fps, threads = cpu_forward_fps(n, 4)
+        vals.append(fps)
+    fps = statistics.median(vals)
+    line = {
+        "impl": "reference", "metric": "752x576 frames/sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * n / fps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": f"each step = {n}-frame sample of the workload, batch 4"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": f"{n} frames per step, oracle port of the PyTorch eval forward, fp32"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t_all,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from fs_uae_image_enhancer_project_b200 import _lib, model_pix_shuffle
+    from oracle import enhancer_oracle as O     # synthetic frames, seeded weights, cpu_baseline leg only
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    spec = O.pix_shuffle_preset("lightweight")
+    sd = O.make_pix_shuffle_state_dict(spec, 7)
+    model = model_pix_shuffle.get_model("lightweight")
+    model.load_state_dict(sd)
+    model = model.to(dev)
+    model.chunk_frames = 16
+    precision = args.precision
+    if precision in ("auto", "bf16"):
+        try:
+            model.set_precision("bf16")
+            model.engine_for(dev, FRAME_H, FRAME_W)
+            precision = "bf16"
+        except _lib.EngineError as exc:
+            if args.precision == "bf16" or exc.code != _lib.ERR_UNSUPPORTED:
+                raise
+            precision = "fp32"
+    if precision == "fp32":
+        model.set_precision("fp32")
+    eng = model.engine_for(dev, FRAME_H, FRAME_W)
+
+    # two rotating batches: 2 x 64 frames x (1.73 MB in + 1.73 MB out) = 443 MB > 126 MB L2
+    host = [O.synth_framebuffers(BATCH, seed=1000 + 10 * rank + i).pin_memory() for i in range(2)]
+    d_in = [h.to(dev) for h in host]
+    d_out = [torch.empty_like(t) for t in d_in]
+    flags = _lib.FLAG_GAMMA_IN | _lib.FLAG_GAMMA_OUT
+
+    def step(i):
+        eng.enqueue(d_in[i & 1], d_out[i & 1], BATCH, _lib.FMT_U8_NHWC4, _lib.FMT_U8_NHWC4, flags)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    launches_per_step = eng.last_launch_count
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        step(i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # single-frame latency, device resident (p50 over 200 launches)
+    lat = []
+    one_in, one_out = d_in[0][:1].contiguous(), d_out[0][:1].contiguous()
+    for i in range(20):
+        eng.enqueue(one_in, one_out, 1, _lib.FMT_U8_NHWC4, _lib.FMT_U8_NHWC4, flags)
+    torch.cuda.synchronize(dev)
+    for i in range(200):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        eng.enqueue(one_in, one_out, 1, _lib.FMT_U8_NHWC4, _lib.FMT_U8_NHWC4, flags)
+        b.record()
+        b.synchronize()
+        lat.append(a.elapsed_time(b))
+    lat.sort()
+
+    # end to end through the host-buffer C-ABI call (pinned host memory; H2D and D2H inside)
+    h_out = [torch.empty_like(h).pin_memory() for h in host]
+    for i in range(2):
+        eng.run_host(host[i & 1], h_out[i & 1], BATCH, _lib.FMT_U8_NHWC4, _lib.FMT_U8_NHWC4, flags)
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        eng.run_host(host[i & 1], h_out[i & 1], BATCH, _lib.FMT_U8_NHWC4, _lib.FMT_U8_NHWC4, flags)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = t[0].item(), t[1].item()
+
+    if rank == 0:
+        frames = BATCH * world * args.steps
+        fps = frames / (ms / 1000.0)
+        tf_peak, hbm_peak, how = measured_peaks()
+        per_gpu_step_s = ms / 1000.0 / args.steps
+        achieved_tf = GFLOP_PER_FRAME * BATCH / per_gpu_step_s / 1000.0
+        line = {
+            "metric": "752x576 frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "variant": eng.variant, "frames_per_gpu_per_step": BATCH,
+                       "l2": "inputs rotate over 2 batches (443 MB in+out) > 126 MB L2",
+                       "sharding": "frame-wise, one replica per GPU, no collective"},
+            "latency_p50_ms": lat[len(lat) // 2], "latency_p99_ms": lat[int(len(lat) * 0.99) - 1],
+            "us_per_frame": 1e6 * per_gpu_step_s / BATCH,
+            "e2e": {"value": BATCH * world * e2e_steps / e2e_s, "unit": "frames/s",
+                    "h2d_bytes_per_step": BATCH * FRAME_H * FRAME_W * 4, "d2h_bytes_per_step": BATCH * FRAME_H * FRAME_W * 4,
+                    "steps": e2e_steps},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": tf_peak, "unit": "TFLOP/s",
+                         "frac": achieved_tf / tf_peak, "traffic": None,
+                         "note": f"algorithmic 29.472 GFLOP/frame x {BATCH} frames / step device time (all kernels of the "
+                                 f"pass); peak = {how} sustained bf16; HBM floor: {BYTES_PER_FRAME_U8 * BATCH / 1e9 / (hbm_peak) * 1e3:.3f} ms/step"},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cfps, threads = cpu_forward_fps(16, 4)
+            line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": threads, "kind": "port",
+                                    "sample": "16 of the 64 frames, batch 4, oracle port of the PyTorch fp32 eval forward"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

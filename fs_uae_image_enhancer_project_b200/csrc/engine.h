@@ -1,0 +1,107 @@
+// Internal engine state shared by the ABI layer and the two arithmetic builds.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "fsuae_enhancer.h"
+
+namespace fsuae {
+
+struct Bf16Plan;  // bf16_tc.cu
+
+}  // namespace fsuae
+
+struct fsuae_engine {
+  fsuae_net_desc desc;
+  int device = 0;
+  int precision = 0;
+  int H = 0, W = 0;          // full-resolution frame
+  int chunk = 1;             // frames per internal pass
+  int sm_count = 148;
+  std::string variant;
+  std::string last_error;
+  int64_t launches = 0;
+  size_t device_bytes = 0;
+
+  // parameters
+  float* d_blob = nullptr;
+  size_t blob_floats = 0;
+  std::vector<float> h_blob;
+
+  // fp32 build: planar fp32 activations, one buffer per layer output (+ head buffer 0)
+  std::vector<float*> f32_buf;      // [n_layers + 1]
+  std::vector<int> buf_channels;    // channels of each buffer
+
+  // bf16 build
+  fsuae::Bf16Plan* bf16 = nullptr;
+
+  // run_host staging
+  void* d_stage_in[2] = {nullptr, nullptr};
+  void* d_stage_out[2] = {nullptr, nullptr};
+  cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+};
+
+namespace fsuae {
+
+// geometry of one pass
+struct Geom {
+  int H, W;      // full-res frame
+  int xoff;      // first column the network sees (0 or 16)
+  int We;        // effective full-res width = W - xoff
+  int Hw, Ww;    // working resolution (half-res for the unshuffle head)
+};
+
+inline Geom make_geom(const fsuae_engine* e, uint32_t flags) {
+  Geom g;
+  g.H = e->H;
+  g.W = e->W;
+  g.xoff = (flags & FSUAE_FLAG_CROP16) ? 16 : 0;
+  g.We = e->W - g.xoff;
+  if (e->desc.head == FSUAE_HEAD_UNSHUFFLE2) {
+    g.Hw = e->H / 2;
+    g.Ww = g.We / 2;
+  } else {
+    g.Hw = e->H;
+    g.Ww = g.We;
+  }
+  return g;
+}
+
+inline size_t fmt_frame_bytes(int fmt, int H, int W) {
+  switch (fmt) {
+    case FSUAE_FMT_F32_NCHW3: return (size_t)3 * H * W * 4;
+    case FSUAE_FMT_U8_NHWC4: return (size_t)4 * H * W;
+    case FSUAE_FMT_U8_NCHW4: return (size_t)4 * H * W;
+    case FSUAE_FMT_F32_NCHW4: return (size_t)4 * H * W * 4;
+  }
+  return 0;
+}
+
+// fp32 build (fp32_path.cu)
+int fp32_create(fsuae_engine* e);
+void fp32_destroy(fsuae_engine* e);
+int fp32_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in_fmt, int out_fmt,
+                       uint32_t flags, cudaStream_t st);
+
+// bf16 build (bf16_tc.cu)
+int bf16_create(fsuae_engine* e);
+void bf16_destroy(fsuae_engine* e);
+int bf16_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in_fmt, int out_fmt,
+                       uint32_t flags, cudaStream_t st);
+
+int set_error(fsuae_engine* e, int code, const std::string& msg);
+
+#define FSUAE_CUDA_CHECK(e, call)                                                              \
+  do {                                                                                         \
+    cudaError_t _err = (call);                                                                 \
+    if (_err != cudaSuccess)                                                                   \
+      return fsuae::set_error((e), FSUAE_ERR_CUDA,                                             \
+                              std::string(#call) + ": " + cudaGetErrorString(_err));           \
+  } while (0)
+
+}  // namespace fsuae

@@ -1,0 +1,182 @@
+/*
+ * fsuae_enhancer.h -- C ABI of the B200-native FS-UAE image-enhancer inference engine.
+ *
+ * This is the drop-in boundary for the ONE hot path of cminnoy/fs_uae_image_enhancer_project:
+ * the per-frame forward of the upscaling network plus its uint8/gamma framebuffer glue.
+ * Plain pointers and sizes only; no torch / C++ types cross it.  Every entry point returns an
+ * int status (FSUAE_OK == 0), never throws, and -- except fsuae_engine_run_host and
+ * fsuae_engine_create/destroy -- never synchronises the device or allocates memory.
+ *
+ * Reference interfaces each entry point replaces (paths relative to the reference repo):
+ *
+ *   fsuae_engine_create      model/model_pix_shuffle.py:20-182 Model.__init__ + :304-314 get_model
+ *                            (and model_conv3.py:20-55/:206-211, model_conv5.py:22-68/:157-162)
+ *                            followed by load_state_dict / .to(device) / .half()
+ *                            -- and, at deploy time, OrtCreateSession on the exported graph
+ *                            (convertion_tools/convert_raw_to_png_using_final_model.py:66)
+ *   fsuae_engine_enqueue     Model.forward(x): model_pix_shuffle.py:227-298,
+ *                            model_conv3.py:102-155, model_conv5.py:114-151; with the
+ *                            FSUAE_FMT_U8_NHWC4 formats it is the whole exported graph
+ *                            input_rgba_chunky -> output_rgba_uint8_chunky
+ *                            (convertion_tools/torch2onnx.py:184-768), i.e. OrtRun
+ *                            (convert_raw_to_png_using_final_model.py:82)
+ *   fsuae_engine_run_host    the same call as made from the emulator side with HOST framebuffers
+ *                            (README.md:21-24: upload, upscale, copy back)
+ *   fsuae_engine_destroy     Python GC of the module / OrtReleaseSession
+ *   fsuae_last_error         Python exception text (ValueError at model_conv3.py:109-110,
+ *                            model_pix_shuffle.py:81-83, activations.py:123-127)
+ *
+ * The network is handed over as a flat descriptor + one float32 parameter blob, produced on the
+ * host from a reference state_dict (fs_uae_image_enhancer_project_b200/descriptor.py): conv
+ * weights in PyTorch order [Cout][Cin][3][3] with BatchNorm already folded
+ * (model_conv3.py:41-52 eval semantics), biases, and activation parameters.
+ */
+#ifndef FSUAE_ENHANCER_H
+#define FSUAE_ENHANCER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define FSUAE_API __attribute__((visibility("default")))
+#else
+#define FSUAE_API
+#endif
+
+#define FSUAE_ABI_VERSION 1
+#define FSUAE_MAX_LAYERS 16
+#define FSUAE_MAX_ACTS 4 /* activation slots before / after the skip add (reference uses <= 2) */
+
+/* status codes */
+enum {
+  FSUAE_OK = 0,
+  FSUAE_ERR_INVALID = 1,     /* bad argument / descriptor (reference: ValueError) */
+  FSUAE_ERR_UNSUPPORTED = 2, /* valid network the selected precision build cannot run; never a CPU fallback */
+  FSUAE_ERR_CUDA = 3,        /* CUDA runtime error; text in fsuae_last_error */
+  FSUAE_ERR_NO_DEVICE = 4
+};
+
+/* activation op-codes: the registry of model/activations.py:69-95 */
+enum {
+  FSUAE_ACT_IDENTITY = 0,
+  FSUAE_ACT_RELU = 1,
+  FSUAE_ACT_RELU6 = 2,
+  FSUAE_ACT_TANH = 3,
+  FSUAE_ACT_SIGMOID = 4,
+  FSUAE_ACT_SILU = 5,        /* 'silu' and 'swish' */
+  FSUAE_ACT_MISH = 6,
+  FSUAE_ACT_GELU = 7,        /* exact erf form */
+  FSUAE_ACT_ELU = 8,         /* p0 = alpha (scalar) */
+  FSUAE_ACT_SOFTPLUS = 9,    /* p0 = beta, p1 = threshold (scalars) */
+  FSUAE_ACT_LEAKY_RELU = 10, /* p0 = negative_slope (scalar) */
+  FSUAE_ACT_PRELU = 11,      /* p0 = slope[n0], n0 in {1, C} */
+  FSUAE_ACT_SCALED_TANH = 12,
+  FSUAE_ACT_TELU = 13,
+  FSUAE_ACT_SINLU = 14,      /* p0 = a, p1 = b (scalars) */
+  FSUAE_ACT_BIASED_RELU = 15,  /* p0 = bias[n0] */
+  FSUAE_ACT_BIASED_PRELU = 16, /* p0 = bias[n0], p1 = slope[n1] */
+  FSUAE_ACT_SOFTMAX = 17,      /* over channels (dim=1) */
+  FSUAE_ACT_LOG_SOFTMAX = 18,
+  FSUAE_ACT_COUNT = 19
+};
+
+typedef struct fsuae_act_desc {
+  int32_t op;
+  int32_t n0, p0_off; /* count and float offset into the blob of parameter 0 */
+  int32_t n1, p1_off; /* count and float offset of parameter 1 */
+} fsuae_act_desc;
+
+/* One 3x3 / stride 1 / zero-pad 1 convolution with its fused epilogue:
+ *   y = post( skip + pre( conv(cat[src0, src1]) + bias ) )
+ * Buffer ids: 0 = the network input after the head stage, i = output of layers[i-1]. */
+typedef struct fsuae_layer_desc {
+  int32_t cin0, cin1; /* channels taken from src0 / src1 (cin1 == 0: no concat) */
+  int32_t cout;
+  int32_t src0, src1;
+  int32_t skip_src;   /* -1: no skip add */
+  int32_t w_off;      /* float offset: weights [cout][cin0+cin1][3][3] */
+  int32_t b_off;      /* float offset: bias [cout]; -1: none */
+  int32_t n_pre, n_post;
+  fsuae_act_desc pre[FSUAE_MAX_ACTS];
+  fsuae_act_desc post[FSUAE_MAX_ACTS];
+} fsuae_layer_desc;
+
+/* head: how buffer 0 is derived from the frame */
+enum {
+  FSUAE_HEAD_PLAIN = 0,      /* 3 channels at full resolution (conv3, conv5) */
+  FSUAE_HEAD_UNSHUFFLE2 = 1  /* PixelUnshuffle(2): 12 channels at half resolution, channel c*4+dy*2+dx */
+};
+/* tail: how the last layer's output becomes the frame */
+enum {
+  FSUAE_TAIL_PLAIN = 0,                 /* 3 channels as they are (conv5) */
+  FSUAE_TAIL_SHUFFLE2_RESIDUAL_RELU = 1,/* PixelShuffle(2), + input, ReLU (model_pix_shuffle.py:293-296) */
+  FSUAE_TAIL_SCALE255_ALPHA = 2         /* x255 and alpha=255.0 appended (model_conv3.py:145-153) */
+};
+
+typedef struct fsuae_net_desc {
+  int32_t abi_version; /* FSUAE_ABI_VERSION */
+  int32_t n_layers;
+  int32_t head, tail;
+  fsuae_layer_desc layers[FSUAE_MAX_LAYERS];
+} fsuae_net_desc;
+
+/* arithmetic builds */
+enum {
+  FSUAE_PREC_FP32 = 0, /* fp32 FMA kernels, accurate libm activations */
+  FSUAE_PREC_BF16 = 1  /* bf16 operands on tcgen05 tensor cores, fp32 accumulate + epilogue */
+};
+
+/* frame formats at the boundary (all row-major, contiguous) */
+enum {
+  FSUAE_FMT_F32_NCHW3 = 0, /* float [B,3,H,W] in [0,1]; pix_shuffle: linear light (train.py:61) */
+  FSUAE_FMT_U8_NHWC4 = 1,  /* uint8 [B,H,W,4] RGBA framebuffer (torch2onnx.py:225-232, 717-756) */
+  FSUAE_FMT_U8_NCHW4 = 2,  /* uint8 [B,4,H,W] planar RGBA, input only (model_conv3.py:109-113) */
+  FSUAE_FMT_F32_NCHW4 = 3  /* float [B,4,H,W], output only, with FSUAE_TAIL_SCALE255_ALPHA */
+};
+
+/* flags */
+#define FSUAE_FLAG_GAMMA_IN  1u /* uint8 input: (u8/255)**2.2 (gamma.py:13-15; torch2onnx.py:391-412) */
+#define FSUAE_FLAG_GAMMA_OUT 2u /* uint8 output: clamp(y**(1/2.2),0,1)*255, truncate (gamma.py:31-33; train.py:70) */
+#define FSUAE_FLAG_CROP16    4u /* run the net on columns [16,W) and emit 16 black columns (torch2onnx.py:299-355, 634-674) */
+
+typedef struct fsuae_engine fsuae_engine;
+
+FSUAE_API int fsuae_abi_version(void);
+
+/* Build an engine for frames of height x width on CUDA device `device`.
+ * `blob` holds `blob_floats` float32 parameters addressed by the descriptor's offsets.
+ * `max_chunk_frames` bounds the frames processed per internal pass (workspace is sized for it);
+ * enqueue accepts any n_frames and loops.  All device memory is allocated here. */
+FSUAE_API int fsuae_engine_create(const fsuae_net_desc* desc, const float* blob, size_t blob_floats,
+                        int device, int precision, int height, int width, int max_chunk_frames,
+                        fsuae_engine** out);
+FSUAE_API int fsuae_engine_destroy(fsuae_engine* e);
+
+/* Asynchronous: enqueue the forward of n_frames frames on `cuda_stream` (a cudaStream_t).
+ * `in_dev` / `out_dev` are device pointers in the given formats. */
+FSUAE_API int fsuae_engine_enqueue(fsuae_engine* e, const void* in_dev, void* out_dev, int n_frames,
+                         int in_fmt, int out_fmt, uint32_t flags, void* cuda_stream);
+
+/* Synchronous end-to-end call with HOST buffers (pinned memory recommended): chunks the frames,
+ * overlaps H2D copy, compute and D2H copy on internal streams, returns when out_host is complete. */
+FSUAE_API int fsuae_engine_run_host(fsuae_engine* e, const void* in_host, void* out_host, int n_frames,
+                          int in_fmt, int out_fmt, uint32_t flags);
+
+/* Device bytes held by the engine (parameters + workspace + staging). */
+FSUAE_API size_t fsuae_engine_device_bytes(const fsuae_engine* e);
+/* Number of kernel launches the last enqueue / run_host issued (bench.py's gpu_launches). */
+FSUAE_API int64_t fsuae_engine_last_launch_count(const fsuae_engine* e);
+/* Name of the kernel variant the engine selected, e.g. "fp32_fma" / "bf16_tcgen05". */
+FSUAE_API const char* fsuae_engine_variant(const fsuae_engine* e);
+
+/* Text of the last error on this engine (or of the last failed create when e == NULL). */
+FSUAE_API const char* fsuae_last_error(const fsuae_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSUAE_ENHANCER_H */

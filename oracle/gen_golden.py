@@ -1,0 +1,157 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/* by running the REAL reference modules.  TEST INFRASTRUCTURE ONLY.
+
+Runs only in the build container (needs /root/reference, which does not exist on the GPU box);
+the vectors it writes are committed.  Recipe: put
+/root/reference/model on sys.path and pre-seed ``loss_vgg`` / ``loss_ssim`` with stub modules
+(the real ones need kornia, a VGG16 download and a file that is not in the repo).
+
+    python oracle/gen_golden.py            # rewrites tests/golden/
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+GOLD = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
+
+from oracle import enhancer_oracle as O  # noqa: E402
+from fs_uae_image_enhancer_project_b200 import onnx_weights  # noqa: E402
+
+
+def import_reference():
+    sys.path.insert(0, os.path.join(REF, "model"))
+    for mod, cls in (("loss_vgg", "PerceptualLoss"), ("loss_ssim", "SSIMLoss")):
+        m = types.ModuleType(mod)
+
+        class _Stub(nn.Module):
+            def __init__(self, *a, **k):
+                super().__init__()
+        setattr(m, cls, _Stub)
+        sys.modules[mod] = m
+    import model_pix_shuffle, model_conv3, model_conv5, gamma  # noqa
+    return model_pix_shuffle, model_conv3, model_conv5, gamma
+
+
+def ref_pix_shuffle(mps, spec: O.PixShuffleSpec):
+    c = spec.channels
+    kw = {f"layer{i + 1}_out_channels": c[i] for i in range(6)}
+    for slot, (name, params) in spec.acts.items():
+        layer, idx = slot[1], slot[-1]
+        kw[f"layer{layer}_act{idx}"] = name
+        kw[f"layer{layer}_act{idx}_params"] = params
+    return mps.Model(**kw).eval()
+
+
+# activation-vocabulary coverage: every registry name appears in some slot
+VOCAB_SPECS = {
+    "vocab_a": O.PixShuffleSpec((24, 24, 40, 40, 16, 24)).with_acts(
+        l1_act1="gelu", l1_act2=("leaky_relu", {"negative_slope": 0.05}),
+        l2_act1="silu", l2_act2=("biased_relu", {"num_parameters": 24}),
+        l2_act3="sigmoid", l2_act4=("prelu", {"num_parameters": 24}),
+        l3_act1="elu", l3_act2="relu",
+        l4_act1="softplus", l4_act2=("biased_prelu", {"num_parameters": 1}),
+        l4_act3="scaled_tanh", l4_act4="relu6",
+        l5_act1="swish", l5_act2="identity",
+        l6_act1="telu", l6_act2=("biased_relu", {"num_parameters": 1}),
+        l7_act1="tanh", l7_act2="identity"),
+    "vocab_b": O.PixShuffleSpec((16, 16, 32, 32, 16, 16)).with_acts(
+        l1_act1="mish", l1_act2="identity",
+        l2_act1="sinlu", l2_act2="relu",
+        l2_act3="softmax", l2_act4="identity",
+        l3_act1="log_softmax", l3_act2="tanh",
+        l4_act1=("elu", {"alpha": 0.7}), l4_act2=("prelu", {"num_parameters": 1}),
+        l4_act3="gelu", l4_act4=("leaky_relu", None),
+        l6_act1="sigmoid", l6_act2="relu6",
+        l7_act1="sinlu", l7_act2=("prelu", None)),
+}
+
+
+def main():
+    mps, mc3, mc5, gamma = import_reference()
+    if os.path.isdir(GOLD):
+        shutil.rmtree(GOLD)
+    os.makedirs(GOLD)
+    torch.set_num_threads(8)
+    g = torch.Generator().manual_seed(1234)
+
+    # ---- pix_shuffle, float path (model_pix_shuffle.py:227-298) ----
+    cases = {"lightweight": O.pix_shuffle_preset("lightweight"),
+             "heavyweight": O.pix_shuffle_preset("heavyweight"), **VOCAB_SPECS}
+    for seed, (name, spec) in enumerate(cases.items(), start=11):
+        sd = O.make_pix_shuffle_state_dict(spec, seed)
+        model = ref_pix_shuffle(mps, spec)
+        missing = model.load_state_dict(sd, strict=True)
+        # inputs: uniform rand (the reference's own benchmark input, :348) incl. a frame that
+        # exceeds [0,1] a little, odd tile-unfriendly sizes, batch 2
+        x = torch.rand((2, 3, 44, 60), generator=g) * 1.1
+        with torch.no_grad():
+            y = model(x)
+        np.savez_compressed(os.path.join(GOLD, f"pix_shuffle_{name}.npz"), seed=seed,
+                            x=x.numpy(), y=y.numpy())
+        yo = O.pix_shuffle_forward(sd, spec, x)
+        print(f"pix_shuffle {name}: oracle-vs-reference max|d| = {(y - yo).abs().max().item():.3e}")
+
+    # ---- conv3 / conv5 (model_conv3.py:102-155, model_conv5.py:114-151) ----
+    for preset in ("lightweight", "heavyweight"):
+        seed = 31 if preset == "lightweight" else 32
+        sd = O.make_bn_state_dict(O.conv3_channels(preset), seed)
+        m = mc3.get_model(preset).eval()
+        m.load_state_dict(sd, strict=True)
+        xu = torch.randint(0, 256, (2, 4, 36, 52), generator=g, dtype=torch.uint8)
+        with torch.no_grad():
+            y = m(xu)
+        np.savez_compressed(os.path.join(GOLD, f"conv3_{preset}.npz"), seed=seed, x=xu.numpy(), y=y.numpy())
+        print(f"conv3 {preset}: max|d| = {(y - O.conv3_forward(sd, xu)).abs().max().item():.3e}")
+
+        seed += 10
+        sd = O.make_bn_state_dict(O.conv5_channels(preset), seed)
+        m = mc5.get_model(preset).eval()
+        m.load_state_dict(sd, strict=True)
+        x = torch.rand((2, 3, 36, 52), generator=g)
+        with torch.no_grad():
+            y = m(x)
+        np.savez_compressed(os.path.join(GOLD, f"conv5_{preset}.npz"), seed=seed, x=x.numpy(), y=y.numpy())
+        print(f"conv5 {preset}: max|d| = {(y - O.conv5_forward(sd, x)).abs().max().item():.3e}")
+
+    # ---- gamma (gamma.py:13-15, 31-33) ----
+    t = torch.linspace(0, 1.3, 257)
+    np.savez_compressed(os.path.join(GOLD, "gamma.npz"), t=t.numpy(),
+                        to_linear=gamma.srgb_to_linear_approx(t).numpy(),
+                        to_srgb=gamma.linear_to_srgb_approx(t).numpy())
+
+    # ---- trained weights + the reference's own regression artefacts ----
+    sd = onnx_weights.pix_shuffle_state_dict_from_onnx(os.path.join(REF, "model/model_pix_shuffle/pix_shuffle.onnx"))
+    np.savez_compressed(os.path.join(GOLD, "pix_shuffle_trained_fp16.npz"),
+                        **{k: v.numpy().astype(np.float16) for k, v in sd.items()})
+    for preset, d in (("lightweight", "model_conv3"),):
+        sd3 = onnx_weights.conv3_state_dict_from_onnx(os.path.join(REF, f"model/{d}/conv3.onnx"))
+        np.savez_compressed(os.path.join(GOLD, "conv3_trained_fp16.npz"),
+                            **{k: (v.numpy().astype(np.float16) if v.dtype.is_floating_point else v.numpy())
+                               for k, v in sd3.items()})
+    os.makedirs(os.path.join(GOLD, "samples"))
+    os.makedirs(os.path.join(GOLD, "predicted_pix_shuffle"))
+    os.makedirs(os.path.join(GOLD, "predicted_conv3"))
+    for i in (1, 5, 6):   # three of the eight screenshots keep the fixture set small
+        shutil.copy(os.path.join(REF, f"model/samples/sample{i}.png"), os.path.join(GOLD, "samples"))
+        shutil.copy(os.path.join(REF, f"model/model_pix_shuffle/predicted/sample{i}.png"),
+                    os.path.join(GOLD, "predicted_pix_shuffle"))
+        shutil.copy(os.path.join(REF, f"model/model_conv3/predicted/sample{i}.png"),
+                    os.path.join(GOLD, "predicted_conv3"))
+    for root, _, files in os.walk(GOLD):
+        for f in files:
+            os.chmod(os.path.join(root, f), 0o644)
+    print("golden vectors written to", GOLD)
+
+
+if __name__ == "__main__":
+    main()

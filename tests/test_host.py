@@ -1,0 +1,178 @@
+"""CPU: host-side logic -- the C-ABI library loads and exports what include/fsuae_enhancer.h
+declares, descriptors / state_dict keys / error behaviour mirror the reference."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import enhancer_oracle as O
+from tests.util import build_pkg_pix_shuffle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from fs_uae_image_enhancer_project_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "fsuae_enhancer.h")).read()
+    declared = set(re.findall(r"FSUAE_API\s+[\w\s\*]+?\b(fsuae_\w+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), (declared, set(_lib.EXPORTS))
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.fsuae_abi_version() == _lib.ABI_VERSION
+
+
+def test_struct_layout_matches_header():
+    from fs_uae_image_enhancer_project_b200 import _lib
+    assert ctypes.sizeof(_lib.ActDesc) == 20
+    assert ctypes.sizeof(_lib.LayerDesc) == 40 + 8 * 20
+    assert ctypes.sizeof(_lib.NetDesc) == 16 + 16 * ctypes.sizeof(_lib.LayerDesc)
+
+
+def test_create_without_gpu_fails_loudly():
+    """No CPU fallback: on a box without a GPU the engine refuses to exist."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from fs_uae_image_enhancer_project_b200 import _lib, model_pix_shuffle
+    from fs_uae_image_enhancer_project_b200.descriptor import build_descriptor
+    from fs_uae_image_enhancer_project_b200.engine import Engine
+    m = model_pix_shuffle.get_model("lightweight")
+    desc, blob = build_descriptor(m._layer_specs(), m._head, m._tail)
+    with pytest.raises(_lib.EngineError) as ei:
+        Engine(desc, blob, 0, _lib.PREC_FP32, 576, 752)
+    assert ei.value.code == _lib.ERR_NO_DEVICE
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 8, 8))
+
+
+def test_invalid_descriptor_is_rejected_before_touching_the_gpu():
+    from fs_uae_image_enhancer_project_b200 import _lib, model_pix_shuffle
+    from fs_uae_image_enhancer_project_b200.descriptor import build_descriptor
+    from fs_uae_image_enhancer_project_b200.engine import Engine
+    m = model_pix_shuffle.get_model("lightweight")
+    desc, blob = build_descriptor(m._layer_specs(), m._head, m._tail)
+    with pytest.raises(ValueError, match="even"):
+        Engine(desc, blob, 0, _lib.PREC_FP32, 575, 752)
+    desc.layers[2].cin0 = 35
+    with pytest.raises(ValueError, match="src0"):
+        Engine(desc, blob, 0, _lib.PREC_FP32, 576, 752)
+
+
+@pytest.mark.parametrize("preset", ["lightweight", "heavyweight"])
+def test_pix_shuffle_state_dict_keys_match_reference(preset):
+    from fs_uae_image_enhancer_project_b200 import model_pix_shuffle
+    m = model_pix_shuffle.get_model(preset)
+    spec = O.pix_shuffle_preset(preset)
+    sd = O.make_pix_shuffle_state_dict(spec, 1)       # key set == reference state_dict (checked in gen_golden)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
+    assert sum(p.numel() for p in m.parameters()) == {"lightweight": 136602, "heavyweight": 218105}[preset]
+    assert model_pix_shuffle.get_model("nope") is None
+
+
+def test_conv3_conv5_state_dict_keys_and_param_counts():
+    from fs_uae_image_enhancer_project_b200 import model_conv3, model_conv5
+    for mod, chans, counts in ((model_conv3, O.conv3_channels, (21222, 455366)),
+                               (model_conv5, O.conv5_channels, (67494, 264006))):
+        for preset, want in zip(("lightweight", "heavyweight"), counts):
+            m = mod.get_model(preset)
+            sd = O.make_bn_state_dict(chans(preset), 1)
+            assert set(m.state_dict()) == set(sd)
+            assert sum(p.numel() for p in m.parameters()) == want   # incl. BN affine
+
+
+def test_descriptor_contents_lightweight():
+    from fs_uae_image_enhancer_project_b200 import _lib
+    from fs_uae_image_enhancer_project_b200.descriptor import build_descriptor
+    spec = O.pix_shuffle_preset("lightweight")
+    sd = O.make_pix_shuffle_state_dict(spec, 4)
+    m = build_pkg_pix_shuffle(spec, sd)
+    d, blob = build_descriptor(m._layer_specs(), m._head, m._tail)
+    assert d.n_layers == 7 and d.head == _lib.HEAD_UNSHUFFLE2 and d.tail == _lib.TAIL_SHUFFLE2_RESIDUAL_RELU
+    L = d.layers
+    assert [(L[i].cin0, L[i].cin1, L[i].cout) for i in range(7)] == \
+        [(12, 0, 36), (36, 0, 36), (36, 0, 72), (72, 0, 72), (72, 0, 36), (36, 36, 36), (36, 0, 12)]
+    assert [L[i].skip_src for i in range(7)] == [-1, 1, -1, 3, -1, -1, -1]
+    assert (L[5].src0, L[5].src1) == (1, 5)
+    # identity slots are dropped; l2: telu | sinlu, biased_prelu ; l4: mish, biased_prelu | tanh, relu
+    assert [L[1].pre[0].op, L[1].post[0].op, L[1].post[1].op] == [_lib.ACT["telu"], _lib.ACT["sinlu"], _lib.ACT["biased_prelu"]]
+    assert (L[1].n_pre, L[1].n_post, L[3].n_pre, L[3].n_post, L[2].n_pre, L[6].n_pre) == (1, 2, 2, 2, 0, 1)
+    w4 = blob[L[3].w_off:L[3].w_off + 72 * 72 * 9].reshape(72, 72, 3, 3)
+    assert np.array_equal(w4, sd["conv4.weight"].numpy())
+    a = L[3].pre[1]
+    assert a.n0 == 72 and a.n1 == 72
+    assert np.array_equal(blob[a.p0_off:a.p0_off + 72], sd["l4_act2.bias"].numpy())
+    assert np.array_equal(blob[a.p1_off:a.p1_off + 72], sd["l4_act2.prelu.weight"].numpy())
+    assert L[6].pre[0].n0 == 1 and blob[L[6].pre[0].p0_off] == sd["l7_act2.bias"].item()
+
+
+def test_batchnorm_folding_matches_eval_batchnorm():
+    from fs_uae_image_enhancer_project_b200 import model_conv3
+    from fs_uae_image_enhancer_project_b200.descriptor import build_descriptor
+    m = model_conv3.get_model("lightweight")
+    sd = O.make_bn_state_dict(O.conv3_channels("lightweight"), 9)
+    m.load_state_dict(sd)
+    d, blob = build_descriptor(m._layer_specs(), m._head, m._tail)
+    x = torch.rand(1, 3, 12, 12)
+    w = torch.from_numpy(blob[d.layers[0].w_off:d.layers[0].w_off + 32 * 27].reshape(32, 3, 3, 3))
+    b = torch.from_numpy(blob[d.layers[0].b_off:d.layers[0].b_off + 32])
+    folded = torch.nn.functional.conv2d(x, w, b, padding=1)
+    want = O._bn(sd, 1, torch.nn.functional.conv2d(x, sd["conv1.weight"], None, padding=1), torch.float32)
+    assert (folded - want).abs().max() < 1e-5
+
+
+def test_activation_factory_error_behaviour():
+    from fs_uae_image_enhancer_project_b200 import activations
+    with pytest.raises(ValueError, match="Unsupported activation"):
+        activations.get_activation("nonsense")
+    with pytest.raises(TypeError):
+        activations.get_activation("relu", params={"negative_slope": 0.1})
+    assert activations.get_activation("SoftMax").dim == 1
+    assert activations.get_activation("swish").op_name == "silu"
+    assert set(activations.ACTIVATION_REGISTRY) == set(O.ACTIVATION_NAMES)
+    bp = activations.get_activation("biased_prelu", {"num_parameters": 5})
+    assert set(dict(bp.named_parameters())) == {"bias", "prelu.weight"}
+    assert float(bp.bias.abs().max()) <= 0.1 and float(bp.prelu.weight[0]) == 0.25
+    with pytest.raises(RuntimeError):
+        bp(torch.zeros(1, 5, 2, 2))
+
+
+def test_model_constructor_errors():
+    from fs_uae_image_enhancer_project_b200 import model_conv3, model_pix_shuffle
+    with pytest.raises(ValueError, match="odd"):
+        model_pix_shuffle.Model(layer3_kernel_size=4)
+    with pytest.raises(ValueError, match="odd"):
+        model_conv3.Model(kernel_size=2)
+    with pytest.raises(ValueError):
+        model_pix_shuffle.Model(layer1_out_channels=24, layer2_out_channels=36)   # skip projection
+    with pytest.raises(ValueError, match="Unsupported activation"):
+        model_pix_shuffle.Model(layer1_act1="nonsense")
+
+
+def test_onnx_wire_reader_roundtrip(tmp_path):
+    """The hand-rolled protobuf reader on a hand-assembled ModelProto{graph{initializer, node}}."""
+    from fs_uae_image_enhancer_project_b200 import onnx_weights as ow
+
+    def varint(n):
+        out = b""
+        while True:
+            b = n & 0x7F
+            n >>= 7
+            out += bytes([b | (0x80 if n else 0)])
+            if not n:
+                return out
+
+    def ld(fno, payload):
+        return varint((fno << 3) | 2) + varint(len(payload)) + payload
+
+    arr = np.arange(6, dtype=np.float16).reshape(2, 3)
+    tensor = varint(1 << 3) + varint(2) + varint(1 << 3) + varint(3) + varint(2 << 3) + varint(10) \
+        + ld(8, b"conv1.bias") + ld(9, arr.tobytes())
+    node = ld(1, b"x") + ld(1, b"conv1.bias") + ld(2, b"y") + ld(4, b"PRelu")
+    model = ld(7, ld(1, node) + ld(5, tensor))
+    p = tmp_path / "m.onnx"
+    p.write_bytes(model)
+    inits, nodes = ow.read_onnx_initializers(str(p))
+    assert np.array_equal(inits["conv1.bias"], arr) and nodes == [("PRelu", ["x", "conv1.bias"], ["y"])]

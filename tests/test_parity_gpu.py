@@ -1,0 +1,177 @@
+"""GPU: the engine (through the drop-in modules -> ctypes -> C ABI -> CUDA) against the oracle on the
+same seeded inputs, against the committed reference vectors, and -- at full 752x576 size -- through
+size-independent properties.  Tolerances are SURVEY.md section 8d / BASELINE.md section 4."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import enhancer_oracle as O
+from tests.util import (GOLD, build_pkg_pix_shuffle, gold_spec, load_gold, load_png_rgb, load_png_rgba,
+                        trained_conv3_sd, trained_pix_shuffle_sd)
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5          # fp32 build vs fp32 oracle, float output in [0,~1.2]
+FP32_TOL_255 = 2e-3      # conv3 output scale 0..255
+BF16_TOL = 1e-2          # bf16 build max-abs
+BF16_PSNR = 55.0         # bf16 build PSNR (peak 1.0)
+
+
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    return torch.device("cuda", 0)
+
+
+def test_native_library_is_what_runs():
+    from fs_uae_image_enhancer_project_b200 import _lib
+    spec = O.pix_shuffle_preset("lightweight")
+    m = build_pkg_pix_shuffle(spec, O.make_pix_shuffle_state_dict(spec, 1)).to(dev())
+    y = m(torch.rand(1, 3, 16, 16, device=dev()))
+    assert y.shape == (1, 3, 16, 16)
+    eng = m.engine_for(dev(), 16, 16)
+    assert eng.variant == "fp32_fma" and eng.last_launch_count >= 9
+    assert any("libfsuae_enhancer.so" in l for l in open("/proc/self/maps"))
+
+
+@pytest.mark.parametrize("name", ["lightweight", "heavyweight", "vocab_a", "vocab_b"])
+def test_fp32_pix_shuffle_matches_reference_vectors(name):
+    g = load_gold(f"pix_shuffle_{name}")
+    spec = gold_spec(name)
+    sd = O.make_pix_shuffle_state_dict(spec, int(g["seed"]))
+    m = build_pkg_pix_shuffle(spec, sd).to(dev())
+    y = m(torch.from_numpy(g["x"]).to(dev())).cpu().numpy()
+    assert np.abs(y - g["y"]).max() <= FP32_TOL
+
+
+@pytest.mark.parametrize("preset", ["lightweight", "heavyweight"])
+def test_fp32_conv3_conv5_match_reference_vectors(preset):
+    from fs_uae_image_enhancer_project_b200 import model_conv3, model_conv5
+    g = load_gold(f"conv3_{preset}")
+    m = model_conv3.get_model(preset)
+    m.load_state_dict(O.make_bn_state_dict(O.conv3_channels(preset), int(g["seed"])))
+    y = m.to(dev())(torch.from_numpy(g["x"]).to(dev())).cpu().numpy()
+    assert y.shape == g["y"].shape and np.abs(y - g["y"]).max() <= FP32_TOL_255
+    assert (y[:, 3] == 255.0).all()
+    g = load_gold(f"conv5_{preset}")
+    m = model_conv5.get_model(preset)
+    m.load_state_dict(O.make_bn_state_dict(O.conv5_channels(preset), int(g["seed"])))
+    y = m.to(dev())(torch.from_numpy(g["x"]).to(dev())).cpu().numpy()
+    assert np.abs(y - g["y"]).max() <= FP32_TOL
+
+
+@pytest.mark.parametrize("shape", [(1, 2, 2), (1, 2, 66), (3, 34, 2), (2, 18, 70), (1, 64, 96), (5, 6, 130)])
+def test_fp32_edge_shapes_and_borders(shape):
+    """Tiny / ragged frames: every pixel is a border pixel somewhere; zero padding is per layer."""
+    B, H, W = shape
+    spec = O.pix_shuffle_preset("lightweight")
+    sd = O.make_pix_shuffle_state_dict(spec, 21)
+    x = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(H * W))
+    want = O.pix_shuffle_forward(sd, spec, x)
+    got = build_pkg_pix_shuffle(spec, sd).to(dev())(x.to(dev())).cpu()
+    assert (got - want).abs().max().item() <= FP32_TOL
+
+
+def test_fp32_batch_larger_than_chunk_and_empty_batch():
+    spec = O.pix_shuffle_preset("lightweight")
+    sd = O.make_pix_shuffle_state_dict(spec, 22)
+    m = build_pkg_pix_shuffle(spec, sd).to(dev())
+    m.chunk_frames = 3
+    x = torch.rand(8, 3, 20, 28, generator=torch.Generator().manual_seed(3))
+    got = m(x.to(dev())).cpu()
+    assert (got - O.pix_shuffle_forward(sd, spec, x)).abs().max().item() <= FP32_TOL
+    assert m(torch.zeros(0, 3, 20, 28, device=dev())).shape == (0, 3, 20, 28)
+
+
+def test_forward_is_stateless_and_rebuilds_after_load_state_dict():
+    spec = O.pix_shuffle_preset("lightweight")
+    sd1, sd2 = O.make_pix_shuffle_state_dict(spec, 1), O.make_pix_shuffle_state_dict(spec, 2)
+    m = build_pkg_pix_shuffle(spec, sd1).to(dev())
+    x = torch.rand(1, 3, 24, 24, generator=torch.Generator().manual_seed(9))
+    a = m(x.to(dev())).cpu()
+    b = m(x.to(dev())).cpu()
+    assert torch.equal(a, b)
+    m.load_state_dict(sd2)
+    c = m(x.to(dev())).cpu()
+    assert (c - O.pix_shuffle_forward(sd2, spec, x)).abs().max().item() <= FP32_TOL
+    assert (c - a).abs().max().item() > 1e-3
+
+
+def test_error_behaviour_on_gpu():
+    from fs_uae_image_enhancer_project_b200 import model_conv3
+    spec = O.pix_shuffle_preset("lightweight")
+    m = build_pkg_pix_shuffle(spec, O.make_pix_shuffle_state_dict(spec, 1)).to(dev())
+    with pytest.raises(ValueError, match="even"):
+        m(torch.zeros(1, 3, 15, 16, device=dev()))
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 4, 16, 16, device=dev()))
+    m3 = model_conv3.get_model("lightweight").to(dev())
+    with pytest.raises(ValueError, match="uint8"):
+        m3(torch.zeros(1, 3, 16, 16, device=dev()))
+
+
+@pytest.mark.parametrize("crop16", [False, True])
+def test_fp32_framebuffer_contract_full_size(crop16):
+    """Deployed uint8 RGBA contract at 752x576 on mixed pixel-mode RGB444 frames: <= 1 LSB."""
+    spec = O.pix_shuffle_preset("lightweight")
+    sd = O.make_pix_shuffle_state_dict(spec, 31)
+    fb = O.synth_framebuffers(4, seed=8)
+    want = O.framebuffer_forward(sd, spec, fb, crop16=crop16)
+    m = build_pkg_pix_shuffle(spec, sd).to(dev())
+    got = m.forward_framebuffer(fb.to(dev()), crop16=crop16).cpu()
+    d = (got.int() - want.int()).abs()
+    assert d.max().item() <= 1 and (d == 0).float().mean().item() >= 0.999
+    assert (got[..., 3] == 255).all()
+    if crop16:
+        assert (got[:, :, :16, :3] == 0).all()
+    # host-buffer entry point gives the identical bytes
+    host = m.run_host(fb.pin_memory(), crop16=crop16)
+    assert torch.equal(host, got)
+
+
+@pytest.mark.parametrize("i", [1, 5, 6])
+def test_fp32_trained_weights_reproduce_shipped_screenshots(i):
+    sd = trained_pix_shuffle_sd()
+    spec = O.pix_shuffle_preset("lightweight")
+    m = build_pkg_pix_shuffle(spec, sd).to(dev())
+    rgba = load_png_rgba(os.path.join(GOLD, "samples", f"sample{i}.png"))
+    want = load_png_rgb(os.path.join(GOLD, "predicted_pix_shuffle", f"sample{i}.png"))
+    got = m.forward_framebuffer(rgba.to(dev())).cpu()[..., :3].permute(0, 3, 1, 2)
+    assert O.psnr(got, want, 255.0) >= 60.0
+    assert (got.int() - want.int()).abs().max().item() <= 4
+
+
+def test_fp32_trained_conv3_reproduces_shipped_screenshots():
+    from fs_uae_image_enhancer_project_b200 import model_conv3
+    m = model_conv3.get_model("lightweight")
+    m.load_state_dict(trained_conv3_sd())
+    m = m.to(dev())
+    x = load_png_rgba(os.path.join(GOLD, "samples", "sample5.png")).permute(0, 3, 1, 2).contiguous()
+    want = load_png_rgba(os.path.join(GOLD, "predicted_conv3", "sample5.png")).permute(0, 3, 1, 2)
+    got = m(x.to(dev())).cpu().clamp(0, 255).to(torch.uint8)
+    assert (got.int() - want.int()).abs().max().item() <= 1
+
+
+def test_fp32_full_size_properties():
+    """752x576: (a) frames are independent -- a batch equals its frames run one by one, in any
+    order; (b) translation equivariance away from the border: shifting the input by (2,2) full-res
+    pixels shifts the interior of the output; (c) output >= 0 (final ReLU)."""
+    spec = O.pix_shuffle_preset("lightweight")
+    sd = O.make_pix_shuffle_state_dict(spec, 41)
+    m = build_pkg_pix_shuffle(spec, sd).to(dev())
+    x = torch.rand(3, 3, 576, 752, generator=torch.Generator().manual_seed(1)).to(dev())
+    y = m(x)
+    assert (y >= 0).all()
+    y_rev = m(x.flip(0).contiguous()).flip(0)
+    assert torch.equal(y, y_rev)
+    y1 = m(x[1:2].contiguous())
+    assert torch.equal(y[1:2], y1)
+    xs = torch.roll(x[:1], shifts=(2, 2), dims=(2, 3)).contiguous()
+    ys = m(xs)
+    a = ys[:, :, 32:-32, 32:-32]
+    b = torch.roll(y[:1], shifts=(2, 2), dims=(2, 3))[:, :, 32:-32, 32:-32]
+    assert (a - b).abs().max().item() <= 1e-6
+    # spot-check against the oracle on one full-size frame
+    want = O.pix_shuffle_forward(sd, spec, x[:1].cpu())
+    assert (y[:1].cpu() - want).abs().max().item() <= FP32_TOL
