@@ -85,6 +85,8 @@ class FusedEnhancer(nn.Module):
         xf = x.contiguous() if x.dtype == torch.float32 else x.float().contiguous()
         B, _, H, W = xf.shape
         out = torch.empty((B, out_channels, H, W), dtype=torch.float32, device=x.device)
+        if B == 0:
+            return out.to(in_dtype)
         self.engine_for(x.device, H, W).enqueue(xf, out, B, L.FMT_F32_NCHW3, out_fmt)
         return out if in_dtype == torch.float32 else out.to(in_dtype)
 
@@ -98,6 +100,8 @@ class FusedEnhancer(nn.Module):
         rgba = rgba.contiguous()
         B, H, W, _ = rgba.shape
         out = torch.empty_like(rgba)
+        if B == 0:
+            return out
         flags = (L.FLAG_GAMMA_IN | L.FLAG_GAMMA_OUT if gamma else 0) | (L.FLAG_CROP16 if crop16 else 0)
         self.engine_for(rgba.device, H, W).enqueue(rgba, out, B, L.FMT_U8_NHWC4, L.FMT_U8_NHWC4, flags)
         return out

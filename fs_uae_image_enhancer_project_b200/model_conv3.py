@@ -50,7 +50,8 @@ class Model(FusedEnhancer):
         x = x.contiguous()
         B, _, H, W = x.shape
         out = torch.empty((B, 4, H, W), dtype=torch.float32, device=x.device)
-        self.engine_for(x.device, H, W).enqueue(x, out, B, L.FMT_U8_NCHW4, L.FMT_F32_NCHW4)
+        if B > 0:
+            self.engine_for(x.device, H, W).enqueue(x, out, B, L.FMT_U8_NCHW4, L.FMT_F32_NCHW4)
         p = next(self.parameters())
         return out if p.dtype == torch.float32 else out.to(p.dtype)
 
