@@ -1,10 +1,722 @@
-// bf16 tcgen05 build (placeholder until the tensor-core path lands).
+// bf16 build: every 3x3 convolution runs as an implicit GEMM on the 5th-gen tensor cores
+// (tcgen05.mma, kind::f16, bf16 operands, fp32 accumulators in TMEM) with the layer's whole
+// epilogue fused behind the accumulator read-back (tcgen05.ld).
+//
+// Data layout ("chunk-planar"): an activation map with C channels is ceil(C/8) planes; a plane is
+// (Hw+2) rows x PW slots of 16 bytes (8 bf16 channels of one pixel), with a zero border of one
+// pixel baked in (row 0, row Hw+1, column 0, columns > Ww) so the per-layer zero padding of
+// nn.Conv2d(padding=1) needs no special case anywhere: borders are never written.
+//
+// Implicit GEMM: M = 128 consecutive pixels of one image row (a "strip row": 126 valid outputs +
+// 2 discarded), N = Cout padded to 16, K = 16 per instruction.  A strip row of every input plane
+// is one contiguous 2 KB run in global memory, brought into a shared-memory ring by TMA bulk
+// copies; in the no-swizzle K-major canonical layout one plane row IS a valid A operand
+// (core matrix = 8 pixels x 16 B), and a 3x3 tap is nothing but a different start address
+// (row slot +/- 1, +/- 16 bytes) -- no im2col, no data movement.  The two 8-channel halves of one
+// K=16 instruction are any two (tap, channel-chunk) units; their distance is the descriptor's LBO.
+// Weights for the whole layer stay resident in shared memory, pre-packed per instruction.
+//
+// Warp roles (192 threads, one persistent CTA per SM): warp 0 = TMA producer, warp 1 = MMA issuer
+// (one elected lane), warps 2-5 = epilogue (thread = pixel, TMEM lane = pixel).
+//
+// Reference semantics: model/model_pix_shuffle.py:227-298 (and activations.py for the slots).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
 #include "engine.h"
+#include "tc_ptx.cuh"
 
 namespace fsuae {
-int bf16_create(fsuae_engine* e) { return set_error(e, FSUAE_ERR_UNSUPPORTED, "bf16 build not implemented yet"); }
-void bf16_destroy(fsuae_engine*) {}
-int bf16_enqueue_chunk(fsuae_engine* e, const void*, void*, int, int, int, uint32_t, cudaStream_t) {
-  return set_error(e, FSUAE_ERR_UNSUPPORTED, "bf16 build not implemented yet");
+
+namespace {
+
+using namespace tc;
+
+constexpr int MAXC = 112;
+constexpr int STRIP = 126;            // valid output columns per strip row
+constexpr int MROWS = 128;            // MMA M = slots per strip row
+constexpr int PLANE_ROW = MROWS * 16; // bytes of one plane of one strip row
+constexpr int SMEM_LIMIT = 232448 - 2048;
+constexpr int NTHREADS = 192;
+
+enum { EPI_STORE = 0, EPI_TAIL_SHUFFLE = 1 };
+
+struct LayerK {
+  int Hw, Ww, PW, S, RB, n_frames, rb_per_strip, n_items;
+  int P0, P1, cout;
+  unsigned long long fs0, fs1, fs_skip, fs_dst;  // frame strides in bytes
+  const unsigned char* src0;
+  const unsigned char* src1;
+  const unsigned char* skip;
+  unsigned char* dst;
+  const unsigned char* wpack;
+  // tail (EPI_TAIL_SHUFFLE)
+  const void* frame_in;
+  void* frame_out;
+  int in_fmt, out_fmt, H, W, xoff, gamma_in, gamma_out;
+  // epilogue parameters, expanded per channel on the host
+  int n_pre, n_post;
+  int op[4];               // pre0, pre1, post0, post1 (identity-padded)
+  float bias[MAXC];
+  float p0[4][MAXC];
+  float p1[4][MAXC];
+};
+
+template <int PT, int NPAD>
+struct Cfg {
+  static constexpr int UNITS_ROW = 3 * PT;                 // (chunk, dx) units of one input row
+  static constexpr int STEPS_ROW = (UNITS_ROW + 1) / 2;    // K=16 instructions per input row
+  static constexpr int STEPS = 3 * STEPS_ROW;
+  static constexpr int WBYTES = STEPS * NPAD * 32;
+  static constexpr int ROWBYTES = PT * PLANE_ROW;
+  static constexpr int RING_FIT = (SMEM_LIMIT - WBYTES - 64 - 512) / ROWBYTES;
+  static constexpr int RING = RING_FIT > 10 ? 10 : RING_FIT;
+  static constexpr int STAGES = (512 / NPAD) > 4 ? 4 : (512 / NPAD);
+  static constexpr int BAR_OFF = WBYTES + RING * ROWBYTES + 64;
+  static constexpr int SMEM = BAR_OFF + 512;
+  static_assert(RING >= 4, "layer does not fit: weights + 4 ring rows exceed shared memory");
+  static_assert(STAGES >= 2, "need two accumulator stages");
+};
+
+// ---- fast activation math for the bf16 build (error well below bf16 resolution) ----------------
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(tanh_fast(0.5f * x), 0.5f, 0.5f); }
+
+__device__ __forceinline__ float act_rt(int op, float x, float p0, float p1) {
+  switch (op) {
+    case FSUAE_ACT_IDENTITY: return x;
+    case FSUAE_ACT_RELU: return fmaxf(x, 0.f);
+    case FSUAE_ACT_RELU6: return fminf(fmaxf(x, 0.f), 6.f);
+    case FSUAE_ACT_TANH: return tanh_fast(x);
+    case FSUAE_ACT_SIGMOID: return sigmoid_fast(x);
+    case FSUAE_ACT_SILU: return x * sigmoid_fast(x);
+    case FSUAE_ACT_MISH: {   // x * tanh(softplus(x)) = x * w / (w + 2), w = e^x (e^x + 2)
+      float n = __expf(fminf(x, 20.f));
+      float w = n * (n + 2.f);
+      return x * __fdividef(w, w + 2.f);
+    }
+    case FSUAE_ACT_GELU: return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+    case FSUAE_ACT_ELU: return x > 0.f ? x : p0 * (__expf(x) - 1.f);
+    case FSUAE_ACT_SOFTPLUS: {
+      float bx = x * p0;
+      return bx > p1 ? x : __fdividef(__logf(1.f + __expf(bx)), p0);
+    }
+    case FSUAE_ACT_LEAKY_RELU: return x >= 0.f ? x : p0 * x;
+    case FSUAE_ACT_PRELU: return x >= 0.f ? x : p0 * x;
+    case FSUAE_ACT_SCALED_TANH: return fmaf(tanh_fast(x), 0.5f, 0.5f);
+    case FSUAE_ACT_TELU: return x * tanh_fast(__expf(x));
+    case FSUAE_ACT_SINLU: return sigmoid_fast(x) * fmaf(p0, __sinf(p1 * x), x);
+    case FSUAE_ACT_BIASED_RELU: return fmaxf(x - p0, 0.f);
+    case FSUAE_ACT_BIASED_PRELU: {
+      float y = x - p0;
+      return y >= 0.f ? y : p1 * y;
+    }
+    default: return x;
+  }
+}
+
+// OP >= 0: compile-time op (the switch folds away); OP < 0: op-code read from the layer parameters
+template <int OP>
+__device__ __forceinline__ float act_slot(const LayerK& P, int slot, int ch, float x) {
+  if constexpr (OP == FSUAE_ACT_IDENTITY) return x;
+  else if constexpr (OP >= 0) return act_rt(OP, x, P.p0[slot][ch], P.p1[slot][ch]);
+  else return act_rt(P.op[slot], x, P.p0[slot][ch], P.p1[slot][ch]);
+}
+
+template <int PRE0, int PRE1, int POST0, int POST1, bool SKIP>
+struct Epi {
+  static constexpr bool kSkip = SKIP;
+  __device__ static __forceinline__ float pre(const LayerK& P, int ch, float v) {
+    v = act_slot<PRE0>(P, 0, ch, v);
+    return act_slot<PRE1>(P, 1, ch, v);
+  }
+  __device__ static __forceinline__ float post(const LayerK& P, int ch, float v) {
+    v = act_slot<POST0>(P, 2, ch, v);
+    return act_slot<POST1>(P, 3, ch, v);
+  }
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+__device__ __forceinline__ uint8_t to_u8_fast(float v, int gamma_out) {
+  if (gamma_out) v = __powf(fmaxf(v, 0.f), 1.0f / 2.2f);
+  v = fminf(fmaxf(v, 0.f), 1.f) * 255.0f;
+  return (uint8_t)v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the layer kernel
+// ------------------------------------------------------------------------------------------------
+template <int PT, int NPAD, int OUT_PLANES, int KIND, class EPI>
+__global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_constant__ LayerK P) {
+  using C = Cfg<PT, NPAD>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* s_w = smem;
+  uint8_t* s_ring = smem + C::WBYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
+  uint64_t* full = bars;                       // [RING]  TMA -> MMA
+  uint64_t* empty = bars + C::RING;            // [RING]  MMA -> TMA
+  uint64_t* tfull = bars + 2 * C::RING;        // [STAGES] MMA -> epilogue
+  uint64_t* tempty = tfull + C::STAGES;        // [STAGES] epilogue -> MMA
+  uint64_t* wbar = tempty + C::STAGES;         // weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+  __shared__ float s_lut[256];
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C::RING; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < C::STAGES; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    mbar_init(wbar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + 16) {   // zero the 64-byte overrun pad behind the ring
+    reinterpret_cast<uint32_t*>(s_ring + C::RING * C::ROWBYTES)[threadIdx.x - 64] = 0u;
+  }
+  if constexpr (KIND == EPI_TAIL_SHUFFLE) {
+    for (int i = threadIdx.x; i < 256; i += NTHREADS) {
+      float t = (float)i * (1.0f / 255.0f);
+      s_lut[i] = P.gamma_in ? powf(t, 2.2f) : t;
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const size_t row_pitch = (size_t)P.PW * 16;                  // bytes of one padded image row of one plane
+  const size_t plane_pitch = (size_t)(P.Hw + 2) * row_pitch;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (elect_one()) {
+      mbar_arrive_expect_tx(wbar, C::WBYTES);
+      tma_load_1d(s_w, P.wpack, C::WBYTES, wbar);
+      uint32_t slot = 0, par = 1;   // waiting on parity 1 of a fresh barrier passes immediately
+      for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+        const int f = item / (P.S * P.rb_per_strip);
+        const int r = item - f * (P.S * P.rb_per_strip);
+        const int s = r / P.rb_per_strip;
+        const int y0 = (r - s * P.rb_per_strip) * P.RB;
+        const int rows = min(P.RB, P.Hw - y0);
+        const unsigned char* g0 = P.src0 + (size_t)f * P.fs0 + (size_t)y0 * row_pitch + (size_t)s * STRIP * 16;
+        const unsigned char* g1 = P.P1 ? P.src1 + (size_t)f * P.fs1 + (size_t)y0 * row_pitch + (size_t)s * STRIP * 16 : nullptr;
+        for (int k = 0; k < rows + 2; ++k) {          // padded rows y0 .. y0+rows+1
+          mbar_wait(&empty[slot], par);
+          mbar_arrive_expect_tx(&full[slot], C::ROWBYTES);
+          uint8_t* d = s_ring + slot * C::ROWBYTES;
+          for (int j = 0; j < P.P0; ++j)
+            tma_load_1d(d + j * PLANE_ROW, g0 + (size_t)j * plane_pitch + (size_t)k * row_pitch, PLANE_ROW, &full[slot]);
+          for (int j = 0; j < P.P1; ++j)
+            tma_load_1d(d + (P.P0 + j) * PLANE_ROW, g1 + (size_t)j * plane_pitch + (size_t)k * row_pitch, PLANE_ROW, &full[slot]);
+          if (++slot == C::RING) { slot = 0; par ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    if (elect_one()) {
+      constexpr uint32_t IDESC = umma_idesc_bf16(MROWS, NPAD);
+      const uint32_t ring_lo = (smem_u32(s_ring) & 0x3FFFFu) >> 4;
+      const uint32_t w_lo = ((smem_u32(s_w) & 0x3FFFFu) >> 4) | ((uint32_t)((NPAD * 16) >> 4) << 16);
+      constexpr uint32_t HI = (uint32_t)((128u >> 4)) | (1u << 14);   // SBO = 128 B, descriptor version 1
+      mbar_wait(wbar, 0);
+      uint32_t wslot = 0, wpar = 0;       // next ring slot to wait for
+      uint32_t stage = 0, spar = 1;       // accumulator stage / parity for tempty
+      for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+        const int r = item % (P.S * P.rb_per_strip);
+        const int y0 = (r % P.rb_per_strip) * P.RB;
+        const int rows = min(P.RB, P.Hw - y0);
+        uint32_t s0 = wslot;              // slot of the block's first input row
+        // first two rows of the item
+        for (int k = 0; k < 2; ++k) {
+          mbar_wait(&full[wslot], wpar);
+          if (++wslot == C::RING) { wslot = 0; wpar ^= 1; }
+        }
+        for (int b = 0; b < rows; ++b) {
+          mbar_wait(&full[wslot], wpar);
+          if (++wslot == C::RING) { wslot = 0; wpar ^= 1; }
+          mbar_wait(&tempty[stage], spar);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + stage * NPAD;
+          uint32_t rs = s0;
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            const uint32_t a_row = ring_lo + rs * (C::ROWBYTES >> 4);
+#pragma unroll
+            for (int st = 0; st < C::STEPS_ROW; ++st) {
+              // units (2 st, 2 st + 1) form one K=16 instruction.  A row has 3*PT units; when that is odd the
+              // last instruction carries unit 3*PT-1 in its SECOND half and re-reads unit 3*PT-2 (against
+              // zero weights) in its first half, so both halves always point at landed, finite data --
+              // anything else could turn never-written shared memory into 0 * NaN.
+              const int u = (2 * st + 1 < C::UNITS_ROW) ? 2 * st : 2 * st - 1;   // first unit: chunk u/3, tap dx = u%3
+              const uint32_t off = (uint32_t)((u / 3) * (PLANE_ROW >> 4) + (u % 3));
+              const uint32_t lbo = (u % 3) < 2 ? 1u : (uint32_t)((PLANE_ROW >> 4) - 2);
+              const uint64_t ad = ((uint64_t)HI << 32) | (uint64_t)((a_row + off) | (lbo << 16));
+              const uint64_t bd = ((uint64_t)HI << 32) | (uint64_t)(w_lo + (uint32_t)((dy * C::STEPS_ROW + st) * ((NPAD * 32) >> 4)));
+              umma_bf16(d_tmem, ad, bd, IDESC, (dy | st) != 0);
+            }
+            if (++rs == C::RING) rs = 0;
+          }
+          umma_commit(&tfull[stage]);
+          umma_commit(&empty[s0]);            // the block's first row is not needed again
+          if (b == rows - 1) {                // item done: release its last two rows as well
+            uint32_t s1 = s0 + 1 == C::RING ? 0 : s0 + 1;
+            uint32_t s2 = s1 + 1 == C::RING ? 0 : s1 + 1;
+            umma_commit(&empty[s1]);
+            umma_commit(&empty[s2]);
+          }
+          if (++s0 == C::RING) s0 = 0;
+          if (++stage == C::STAGES) { stage = 0; spar ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ======================= epilogue (warps 2..5) =======================
+    const int q = warp & 3;                    // TMEM lane quadrant this warp may access
+    const int m = q * 32 + lane;               // pixel index inside the strip row
+    uint32_t stage = 0, spar = 0;
+    for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+      const int f = item / (P.S * P.rb_per_strip);
+      const int r = item - f * (P.S * P.rb_per_strip);
+      const int s = r / P.rb_per_strip;
+      const int y0 = (r - s * P.rb_per_strip) * P.RB;
+      const int rows = min(P.RB, P.Hw - y0);
+      const int x = s * STRIP + m;
+      const bool valid = m < STRIP && x < P.Ww;
+      for (int b = 0; b < rows; ++b) {
+        const int y = y0 + b;
+        const size_t pix = (size_t)(y + 1) * row_pitch + (size_t)(x + 1) * 16;
+        uint4 sk[EPI::kSkip ? OUT_PLANES : 1];
+        if constexpr (EPI::kSkip) {
+          const unsigned char* sp = P.skip + (size_t)f * P.fs_skip + pix;
+#pragma unroll
+          for (int c = 0; c < OUT_PLANES; ++c)
+            sk[c] = valid ? __ldg(reinterpret_cast<const uint4*>(sp + (size_t)c * plane_pitch)) : make_uint4(0, 0, 0, 0);
+        }
+        mbar_wait(&tfull[stage], spar);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + stage * NPAD;
+
+        if constexpr (KIND == EPI_STORE) {
+          unsigned char* dp = P.dst + (size_t)f * P.fs_dst + pix;
+#pragma unroll
+          for (int c = 0; c < OUT_PLANES; ++c) {
+            uint32_t v[8];
+            tmem_ld_x8(taddr + c * 8, v);
+            tmem_ld_wait();
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int ch = c * 8 + i;
+              float t = EPI::pre(P, ch, __uint_as_float(v[i]) + P.bias[ch]);
+              if constexpr (EPI::kSkip) {
+                const uint32_t w = (&sk[c].x)[i >> 1];
+                t += (i & 1) ? bf16_hi(w) : bf16_lo(w);
+              }
+              t = EPI::post(P, ch, t);
+              o[i] = ch < P.cout ? t : 0.f;     // padding channels stay exactly zero
+            }
+            if (valid) {
+              uint4 pk = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                                    pack_bf16x2(o[6], o[7]));
+              *reinterpret_cast<uint4*>(dp + (size_t)c * plane_pitch) = pk;
+            }
+          }
+        } else {
+          // PixelShuffle(2) + input residual + ReLU, straight to the output frame
+          uint32_t v[16];
+          tmem_ld_x16(taddr, v);
+          tmem_ld_wait();
+          float o[12];
+#pragma unroll
+          for (int ch = 0; ch < 12; ++ch) {
+            float t = EPI::pre(P, ch, __uint_as_float(v[ch]) + P.bias[ch]);
+            o[ch] = EPI::post(P, ch, t);
+          }
+          if (valid) {
+            const size_t fpl = (size_t)P.H * P.W;
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+              const int Y = 2 * y + dy, X = 2 * x + P.xoff;
+              const size_t p0 = (size_t)Y * P.W + X;
+              float idv[3][2];
+              if (P.in_fmt == FSUAE_FMT_F32_NCHW3) {
+                const float* ip = (const float*)P.frame_in + (size_t)f * 3 * fpl + p0;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                  float2 t2 = *reinterpret_cast<const float2*>(ip + c * fpl);
+                  idv[c][0] = t2.x; idv[c][1] = t2.y;
+                }
+              } else if (P.in_fmt == FSUAE_FMT_U8_NHWC4) {
+                uint2 t2 = *reinterpret_cast<const uint2*>((const unsigned char*)P.frame_in + ((size_t)f * fpl + p0) * 4);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                  idv[c][0] = s_lut[(t2.x >> (8 * c)) & 0xFF];
+                  idv[c][1] = s_lut[(t2.y >> (8 * c)) & 0xFF];
+                }
+              } else {
+                const unsigned char* ip = (const unsigned char*)P.frame_in + (size_t)f * 4 * fpl + p0;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                  idv[c][0] = s_lut[ip[c * fpl]];
+                  idv[c][1] = s_lut[ip[c * fpl + 1]];
+                }
+              }
+              float res[3][2];
+#pragma unroll
+              for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) res[c][dx] = fmaxf(o[c * 4 + dy * 2 + dx] + idv[c][dx], 0.f);
+              if (P.out_fmt == FSUAE_FMT_F32_NCHW3) {
+                float* op = (float*)P.frame_out + (size_t)f * 3 * fpl + p0;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) *reinterpret_cast<float2*>(op + c * fpl) = make_float2(res[c][0], res[c][1]);
+              } else {
+                uint32_t px[2];
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx)
+                  px[dx] = (uint32_t)to_u8_fast(res[0][dx], P.gamma_out) | ((uint32_t)to_u8_fast(res[1][dx], P.gamma_out) << 8) |
+                           ((uint32_t)to_u8_fast(res[2][dx], P.gamma_out) << 16) | 0xFF000000u;
+                *reinterpret_cast<uint2*>((unsigned char*)P.frame_out + ((size_t)f * fpl + p0) * 4) = make_uint2(px[0], px[1]);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[stage]);
+        if (++stage == C::STAGES) { stage = 0; spar ^= 1; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// head: frame -> chunk-planar bf16 (PixelUnshuffle(2): 12 channels -> 2 planes, 4 zero channels)
+// ------------------------------------------------------------------------------------------------
+__global__ void head_unshuffle_bf16_kernel(const void* __restrict__ in, unsigned char* __restrict__ dst, int n_frames,
+                                           int in_fmt, int H, int W, int xoff, int Hw, int Ww, int PW,
+                                           unsigned long long fs_dst, int gamma_in) {
+  __shared__ float lut[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    float t = (float)i * (1.0f / 255.0f);
+    lut[i] = gamma_in ? powf(t, 2.2f) : t;
+  }
+  __syncthreads();
+  const size_t plane = (size_t)Hw * Ww, total = (size_t)n_frames * plane;
+  const size_t fpl = (size_t)H * W;
+  const size_t row_pitch = (size_t)PW * 16, plane_pitch = (size_t)(Hw + 2) * row_pitch;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int f = (int)(idx / plane);
+    const int r = (int)(idx - (size_t)f * plane);
+    const int h = r / Ww, w = r - h * Ww;
+    float v[12];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const size_t p0 = (size_t)(2 * h + dy) * W + 2 * w + xoff;
+      if (in_fmt == FSUAE_FMT_F32_NCHW3) {
+        const float* ip = (const float*)in + (size_t)f * 3 * fpl + p0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float2 t2 = *reinterpret_cast<const float2*>(ip + c * fpl);
+          v[c * 4 + dy * 2] = t2.x; v[c * 4 + dy * 2 + 1] = t2.y;
+        }
+      } else if (in_fmt == FSUAE_FMT_U8_NHWC4) {
+        uint2 t2 = *reinterpret_cast<const uint2*>((const unsigned char*)in + ((size_t)f * fpl + p0) * 4);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          v[c * 4 + dy * 2] = lut[(t2.x >> (8 * c)) & 0xFF];
+          v[c * 4 + dy * 2 + 1] = lut[(t2.y >> (8 * c)) & 0xFF];
+        }
+      } else {
+        const unsigned char* ip = (const unsigned char*)in + (size_t)f * 4 * fpl + p0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          v[c * 4 + dy * 2] = lut[ip[c * fpl]];
+          v[c * 4 + dy * 2 + 1] = lut[ip[c * fpl + 1]];
+        }
+      }
+    }
+    unsigned char* dp = dst + (size_t)f * fs_dst + (size_t)(h + 1) * row_pitch + (size_t)(w + 1) * 16;
+    *reinterpret_cast<uint4*>(dp) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                               pack_bf16x2(v[6], v[7]));
+    *reinterpret_cast<uint4*>(dp + plane_pitch) = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), 0u, 0u);
+  }
+}
+
+__global__ void black_columns_bf16_kernel(void* __restrict__ out, int n_frames, int out_fmt, int H, int W, int ncols) {
+  const size_t total = (size_t)n_frames * H * ncols;
+  const size_t fplane = (size_t)H * W;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int x = (int)(i % ncols);
+    size_t t = i / ncols;
+    int y = (int)(t % H);
+    int f = (int)(t / H);
+    size_t pix = (size_t)y * W + x;
+    if (out_fmt == FSUAE_FMT_U8_NHWC4) {
+      ((uchar4*)out)[(size_t)f * fplane + pix] = make_uchar4(0, 0, 0, 255);
+    } else {
+      float* o = (float*)out + (size_t)f * 3 * fplane + pix;
+      o[0] = 0.f; o[fplane] = 0.f; o[2 * fplane] = 0.f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host: weight packing, kernel table, plan
+// ------------------------------------------------------------------------------------------------
+
+uint16_t f2bf(float f) {   // round to nearest even, like __float2bfloat16_rn
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+// B operand of instruction (dy, st): [2 halves][NPAD rows][8 k]; half h <-> unit u = 2 st + h (see the kernel for the odd tail),
+// chunk j = u / 3 (plane of the concatenated sources), tap dx = u % 3, channels 8j .. 8j+7.
+std::vector<uint16_t> pack_weights(const float* w, int cout, int cin0, int cin1, int P0, int P1, int NPAD) {
+  const int PT = P0 + P1, cin = cin0 + cin1;
+  const int steps_row = (3 * PT + 1) / 2;
+  std::vector<uint16_t> out((size_t)3 * steps_row * NPAD * 16, 0);
+  for (int dy = 0; dy < 3; ++dy)
+    for (int st = 0; st < steps_row; ++st)
+      for (int h = 0; h < 2; ++h) {
+        int u = 2 * st + h;
+        if (2 * st + 1 >= 3 * PT) {       // odd tail: real unit in the second half, zeros in the first
+          if (h == 0) continue;
+          u = 3 * PT - 1;
+        }
+        const int j = u / 3, dx = u % 3;
+        for (int n = 0; n < cout; ++n)
+          for (int k = 0; k < 8; ++k) {
+            int ci;   // channel inside the concatenated input
+            if (j < P0) { ci = j * 8 + k; if (ci >= cin0) continue; }
+            else { ci = (j - P0) * 8 + k; if (ci >= cin1) continue; ci += cin0; }
+            const float v = w[((size_t)n * cin + ci) * 9 + dy * 3 + dx];
+            out[(((size_t)(dy * steps_row + st) * 2 + h) * NPAD + n) * 8 + k] = f2bf(v);
+          }
+      }
+  return out;
+}
+
+typedef void (*KernelFn)(const LayerK);
+
+struct Variant {
+  int PT, NPAD, OUT_PLANES, KIND;
+  int pre0, pre1, post0, post1, skip;   // -1 = generic (runtime op-codes)
+  KernelFn fn;
+  int smem;
+};
+
+template <int PT, int NPAD, int OP, int KIND, class EPI>
+Variant make_variant(int a, int b, int c, int d, int skip) {
+  Variant v{PT, NPAD, OP, KIND, a, b, c, d, skip, conv3x3_tc_kernel<PT, NPAD, OP, KIND, EPI>, Cfg<PT, NPAD>::SMEM};
+  return v;
+}
+
+#define A(x) FSUAE_ACT_##x
+const std::vector<Variant>& variants() {
+  static const std::vector<Variant> v = {
+      // ---- pix_shuffle lightweight, compile-time epilogues (model_pix_shuffle.py:306-311) ----
+      make_variant<2, 48, 5, EPI_STORE, Epi<A(SINLU), A(RELU6), 0, 0, false>>(A(SINLU), A(RELU6), 0, 0, 0),
+      make_variant<5, 48, 5, EPI_STORE, Epi<A(TELU), 0, A(SINLU), A(BIASED_PRELU), true>>(A(TELU), 0, A(SINLU), A(BIASED_PRELU), 1),
+      make_variant<5, 80, 9, EPI_STORE, Epi<0, 0, 0, 0, false>>(0, 0, 0, 0, 0),
+      make_variant<9, 80, 9, EPI_STORE, Epi<A(MISH), A(BIASED_PRELU), A(TANH), A(RELU), true>>(A(MISH), A(BIASED_PRELU), A(TANH), A(RELU), 1),
+      make_variant<9, 48, 5, EPI_STORE, Epi<0, 0, 0, 0, false>>(0, 0, 0, 0, 0),
+      make_variant<10, 48, 5, EPI_STORE, Epi<A(MISH), A(RELU6), 0, 0, false>>(A(MISH), A(RELU6), 0, 0, 0),
+      make_variant<5, 16, 2, EPI_TAIL_SHUFFLE, Epi<A(BIASED_PRELU), 0, 0, 0, false>>(A(BIASED_PRELU), 0, 0, 0, 0),
+      // ---- generic epilogues (any activation chain of the registry except channel softmax) ----
+      make_variant<2, 48, 5, EPI_STORE, Epi<-1, -1, -1, -1, false>>(-1, -1, -1, -1, 0),
+      make_variant<5, 48, 5, EPI_STORE, Epi<-1, -1, -1, -1, false>>(-1, -1, -1, -1, 0),
+      make_variant<5, 48, 5, EPI_STORE, Epi<-1, -1, -1, -1, true>>(-1, -1, -1, -1, 1),
+      make_variant<5, 80, 9, EPI_STORE, Epi<-1, -1, -1, -1, false>>(-1, -1, -1, -1, 0),
+      make_variant<9, 80, 9, EPI_STORE, Epi<-1, -1, -1, -1, true>>(-1, -1, -1, -1, 1),
+      make_variant<9, 80, 9, EPI_STORE, Epi<-1, -1, -1, -1, false>>(-1, -1, -1, -1, 0),
+      make_variant<9, 48, 5, EPI_STORE, Epi<-1, -1, -1, -1, false>>(-1, -1, -1, -1, 0),
+      make_variant<10, 48, 5, EPI_STORE, Epi<-1, -1, -1, -1, false>>(-1, -1, -1, -1, 0),
+      make_variant<5, 16, 2, EPI_TAIL_SHUFFLE, Epi<-1, -1, -1, -1, false>>(-1, -1, -1, -1, 0),
+  };
+  return v;
+}
+#undef A
+
+struct LayerPlan {
+  const Variant* var = nullptr;
+  unsigned char* d_w = nullptr;
+  int P0 = 0, P1 = 0, NPAD = 0, out_planes = 0;
+  LayerK k{};   // geometry-independent fields prefilled
+};
+
+}  // namespace
+
+struct Bf16Plan {
+  std::vector<LayerPlan> layers;
+  std::vector<unsigned char*> buf;     // chunk-planar activation buffers, id 0..n_layers-1 (last layer writes the frame)
+  std::vector<int> planes;
+  std::vector<size_t> buf_bytes;
+  int zero_Hw = -1, zero_Ww = -1;      // geometry the borders are currently valid for
+};
+
+static int planes_of(int c) { return (c + 7) / 8; }
+
+int bf16_create(fsuae_engine* e) {
+  const fsuae_net_desc& d = e->desc;
+  if (d.head != FSUAE_HEAD_UNSHUFFLE2 || d.tail != FSUAE_TAIL_SHUFFLE2_RESIDUAL_RELU)
+    return set_error(e, FSUAE_ERR_UNSUPPORTED, "bf16 build: only the pix_shuffle family (unshuffle head / shuffle tail) is implemented");
+  Bf16Plan* plan = new Bf16Plan();
+  e->bf16 = plan;
+  std::vector<int> ch(d.n_layers + 1);
+  ch[0] = 12;
+  for (int i = 0; i < d.n_layers; ++i) ch[i + 1] = d.layers[i].cout;
+
+  plan->layers.resize(d.n_layers);
+  for (int i = 0; i < d.n_layers; ++i) {
+    const fsuae_layer_desc& L = d.layers[i];
+    LayerPlan& lp = plan->layers[i];
+    const bool last = i == d.n_layers - 1;
+    lp.P0 = planes_of(L.cin0);
+    lp.P1 = L.cin1 > 0 ? planes_of(L.cin1) : 0;
+    lp.NPAD = (L.cout + 15) / 16 * 16;
+    lp.out_planes = planes_of(L.cout);
+    if (L.cout > MAXC) return set_error(e, FSUAE_ERR_UNSUPPORTED, "bf16 build: more than 112 output channels");
+    int ops[4] = {0, 0, 0, 0};
+    for (int k = 0; k < L.n_pre + L.n_post; ++k) {
+      const fsuae_act_desc& a = k < L.n_pre ? L.pre[k] : L.post[k - L.n_pre];
+      if (act_is_softmax(a.op)) return set_error(e, FSUAE_ERR_UNSUPPORTED, "bf16 build: channel softmax slots are not implemented (use the fp32 build)");
+    }
+    if (L.n_pre > 2 || L.n_post > 2) return set_error(e, FSUAE_ERR_UNSUPPORTED, "bf16 build: at most 2 activation slots before and after the skip add");
+    for (int k = 0; k < L.n_pre; ++k) ops[k] = L.pre[k].op;
+    for (int k = 0; k < L.n_post; ++k) ops[2 + k] = L.post[k].op;
+    const int kind = last ? EPI_TAIL_SHUFFLE : EPI_STORE;
+    const int skip = L.skip_src >= 0 ? 1 : 0;
+    const Variant* exact = nullptr;
+    const Variant* generic = nullptr;
+    for (const Variant& v : variants()) {
+      if (v.PT != lp.P0 + lp.P1 || v.NPAD != lp.NPAD || v.OUT_PLANES != lp.out_planes || v.KIND != kind || v.skip != skip) continue;
+      if (v.pre0 == ops[0] && v.pre1 == ops[1] && v.post0 == ops[2] && v.post1 == ops[3]) exact = &v;
+      if (v.pre0 == -1) generic = &v;
+    }
+    lp.var = exact ? exact : generic;
+    if (!lp.var)
+      return set_error(e, FSUAE_ERR_UNSUPPORTED,
+                       "bf16 build: no tensor-core kernel instantiated for layer " + std::to_string(i + 1) + " (planes " +
+                           std::to_string(lp.P0 + lp.P1) + ", N " + std::to_string(lp.NPAD) + "); use the fp32 build");
+    // weights
+    std::vector<uint16_t> wp = pack_weights(e->h_blob.data() + L.w_off, L.cout, L.cin0, L.cin1, lp.P0, lp.P1, lp.NPAD);
+    FSUAE_CUDA_CHECK(e, cudaMalloc(&lp.d_w, wp.size() * 2));
+    FSUAE_CUDA_CHECK(e, cudaMemcpy(lp.d_w, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
+    e->device_bytes += wp.size() * 2;
+    FSUAE_CUDA_CHECK(e, cudaFuncSetAttribute((const void*)lp.var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, lp.var->smem));
+    // epilogue parameters, expanded per channel
+    LayerK& k = lp.k;
+    std::memset(&k, 0, sizeof(k));
+    k.P0 = lp.P0; k.P1 = lp.P1; k.cout = L.cout;
+    k.wpack = lp.d_w;
+    k.n_pre = L.n_pre; k.n_post = L.n_post;
+    for (int c = 0; c < MAXC; ++c) k.bias[c] = (c < L.cout && L.b_off >= 0) ? e->h_blob[L.b_off + c] : 0.f;
+    for (int s = 0; s < 4; ++s) {
+      k.op[s] = ops[s];
+      const fsuae_act_desc* a = nullptr;
+      if (s < 2 && s < L.n_pre) a = &L.pre[s];
+      if (s >= 2 && s - 2 < L.n_post) a = &L.post[s - 2];
+      for (int c = 0; c < MAXC; ++c) {
+        k.p0[s][c] = (a && a->n0 > 0) ? e->h_blob[a->p0_off + (a->n0 == 1 ? 0 : std::min(c, a->n0 - 1))] : 0.f;
+        k.p1[s][c] = (a && a->n1 > 0) ? e->h_blob[a->p1_off + (a->n1 == 1 ? 0 : std::min(c, a->n1 - 1))] : 0.f;
+      }
+    }
+  }
+  // activation buffers at the largest geometry (no crop)
+  const int Hw = e->H / 2, Ww = e->W / 2;
+  const int S = (Ww + STRIP - 1) / STRIP, PW = STRIP * (S - 1) + MROWS;
+  plan->buf.assign(d.n_layers, nullptr);
+  plan->planes.assign(d.n_layers, 0);
+  plan->buf_bytes.assign(d.n_layers, 0);
+  for (int i = 0; i < d.n_layers; ++i) {
+    plan->planes[i] = i == 0 ? 2 : planes_of(ch[i]);
+    size_t bytes = (size_t)e->chunk * plan->planes[i] * (Hw + 2) * PW * 16 + 256;
+    FSUAE_CUDA_CHECK(e, cudaMalloc(&plan->buf[i], bytes));
+    plan->buf_bytes[i] = bytes;
+    e->device_bytes += bytes;
+  }
+  e->variant = "bf16_tcgen05";
+  return FSUAE_OK;
+}
+
+void bf16_destroy(fsuae_engine* e) {
+  if (!e->bf16) return;
+  for (auto& lp : e->bf16->layers)
+    if (lp.d_w) cudaFree(lp.d_w);
+  for (unsigned char* p : e->bf16->buf)
+    if (p) cudaFree(p);
+  delete e->bf16;
+  e->bf16 = nullptr;
+}
+
+int bf16_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in_fmt, int out_fmt, uint32_t flags,
+                       cudaStream_t st) {
+  Bf16Plan* plan = e->bf16;
+  const fsuae_net_desc& d = e->desc;
+  const Geom g = make_geom(e, flags);
+  const int S = (g.Ww + STRIP - 1) / STRIP, PW = STRIP * (S - 1) + MROWS;
+  if (plan->zero_Hw != g.Hw || plan->zero_Ww != g.Ww) {   // (re)establish the zero borders for this geometry
+    for (size_t i = 0; i < plan->buf.size(); ++i) FSUAE_CUDA_CHECK(e, cudaMemsetAsync(plan->buf[i], 0, plan->buf_bytes[i], st));
+    plan->zero_Hw = g.Hw;
+    plan->zero_Ww = g.Ww;
+  }
+  auto fstride = [&](int id) { return (unsigned long long)plan->planes[id] * (g.Hw + 2) * PW * 16; };
+
+  head_unshuffle_bf16_kernel<<<e->sm_count * 8, 256, 0, st>>>(in, plan->buf[0], n, in_fmt, g.H, g.W, g.xoff, g.Hw, g.Ww, PW,
+                                                              fstride(0), (flags & FSUAE_FLAG_GAMMA_IN) ? 1 : 0);
+  e->launches++;
+
+  // rows per work item: enough items to balance the persistent grid, few enough to amortise the 2 halo rows
+  int RB = 48;
+  while (RB > 6 && (long long)n * S * ((g.Hw + RB - 1) / RB) < 3LL * e->sm_count) RB = (RB * 2) / 3;
+  for (int i = 0; i < d.n_layers; ++i) {
+    const fsuae_layer_desc& L = d.layers[i];
+    LayerPlan& lp = plan->layers[i];
+    LayerK k = lp.k;
+    k.Hw = g.Hw; k.Ww = g.Ww; k.PW = PW; k.S = S; k.RB = RB; k.n_frames = n;
+    k.rb_per_strip = (g.Hw + RB - 1) / RB;
+    k.n_items = n * S * k.rb_per_strip;
+    k.src0 = plan->buf[L.src0]; k.fs0 = fstride(L.src0);
+    if (L.cin1 > 0) { k.src1 = plan->buf[L.src1]; k.fs1 = fstride(L.src1); }
+    if (L.skip_src >= 0) { k.skip = plan->buf[L.skip_src]; k.fs_skip = fstride(L.skip_src); }
+    if (i < d.n_layers - 1) { k.dst = plan->buf[i + 1]; k.fs_dst = fstride(i + 1); }
+    k.frame_in = in; k.frame_out = out; k.in_fmt = in_fmt; k.out_fmt = out_fmt;
+    k.H = g.H; k.W = g.W; k.xoff = g.xoff;
+    k.gamma_in = (flags & FSUAE_FLAG_GAMMA_IN) ? 1 : 0;
+    k.gamma_out = (flags & FSUAE_FLAG_GAMMA_OUT) ? 1 : 0;
+    const int grid = std::min(k.n_items, e->sm_count);
+    lp.var->fn<<<grid, NTHREADS, lp.var->smem, st>>>(k);
+    e->launches++;
+  }
+  if (g.xoff > 0) {
+    black_columns_bf16_kernel<<<64, 256, 0, st>>>(out, n, out_fmt, g.H, g.W, g.xoff);
+    e->launches++;
+  }
+  FSUAE_CUDA_CHECK(e, cudaGetLastError());
+  return FSUAE_OK;
+}
+
 }  // namespace fsuae

@@ -175,3 +175,87 @@ def test_fp32_full_size_properties():
     # spot-check against the oracle on one full-size frame
     want = O.pix_shuffle_forward(sd, spec, x[:1].cpu())
     assert (y[:1].cpu() - want).abs().max().item() <= FP32_TOL
+
+
+# ----------------------------------------------------------------------------------------------
+# bf16 tensor-core build (tcgen05): tolerance max-abs <= 1e-2, PSNR >= 55 dB vs the fp32 oracle
+# ----------------------------------------------------------------------------------------------
+
+def _bf16_model(spec, sd):
+    return build_pkg_pix_shuffle(spec, sd).to(dev()).set_precision("bf16")
+
+
+@pytest.mark.parametrize("shape", [(1, 16, 16), (2, 64, 96), (1, 40, 300), (3, 34, 254), (1, 6, 508), (2, 2, 2)])
+def test_bf16_pix_shuffle_small_frames(shape):
+    """Single strip, exactly-two-strips (W/2 = 127), three strips, 1-pixel-high maps."""
+    B, H, W = shape
+    spec = O.pix_shuffle_preset("lightweight")
+    sd = O.make_pix_shuffle_state_dict(spec, 51)
+    x = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(H + W))
+    want = O.pix_shuffle_forward(sd, spec, x)
+    m = _bf16_model(spec, sd)
+    got = m(x.to(dev())).cpu()
+    assert m.engine_for(dev(), H, W).variant == "bf16_tcgen05"
+    assert (got - want).abs().max().item() <= BF16_TOL
+    assert O.psnr(got, want, 1.0) >= BF16_PSNR
+
+
+def test_bf16_matches_reference_vectors_and_trained_weights():
+    g = load_gold("pix_shuffle_lightweight")
+    spec = gold_spec("lightweight")
+    sd = O.make_pix_shuffle_state_dict(spec, int(g["seed"]))
+    got = _bf16_model(spec, sd)(torch.from_numpy(g["x"]).to(dev())).cpu().numpy()
+    assert np.abs(got - g["y"]).max() <= BF16_TOL
+    # trained weights on a real Amiga screenshot vs the shipped prediction (u8, <= 6 LSB, PSNR >= 50 dB)
+    m = _bf16_model(spec, trained_pix_shuffle_sd())
+    rgba = load_png_rgba(os.path.join(GOLD, "samples", "sample5.png"))
+    want = load_png_rgb(os.path.join(GOLD, "predicted_pix_shuffle", "sample5.png"))
+    out = m.forward_framebuffer(rgba.to(dev())).cpu()[..., :3].permute(0, 3, 1, 2)
+    d = (out.int() - want.int()).abs()
+    print(f"bf16 trained sample5: max {d.max().item()} LSB, psnr {O.psnr(out, want, 255.0):.1f} dB, "
+          f"<=1 LSB {(d <= 1).float().mean().item():.4f}")
+    # bf16 rounding of near-black linear values is amplified by the 1/2.2 gamma (slope ~13 at L=0.002)
+    assert d.max().item() <= 16
+    assert O.psnr(out, want, 255.0) >= 48.0
+    assert (d <= 1).float().mean().item() >= 0.97
+
+
+@pytest.mark.parametrize("crop16", [False, True])
+def test_bf16_framebuffer_contract_full_size(crop16):
+    """uint8 RGBA end to end at 752x576 on mixed pixel-mode frames: <= 6 LSB, >= 85 % exact."""
+    spec = O.pix_shuffle_preset("lightweight")
+    sd = O.make_pix_shuffle_state_dict(spec, 31)
+    fb = O.synth_framebuffers(4, seed=8)
+    want = O.framebuffer_forward(sd, spec, fb, crop16=crop16)
+    m = _bf16_model(spec, sd)
+    got = m.forward_framebuffer(fb.to(dev()), crop16=crop16).cpu()
+    d = (got.int() - want.int()).abs()
+    assert d.max().item() <= 6 and (d == 0).float().mean().item() >= 0.85
+    assert (got[..., 3] == 255).all()
+    if crop16:
+        assert (got[:, :, :16, :3] == 0).all()
+    assert torch.equal(m.run_host(fb.pin_memory(), crop16=crop16), got)
+
+
+def test_bf16_full_size_float_and_batch_properties():
+    spec = O.pix_shuffle_preset("lightweight")
+    sd = O.make_pix_shuffle_state_dict(spec, 41)
+    m = _bf16_model(spec, sd)
+    m.chunk_frames = 4
+    x = torch.rand(6, 3, 576, 752, generator=torch.Generator().manual_seed(2)).to(dev())
+    y = m(x)
+    assert (y >= 0).all()
+    assert torch.equal(y[4:5], m(x[4:5].contiguous()))          # frames are independent, chunking is invisible
+    assert torch.equal(y.flip(0), m(x.flip(0).contiguous()))
+    want = O.pix_shuffle_forward(sd, spec, x[:2].cpu())
+    got = y[:2].cpu()
+    assert (got - want).abs().max().item() <= BF16_TOL
+    assert O.psnr(got, want, 1.0) >= BF16_PSNR
+
+
+def test_bf16_unsupported_network_fails_loudly():
+    from fs_uae_image_enhancer_project_b200 import _lib, model_conv5
+    m = model_conv5.get_model("lightweight").to(dev()).set_precision("bf16")
+    with pytest.raises(_lib.EngineError) as ei:
+        m(torch.rand(1, 3, 16, 16, device=dev()))
+    assert ei.value.code == _lib.ERR_UNSUPPORTED
