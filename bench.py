@@ -126,6 +126,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="auto", choices=["auto", "bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunk", type=int, default=16, help="frames per internal engine pass")
+    ap.add_argument("--quick", action="store_true", help="skip latency / e2e legs (tuning runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -149,7 +151,7 @@ def main():
     model = model_pix_shuffle.get_model("lightweight")
     model.load_state_dict(sd)
     model = model.to(dev)
-    model.chunk_frames = 16
+    model.chunk_frames = args.chunk
     precision = args.precision
     if precision in ("auto", "bf16"):
         try:
@@ -195,6 +197,11 @@ def main():
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
 
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"chunk": args.chunk, "fps": BATCH * world * args.steps / (ms / 1000.0),
+                              "us_per_frame": 1e3 * ms / args.steps / BATCH}), flush=True)
+        return
     # single-frame latency, device resident (p50 over 200 launches)
     lat = []
     one_in, one_out = d_in[0][:1].contiguous(), d_out[0][:1].contiguous()

@@ -13,6 +13,7 @@ ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libfsuae_enhancer.so")
 SOURCES = ["abi.cu", "fp32_path.cu", "bf16_tc.cu"]
+FAST_MATH_SOURCES = {"bf16_tc.cu"}   # approximate transcendentals + flush-to-zero: bf16 build only, never the fp32 build
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
@@ -38,6 +39,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
                os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
+        if src in FAST_MATH_SOURCES:
+            cmd.insert(1, "--use_fast_math")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:

@@ -16,12 +16,15 @@
 // K=16 instruction are any two (tap, channel-chunk) units; their distance is the descriptor's LBO.
 // Weights for the whole layer stay resident in shared memory, pre-packed per instruction.
 //
-// Warp roles (192 threads, one persistent CTA per SM): warp 0 = TMA producer, warp 1 = MMA issuer
-// (one elected lane), warps 2-5 = epilogue (thread = pixel, TMEM lane = pixel).
+// Warp roles (576 threads, one persistent CTA per SM): warp 0 = TMA producer, warp 1 = MMA issuer
+// (one elected lane), warps 2-17 = four epilogue warpgroups (thread = pixel, TMEM lane = pixel);
+// warpgroup g drains accumulator stage g, i.e. every fourth strip row, so the activation math of
+// four rows overlaps the MMAs of the following ones.
 //
 // Reference semantics: model/model_pix_shuffle.py:227-298 (and activations.py for the slots).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -39,12 +42,13 @@ constexpr int STRIP = 126;            // valid output columns per strip row
 constexpr int MROWS = 128;            // MMA M = slots per strip row
 constexpr int PLANE_ROW = MROWS * 16; // bytes of one plane of one strip row
 constexpr int SMEM_LIMIT = 232448 - 2048;
-constexpr int NTHREADS = 192;
+constexpr int EPI_WG = 4;                       // epilogue warpgroups; group g owns accumulator stage g
+constexpr int NTHREADS = 64 + 128 * EPI_WG;
 
 enum { EPI_STORE = 0, EPI_TAIL_SHUFFLE = 1 };
 
 struct LayerK {
-  int Hw, Ww, PW, S, RB, n_frames, rb_per_strip, n_items;
+  int Hw, Ww, PW, S, n_frames, n_blocks;   // n_blocks = n_frames * S * Hw strip rows, ordered (frame, strip, row)
   int P0, P1, cout;
   unsigned long long fs0, fs1, fs_skip, fs_dst;  // frame strides in bytes
   const unsigned char* src0;
@@ -73,17 +77,22 @@ struct Cfg {
   static constexpr int ROWBYTES = PT * PLANE_ROW;
   static constexpr int RING_FIT = (SMEM_LIMIT - WBYTES - 64 - 512) / ROWBYTES;
   static constexpr int RING = RING_FIT > 10 ? 10 : RING_FIT;
-  static constexpr int STAGES = (512 / NPAD) > 4 ? 4 : (512 / NPAD);
+  static constexpr int STAGES = EPI_WG;
   static constexpr int BAR_OFF = WBYTES + RING * ROWBYTES + 64;
   static constexpr int SMEM = BAR_OFF + 512;
   static_assert(RING >= 4, "layer does not fit: weights + 4 ring rows exceed shared memory");
-  static_assert(STAGES >= 2, "need two accumulator stages");
+  static_assert(STAGES * NPAD <= 512, "accumulator stages exceed TMEM");
 };
 
 // ---- fast activation math for the bf16 build (error well below bf16 resolution) ----------------
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(tanh_fast(0.5f * x), 0.5f, 0.5f); }
@@ -96,10 +105,10 @@ __device__ __forceinline__ float act_rt(int op, float x, float p0, float p1) {
     case FSUAE_ACT_TANH: return tanh_fast(x);
     case FSUAE_ACT_SIGMOID: return sigmoid_fast(x);
     case FSUAE_ACT_SILU: return x * sigmoid_fast(x);
-    case FSUAE_ACT_MISH: {   // x * tanh(softplus(x)) = x * w / (w + 2), w = e^x (e^x + 2)
-      float n = __expf(fminf(x, 20.f));
+    case FSUAE_ACT_MISH: {   // x * tanh(softplus(x)) = x * w / (w + 2) = x - 2x / (w + 2), w = e^x (e^x + 2)
+      float n = __expf(x);   // overflow is benign: w = inf -> 1/(w+2) = 0 -> x
       float w = n * (n + 2.f);
-      return x * __fdividef(w, w + 2.f);
+      return fmaf(x * rcp_fast(w + 2.f), -2.f, x);
     }
     case FSUAE_ACT_GELU: return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
     case FSUAE_ACT_ELU: return x > 0.f ? x : p0 * (__expf(x) - 1.f);
@@ -129,6 +138,8 @@ __device__ __forceinline__ float act_slot(const LayerK& P, int slot, int ch, flo
   else return act_rt(P.op[slot], x, P.p0[slot][ch], P.p1[slot][ch]);
 }
 
+// SKIP: 0 = no residual add, 1 = the layer's own input (src0) is added -> read from the centre row of
+// the shared-memory ring (no second trip to global memory)
 template <int PRE0, int PRE1, int POST0, int POST1, bool SKIP>
 struct Epi {
   static constexpr bool kSkip = SKIP;
@@ -156,11 +167,39 @@ __device__ __forceinline__ uint8_t to_u8_fast(float v, int gamma_out) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// work partition: the n_blocks strip rows are split into gridDim.x contiguous, equally long ranges
+// (perfect balance for the persistent CTAs); a range is walked as segments that stay inside one
+// strip of one frame.  A segment of `rows` output rows streams rows+2 input rows through the ring.
+// Every warp role iterates the identical segment sequence.
+// ------------------------------------------------------------------------------------------------
+struct Seg { int f, s, y0, rows; };
+
+struct SegIter {
+  int cur, end;
+  __device__ SegIter(const LayerK& P) {
+    cur = (int)((long long)P.n_blocks * blockIdx.x / gridDim.x);
+    end = (int)((long long)P.n_blocks * (blockIdx.x + 1) / gridDim.x);
+  }
+  __device__ bool next(const LayerK& P, Seg& g) {
+    if (cur >= end) return false;
+    const int per_frame = P.S * P.Hw;
+    g.f = cur / per_frame;
+    const int r = cur - g.f * per_frame;
+    g.s = r / P.Hw;
+    g.y0 = r - g.s * P.Hw;
+    g.rows = min(P.Hw - g.y0, end - cur);
+    cur += g.rows;
+    return true;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
 // the layer kernel
 // ------------------------------------------------------------------------------------------------
-template <int PT, int NPAD, int OUT_PLANES, int KIND, class EPI>
+template <int PT, int NPAD, int COUT, int KIND, class EPI>
 __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_constant__ LayerK P) {
   using C = Cfg<PT, NPAD>;
+  constexpr int OUT_PLANES = (COUT + 7) / 8;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_w = smem;
   uint8_t* s_ring = smem + C::WBYTES;
@@ -177,7 +216,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < C::RING; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    // a ring row is released by the MMA commit and, when the residual is read from it, by the 4 epilogue warps
+    for (int i = 0; i < C::RING; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], EPI::kSkip ? 5 : 1); }
     for (int i = 0; i < C::STAGES; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
     mbar_init(wbar, 1);
     fence_mbar_init();
@@ -198,6 +238,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Programmatic dependent launch: let the next layer's grid start its prologue (barrier init, TMEM
+  // allocation, weight fetch) on SMs as they drain; everything that touches activations written by the
+  // previous layer sits behind griddepcontrol.wait.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
   const size_t row_pitch = (size_t)P.PW * 16;                  // bytes of one padded image row of one plane
   const size_t plane_pitch = (size_t)(P.Hw + 2) * row_pitch;
 
@@ -205,14 +250,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
     // ======================= TMA producer =======================
     if (elect_one()) {
       mbar_arrive_expect_tx(wbar, C::WBYTES);
-      tma_load_1d(s_w, P.wpack, C::WBYTES, wbar);
+      tma_load_1d(s_w, P.wpack, C::WBYTES, wbar);      // weights are constants: fetch before the dependency wait
+      asm volatile("griddepcontrol.wait;" ::: "memory");
       uint32_t slot = 0, par = 1;   // waiting on parity 1 of a fresh barrier passes immediately
-      for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
-        const int f = item / (P.S * P.rb_per_strip);
-        const int r = item - f * (P.S * P.rb_per_strip);
-        const int s = r / P.rb_per_strip;
-        const int y0 = (r - s * P.rb_per_strip) * P.RB;
-        const int rows = min(P.RB, P.Hw - y0);
+      SegIter it(P);
+      Seg sg;
+      while (it.next(P, sg)) {
+        const int f = sg.f, s = sg.s, y0 = sg.y0, rows = sg.rows;
         const unsigned char* g0 = P.src0 + (size_t)f * P.fs0 + (size_t)y0 * row_pitch + (size_t)s * STRIP * 16;
         const unsigned char* g1 = P.P1 ? P.src1 + (size_t)f * P.fs1 + (size_t)y0 * row_pitch + (size_t)s * STRIP * 16 : nullptr;
         for (int k = 0; k < rows + 2; ++k) {          // padded rows y0 .. y0+rows+1
@@ -237,10 +281,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
       mbar_wait(wbar, 0);
       uint32_t wslot = 0, wpar = 0;       // next ring slot to wait for
       uint32_t stage = 0, spar = 1;       // accumulator stage / parity for tempty
-      for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
-        const int r = item % (P.S * P.rb_per_strip);
-        const int y0 = (r % P.rb_per_strip) * P.RB;
-        const int rows = min(P.RB, P.Hw - y0);
+      SegIter it(P);
+      Seg sg;
+      while (it.next(P, sg)) {
+        const int rows = sg.rows;
         uint32_t s0 = wslot;              // slot of the block's first input row
         // first two rows of the item
         for (int k = 0; k < 2; ++k) {
@@ -253,22 +297,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
           mbar_wait(&tempty[stage], spar);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + stage * NPAD;
-          uint32_t rs = s0;
+          // One input row = 3*PT (chunk, dx) units, two units per K=16 instruction.  Unit u sits at
+          // (u/3) * 2 KB + (u%3) * 16 B inside the ring row, so every 3 instructions (= 2 chunks) the
+          // pattern {+0 | lbo 16 B, +32 B | lbo 2 KB - 32 B, +2 KB + 16 B | lbo 16 B} repeats.  When 3*PT
+          // is odd the last instruction re-reads unit 3*PT-2 against zero weights in its first half and
+          // carries unit 3*PT-1 in its second, so both halves always point at landed, finite data --
+          // anything else could turn never-written shared memory into 0 * NaN.
+          constexpr uint32_t BSTEP = (NPAD * 32) >> 4;
+          constexpr uint32_t L16 = 1u << 16, L2K = (uint32_t)((PLANE_ROW >> 4) - 2) << 16;
+          constexpr int G3 = C::STEPS_ROW / 3, REM = C::STEPS_ROW % 3;
+          static_assert(REM == 0 || REM == 2, "unexpected instruction count per row");
+          uint32_t rs = s0, acc = 0, b_lo = w_lo;
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy) {
-            const uint32_t a_row = ring_lo + rs * (C::ROWBYTES >> 4);
-#pragma unroll
-            for (int st = 0; st < C::STEPS_ROW; ++st) {
-              // units (2 st, 2 st + 1) form one K=16 instruction.  A row has 3*PT units; when that is odd the
-              // last instruction carries unit 3*PT-1 in its SECOND half and re-reads unit 3*PT-2 (against
-              // zero weights) in its first half, so both halves always point at landed, finite data --
-              // anything else could turn never-written shared memory into 0 * NaN.
-              const int u = (2 * st + 1 < C::UNITS_ROW) ? 2 * st : 2 * st - 1;   // first unit: chunk u/3, tap dx = u%3
-              const uint32_t off = (uint32_t)((u / 3) * (PLANE_ROW >> 4) + (u % 3));
-              const uint32_t lbo = (u % 3) < 2 ? 1u : (uint32_t)((PLANE_ROW >> 4) - 2);
-              const uint64_t ad = ((uint64_t)HI << 32) | (uint64_t)((a_row + off) | (lbo << 16));
-              const uint64_t bd = ((uint64_t)HI << 32) | (uint64_t)(w_lo + (uint32_t)((dy * C::STEPS_ROW + st) * ((NPAD * 32) >> 4)));
-              umma_bf16(d_tmem, ad, bd, IDESC, (dy | st) != 0);
+            uint32_t a_lo = ring_lo + rs * (C::ROWBYTES >> 4);
+#pragma unroll 1
+            for (int g3 = 0; g3 < G3; ++g3) {
+              umma_bf16(d_tmem, ((uint64_t)HI << 32) | (a_lo | L16), ((uint64_t)HI << 32) | b_lo, IDESC, acc);
+              umma_bf16(d_tmem, ((uint64_t)HI << 32) | ((a_lo + 2) | L2K), ((uint64_t)HI << 32) | (b_lo + BSTEP), IDESC, 1);
+              umma_bf16(d_tmem, ((uint64_t)HI << 32) | ((a_lo + (PLANE_ROW >> 4) + 1) | L16), ((uint64_t)HI << 32) | (b_lo + 2 * BSTEP), IDESC, 1);
+              acc = 1;
+              a_lo += 2 * (PLANE_ROW >> 4);
+              b_lo += 3 * BSTEP;
+            }
+            if constexpr (REM == 2) {
+              umma_bf16(d_tmem, ((uint64_t)HI << 32) | (a_lo | L16), ((uint64_t)HI << 32) | b_lo, IDESC, 1);
+              umma_bf16(d_tmem, ((uint64_t)HI << 32) | ((a_lo + 1) | L16), ((uint64_t)HI << 32) | (b_lo + BSTEP), IDESC, 1);
+              b_lo += 2 * BSTEP;
             }
             if (++rs == C::RING) rs = 0;
           }
@@ -286,30 +341,77 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
       }
     }
   } else {
-    // ======================= epilogue (warps 2..5) =======================
+    // ======================= epilogue (warps 2..17) =======================
     const int q = warp & 3;                    // TMEM lane quadrant this warp may access
     const int m = q * 32 + lane;               // pixel index inside the strip row
-    uint32_t stage = 0, spar = 0;
-    for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
-      const int f = item / (P.S * P.rb_per_strip);
-      const int r = item - f * (P.S * P.rb_per_strip);
-      const int s = r / P.rb_per_strip;
-      const int y0 = (r - s * P.rb_per_strip) * P.RB;
-      const int rows = min(P.RB, P.Hw - y0);
+    const uint32_t stage = (uint32_t)(warp - 2) >> 2;   // this warpgroup's accumulator stage
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // epilogues read the frame / write buffers earlier layers still read
+    uint32_t spar = 0, blk = 0, qrow = 0;      // qrow: ring-row counter at the start of the item
+    SegIter it(P);
+    Seg sg;
+    while (it.next(P, sg)) {
+      const int f = sg.f, s = sg.s, y0 = sg.y0, rows = sg.rows;
       const int x = s * STRIP + m;
       const bool valid = m < STRIP && x < P.Ww;
-      for (int b = 0; b < rows; ++b) {
+      for (int b = 0; b < rows; ++b, ++blk) {
+        if ((blk & (EPI_WG - 1)) != stage) continue;
         const int y = y0 + b;
         const size_t pix = (size_t)(y + 1) * row_pitch + (size_t)(x + 1) * 16;
-        uint4 sk[EPI::kSkip ? OUT_PLANES : 1];
-        if constexpr (EPI::kSkip) {
-          const unsigned char* sp = P.skip + (size_t)f * P.fs_skip + pix;
+        // tail: fetch the input pixels of the global residual while the MMAs of this row are still running
+        float idv[KIND == EPI_TAIL_SHUFFLE ? 2 : 1][3][2];
+        if constexpr (KIND == EPI_TAIL_SHUFFLE) {
+          if (valid) {
+            const size_t fpl = (size_t)P.H * P.W;
 #pragma unroll
-          for (int c = 0; c < OUT_PLANES; ++c)
-            sk[c] = valid ? __ldg(reinterpret_cast<const uint4*>(sp + (size_t)c * plane_pitch)) : make_uint4(0, 0, 0, 0);
+            for (int dy = 0; dy < 2; ++dy) {
+              const size_t p0 = (size_t)(2 * y + dy) * P.W + 2 * x + P.xoff;
+              if (P.in_fmt == FSUAE_FMT_F32_NCHW3) {
+                const float* ip = (const float*)P.frame_in + (size_t)f * 3 * fpl + p0;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                  float2 t2 = __ldg(reinterpret_cast<const float2*>(ip + c * fpl));
+                  idv[dy][c][0] = t2.x; idv[dy][c][1] = t2.y;
+                }
+              } else if (P.in_fmt == FSUAE_FMT_U8_NHWC4) {
+                uint2 t2 = __ldg(reinterpret_cast<const uint2*>((const unsigned char*)P.frame_in + ((size_t)f * fpl + p0) * 4));
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                  idv[dy][c][0] = s_lut[(t2.x >> (8 * c)) & 0xFF];
+                  idv[dy][c][1] = s_lut[(t2.y >> (8 * c)) & 0xFF];
+                }
+              } else {
+                const unsigned char* ip = (const unsigned char*)P.frame_in + (size_t)f * 4 * fpl + p0;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                  idv[dy][c][0] = s_lut[ip[c * fpl]];
+                  idv[dy][c][1] = s_lut[ip[c * fpl + 1]];
+                }
+              }
+            }
+          }
         }
         mbar_wait(&tfull[stage], spar);
         tc_fence_after();
+        uint4 sk[EPI::kSkip ? OUT_PLANES : 1];
+        if constexpr (EPI::kSkip) {
+          // residual = this layer's input at the same pixel = centre row of the block, still in the ring.
+          // Only touch the ring barriers AFTER tfull: the block's MMAs have consumed rows kc-1..kc+1, so their
+          // fills are complete and cannot be overtaken before we arrive on `empty` -- a waiter that ran a whole
+          // phase ahead of an mbarrier would see its parity test pass on the wrong fill.
+          const uint32_t kc = qrow + (uint32_t)b + 1;
+          const uint32_t slot = kc % C::RING;
+          mbar_wait(&full[slot], (kc / C::RING) & 1);     // already complete: acquires the TMA-written bytes
+          const uint8_t* sp = s_ring + slot * C::ROWBYTES + (m + 1) * 16;
+#pragma unroll
+          for (int c = 0; c < OUT_PLANES; ++c)
+            sk[c] = valid ? *reinterpret_cast<const uint4*>(sp + c * PLANE_ROW) : make_uint4(0, 0, 0, 0);
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&empty[slot]);
+            if (b == 0) mbar_arrive(&empty[(kc - 1) % C::RING]);          // first row of the segment: no block centres on it
+            if (b == rows - 1) mbar_arrive(&empty[(kc + 1) % C::RING]);   // nor on the last one
+          }
+        }
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + stage * NPAD;
 
         if constexpr (KIND == EPI_STORE) {
@@ -323,13 +425,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int ch = c * 8 + i;
+              if (ch >= COUT) { o[i] = 0.f; continue; }     // padding channels stay exactly zero (and cost nothing)
               float t = EPI::pre(P, ch, __uint_as_float(v[i]) + P.bias[ch]);
               if constexpr (EPI::kSkip) {
                 const uint32_t w = (&sk[c].x)[i >> 1];
                 t += (i & 1) ? bf16_hi(w) : bf16_lo(w);
               }
               t = EPI::post(P, ch, t);
-              o[i] = ch < P.cout ? t : 0.f;     // padding channels stay exactly zero
+              o[i] = t;
             }
             if (valid) {
               uint4 pk = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
@@ -354,34 +457,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
             for (int dy = 0; dy < 2; ++dy) {
               const int Y = 2 * y + dy, X = 2 * x + P.xoff;
               const size_t p0 = (size_t)Y * P.W + X;
-              float idv[3][2];
-              if (P.in_fmt == FSUAE_FMT_F32_NCHW3) {
-                const float* ip = (const float*)P.frame_in + (size_t)f * 3 * fpl + p0;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                  float2 t2 = *reinterpret_cast<const float2*>(ip + c * fpl);
-                  idv[c][0] = t2.x; idv[c][1] = t2.y;
-                }
-              } else if (P.in_fmt == FSUAE_FMT_U8_NHWC4) {
-                uint2 t2 = *reinterpret_cast<const uint2*>((const unsigned char*)P.frame_in + ((size_t)f * fpl + p0) * 4);
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                  idv[c][0] = s_lut[(t2.x >> (8 * c)) & 0xFF];
-                  idv[c][1] = s_lut[(t2.y >> (8 * c)) & 0xFF];
-                }
-              } else {
-                const unsigned char* ip = (const unsigned char*)P.frame_in + (size_t)f * 4 * fpl + p0;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                  idv[c][0] = s_lut[ip[c * fpl]];
-                  idv[c][1] = s_lut[ip[c * fpl + 1]];
-                }
-              }
               float res[3][2];
 #pragma unroll
               for (int c = 0; c < 3; ++c)
 #pragma unroll
-                for (int dx = 0; dx < 2; ++dx) res[c][dx] = fmaxf(o[c * 4 + dy * 2 + dx] + idv[c][dx], 0.f);
+                for (int dx = 0; dx < 2; ++dx) res[c][dx] = fmaxf(o[c * 4 + dy * 2 + dx] + idv[dy][c][dx], 0.f);
               if (P.out_fmt == FSUAE_FMT_F32_NCHW3) {
                 float* op = (float*)P.frame_out + (size_t)f * 3 * fpl + p0;
 #pragma unroll
@@ -400,8 +480,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[stage]);
-        if (++stage == C::STAGES) { stage = 0; spar ^= 1; }
+        spar ^= 1;
       }
+      qrow += (uint32_t)rows + 2;
     }
   }
   tc_fence_before();
@@ -522,7 +603,7 @@ std::vector<uint16_t> pack_weights(const float* w, int cout, int cin0, int cin1,
 typedef void (*KernelFn)(const LayerK);
 
 struct Variant {
-  int PT, NPAD, OUT_PLANES, KIND;
+  int PT, NPAD, COUT, KIND;
   int pre0, pre1, post0, post1, skip;   // -1 = generic (runtime op-codes)
   KernelFn fn;
   int smem;
@@ -538,23 +619,23 @@ Variant make_variant(int a, int b, int c, int d, int skip) {
 const std::vector<Variant>& variants() {
   static const std::vector<Variant> v = {
       // ---- pix_shuffle lightweight, compile-time epilogues (model_pix_shuffle.py:306-311) ----
-      make_variant<2, 48, 5, EPI_STORE, Epi<A(SINLU), A(RELU6), 0, 0, false>>(A(SINLU), A(RELU6), 0, 0, 0),
-      make_variant<5, 48, 5, EPI_STORE, Epi<A(TELU), 0, A(SINLU), A(BIASED_PRELU), true>>(A(TELU), 0, A(SINLU), A(BIASED_PRELU), 1),
-      make_variant<5, 80, 9, EPI_STORE, Epi<0, 0, 0, 0, false>>(0, 0, 0, 0, 0),
-      make_variant<9, 80, 9, EPI_STORE, Epi<A(MISH), A(BIASED_PRELU), A(TANH), A(RELU), true>>(A(MISH), A(BIASED_PRELU), A(TANH), A(RELU), 1),
-      make_variant<9, 48, 5, EPI_STORE, Epi<0, 0, 0, 0, false>>(0, 0, 0, 0, 0),
-      make_variant<10, 48, 5, EPI_STORE, Epi<A(MISH), A(RELU6), 0, 0, false>>(A(MISH), A(RELU6), 0, 0, 0),
-      make_variant<5, 16, 2, EPI_TAIL_SHUFFLE, Epi<A(BIASED_PRELU), 0, 0, 0, false>>(A(BIASED_PRELU), 0, 0, 0, 0),
+      make_variant<2, 48, 36, EPI_STORE, Epi<A(SINLU), A(RELU6), 0, 0, false>>(A(SINLU), A(RELU6), 0, 0, 0),
+      make_variant<5, 48, 36, EPI_STORE, Epi<A(TELU), 0, A(SINLU), A(BIASED_PRELU), true>>(A(TELU), 0, A(SINLU), A(BIASED_PRELU), 1),
+      make_variant<5, 80, 72, EPI_STORE, Epi<0, 0, 0, 0, false>>(0, 0, 0, 0, 0),
+      make_variant<9, 80, 72, EPI_STORE, Epi<A(MISH), A(BIASED_PRELU), A(TANH), A(RELU), true>>(A(MISH), A(BIASED_PRELU), A(TANH), A(RELU), 1),
+      make_variant<9, 48, 36, EPI_STORE, Epi<0, 0, 0, 0, false>>(0, 0, 0, 0, 0),
+      make_variant<10, 48, 36, EPI_STORE, Epi<A(MISH), A(RELU6), 0, 0, false>>(A(MISH), A(RELU6), 0, 0, 0),
+      make_variant<5, 16, 12, EPI_TAIL_SHUFFLE, Epi<A(BIASED_PRELU), 0, 0, 0, false>>(A(BIASED_PRELU), 0, 0, 0, 0),
       // ---- generic epilogues (any activation chain of the registry except channel softmax) ----
-      make_variant<2, 48, 5, EPI_STORE, Epi<-1, -1, -1, -1, false>>(-1, -1, -1, -1, 0),
-      make_variant<5, 48, 5, EPI_STORE, Epi<-1, -1, -1, -1, false>>(-1, -1, -1, -1, 0),
-      make_variant<5, 48, 5, EPI_STORE, Epi<-1, -1, -1, -1, true>>(-1, -1, -1, -1, 1),
-      make_variant<5, 80, 9, EPI_STORE, Epi<-1, -1, -1, -1, false>>(-1, -1, -1, -1, 0),
-      make_variant<9, 80, 9, EPI_STORE, Epi<-1, -1, -1, -1, true>>(-1, -1, -1, -1, 1),
-      make_variant<9, 80, 9, EPI_STORE, Epi<-1, -1, -1, -1, false>>(-1, -1, -1, -1, 0),
-      make_variant<9, 48, 5, EPI_STORE, Epi<-1, -1, -1, -1, false>>(-1, -1, -1, -1, 0),
-      make_variant<10, 48, 5, EPI_STORE, Epi<-1, -1, -1, -1, false>>(-1, -1, -1, -1, 0),
-      make_variant<5, 16, 2, EPI_TAIL_SHUFFLE, Epi<-1, -1, -1, -1, false>>(-1, -1, -1, -1, 0),
+      make_variant<2, 48, 36, EPI_STORE, Epi<-1, -1, -1, -1, false>>(-1, -1, -1, -1, 0),
+      make_variant<5, 48, 36, EPI_STORE, Epi<-1, -1, -1, -1, false>>(-1, -1, -1, -1, 0),
+      make_variant<5, 48, 36, EPI_STORE, Epi<-1, -1, -1, -1, true>>(-1, -1, -1, -1, 1),
+      make_variant<5, 80, 72, EPI_STORE, Epi<-1, -1, -1, -1, false>>(-1, -1, -1, -1, 0),
+      make_variant<9, 80, 72, EPI_STORE, Epi<-1, -1, -1, -1, true>>(-1, -1, -1, -1, 1),
+      make_variant<9, 80, 72, EPI_STORE, Epi<-1, -1, -1, -1, false>>(-1, -1, -1, -1, 0),
+      make_variant<9, 48, 36, EPI_STORE, Epi<-1, -1, -1, -1, false>>(-1, -1, -1, -1, 0),
+      make_variant<10, 48, 36, EPI_STORE, Epi<-1, -1, -1, -1, false>>(-1, -1, -1, -1, 0),
+      make_variant<5, 16, 12, EPI_TAIL_SHUFFLE, Epi<-1, -1, -1, -1, false>>(-1, -1, -1, -1, 0),
   };
   return v;
 }
@@ -609,10 +690,12 @@ int bf16_create(fsuae_engine* e) {
     for (int k = 0; k < L.n_post; ++k) ops[2 + k] = L.post[k].op;
     const int kind = last ? EPI_TAIL_SHUFFLE : EPI_STORE;
     const int skip = L.skip_src >= 0 ? 1 : 0;
+    if (skip && (L.skip_src != L.src0 || L.cin1 > 0))
+      return set_error(e, FSUAE_ERR_UNSUPPORTED, "bf16 build: the residual must be the layer's own input (true for every reference model)");
     const Variant* exact = nullptr;
     const Variant* generic = nullptr;
     for (const Variant& v : variants()) {
-      if (v.PT != lp.P0 + lp.P1 || v.NPAD != lp.NPAD || v.OUT_PLANES != lp.out_planes || v.KIND != kind || v.skip != skip) continue;
+      if (v.PT != lp.P0 + lp.P1 || v.NPAD != lp.NPAD || v.COUT != L.cout || v.KIND != kind || v.skip != skip) continue;
       if (v.pre0 == ops[0] && v.pre1 == ops[1] && v.post0 == ops[2] && v.post1 == ops[3]) exact = &v;
       if (v.pre0 == -1) generic = &v;
     }
@@ -662,6 +745,16 @@ int bf16_create(fsuae_engine* e) {
   return FSUAE_OK;
 }
 
+// debugging aid (not part of the public header): raw chunk-planar bytes of activation buffer `id`
+extern "C" __attribute__((visibility("default"))) long long fsuae_debug_read_bf16_buffer(fsuae_engine* e, int id, void* dst,
+                                                                                        long long max_bytes) {
+  if (!e || !e->bf16 || id < 0 || id >= (int)e->bf16->buf.size()) return -1;
+  cudaDeviceSynchronize();
+  long long n = std::min<long long>(max_bytes, (long long)e->bf16->buf_bytes[id]);
+  if (cudaMemcpy(dst, e->bf16->buf[id], n, cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+  return n;
+}
+
 void bf16_destroy(fsuae_engine* e) {
   if (!e->bf16) return;
   for (auto& lp : e->bf16->layers)
@@ -689,16 +782,12 @@ int bf16_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in
                                                               fstride(0), (flags & FSUAE_FLAG_GAMMA_IN) ? 1 : 0);
   e->launches++;
 
-  // rows per work item: enough items to balance the persistent grid, few enough to amortise the 2 halo rows
-  int RB = 48;
-  while (RB > 6 && (long long)n * S * ((g.Hw + RB - 1) / RB) < 3LL * e->sm_count) RB = (RB * 2) / 3;
   for (int i = 0; i < d.n_layers; ++i) {
     const fsuae_layer_desc& L = d.layers[i];
     LayerPlan& lp = plan->layers[i];
     LayerK k = lp.k;
-    k.Hw = g.Hw; k.Ww = g.Ww; k.PW = PW; k.S = S; k.RB = RB; k.n_frames = n;
-    k.rb_per_strip = (g.Hw + RB - 1) / RB;
-    k.n_items = n * S * k.rb_per_strip;
+    k.Hw = g.Hw; k.Ww = g.Ww; k.PW = PW; k.S = S; k.n_frames = n;
+    k.n_blocks = n * S * g.Hw;
     k.src0 = plan->buf[L.src0]; k.fs0 = fstride(L.src0);
     if (L.cin1 > 0) { k.src1 = plan->buf[L.src1]; k.fs1 = fstride(L.src1); }
     if (L.skip_src >= 0) { k.skip = plan->buf[L.skip_src]; k.fs_skip = fstride(L.skip_src); }
@@ -707,8 +796,19 @@ int bf16_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in
     k.H = g.H; k.W = g.W; k.xoff = g.xoff;
     k.gamma_in = (flags & FSUAE_FLAG_GAMMA_IN) ? 1 : 0;
     k.gamma_out = (flags & FSUAE_FLAG_GAMMA_OUT) ? 1 : 0;
-    const int grid = std::min(k.n_items, e->sm_count);
-    lp.var->fn<<<grid, NTHREADS, lp.var->smem, st>>>(k);
+    int grid = std::min(k.n_blocks, e->sm_count);
+    if (const char* g_env = getenv("FSUAE_DEBUG_GRID")) grid = std::max(1, std::min(k.n_blocks, atoi(g_env)));   // debugging aid: force the CTA count
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = lp.var->smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FSUAE_CUDA_CHECK(e, cudaLaunchKernelEx(&cfg, lp.var->fn, k));
     e->launches++;
   }
   if (g.xoff > 0) {

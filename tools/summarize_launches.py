@@ -1,0 +1,16 @@
+#!/usr/bin/env python3
+"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel."""
+import collections, csv, re, sys
+lines = [l for l in open(sys.argv[1]) if not l.startswith("==")]
+agg = collections.OrderedDict()
+for row in csv.DictReader(lines):
+    name = row["Kernel Name"]
+    m = re.search(r"conv3x3_tc_kernel<(\d+), (\d+), (\d+), (\d+)", name)
+    key = f"tc<PT={m.group(1)},N={m.group(2)},kind={m.group(4)}>" if m else re.sub(r"\(.*", "", name)[-48:]
+    v = float(row["Metric Value"].replace(",", ""))
+    unit = row["Metric Unit"]
+    v = v / 1000 if unit in ("ns", "nsecond") else v * 1000 if unit in ("ms", "msecond") else v
+    agg.setdefault(key, []).append(v)
+tot = sum(sum(v) for v in agg.values())
+for k, v in agg.items():
+    print(f"{k:50s} n={len(v):3d} avg={sum(v)/len(v):9.1f} us  share={100*sum(v)/tot:5.1f}%")
