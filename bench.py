@@ -40,36 +40,48 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md) through NVML
+    (same counters as `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*`), every ~2 ms."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.mask, self.max_mhz = index, [], 0, None
+        self._stop = threading.Event()
+        self._thr = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as exc:  # noqa: BLE001
+            self.err = repr(exc)
+            return
+        self._thr = threading.Thread(target=self._run, daemon=True)
+        self._thr.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        time.sleep(0.05)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        if self._thr is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "?")]}
+        self._stop.set()
+        self._thr.join()
+        reasons = sorted(name for bit, name in self.REASONS.items() if self.mask & bit)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(self.sm)}
 
 
 def cpu_forward_fps(n_frames: int, batch: int, repeats: int = 1):
@@ -126,7 +138,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="auto", choices=["auto", "bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--chunk", type=int, default=16, help="frames per internal engine pass")
+    ap.add_argument("--chunk", type=int, default=64, help="frames per internal engine pass")
     ap.add_argument("--quick", action="store_true", help="skip latency / e2e legs (tuning runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -229,10 +241,8 @@ def main():
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
 
-    if world > 1:
-        t = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s = t[0].item(), t[1].item()
+    from fs_uae_image_enhancer_project_b200.sharding import max_over_ranks
+    ms, e2e_s = max_over_ranks(ms, dev), max_over_ranks(e2e_s, dev)     # whole-job time = slowest rank
 
     if rank == 0:
         frames = BATCH * world * args.steps

@@ -53,6 +53,8 @@ EXPORTS = {
     "fsuae_abi_version": (C.c_int, []),
     "fsuae_engine_create": (C.c_int, [C.POINTER(NetDesc), C.POINTER(C.c_float), C.c_size_t, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "fsuae_engine_create_from_file": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                C.POINTER(C.c_void_p)]),
     "fsuae_engine_destroy": (C.c_int, [C.c_void_p]),
     "fsuae_engine_enqueue": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                        C.c_uint32, C.c_void_p]),

@@ -1,6 +1,7 @@
 // C ABI of the engine (include/fsuae_enhancer.h): descriptor validation, lifetime, chunk loop,
 // host-buffer pipeline.  The arithmetic lives in fp32_path.cu / bf16_tc.cu.
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <mutex>
 
@@ -168,7 +169,8 @@ int fsuae_engine_create(const fsuae_net_desc* desc, const float* blob, size_t bl
   }
 
   // host-pipeline staging: sized for the widest formats
-  size_t in_b = (size_t)e->chunk * 12 * height * width, out_b = (size_t)e->chunk * 16 * height * width;
+  e->host_chunk = std::min(e->chunk, 8);   // finer pipeline stages than the device chunk: H2D / compute / D2H overlap
+  size_t in_b = (size_t)e->host_chunk * 12 * height * width, out_b = (size_t)e->host_chunk * 16 * height * width;
   for (int i = 0; i < 2 && ce == cudaSuccess; ++i) {
     ce = cudaMalloc(&e->d_stage_in[i], in_b);
     if (ce == cudaSuccess) ce = cudaMalloc(&e->d_stage_out[i], out_b);
@@ -187,6 +189,27 @@ int fsuae_engine_create(const fsuae_net_desc* desc, const float* blob, size_t bl
   }
   *out = e;
   return FSUAE_OK;
+}
+
+int fsuae_engine_create_from_file(const char* path, int device, int precision, int height, int width,
+                                  int max_chunk_frames, fsuae_engine** out) {
+  if (!path || !out) return set_error(nullptr, FSUAE_ERR_INVALID, "null argument");
+  *out = nullptr;
+  FILE* f = fopen(path, "rb");
+  if (!f) return set_error(nullptr, FSUAE_ERR_INVALID, std::string("cannot open engine file ") + path);
+  char magic[8];
+  uint32_t hdr[2];
+  fsuae_net_desc desc;
+  std::vector<float> blob;
+  bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, "FSUAEENG", 8) == 0 && fread(hdr, 4, 2, f) == 2 &&
+            hdr[0] == FSUAE_ABI_VERSION && fread(&desc, sizeof(desc), 1, f) == 1;
+  if (ok) {
+    blob.resize(hdr[1]);
+    ok = fread(blob.data(), 4, blob.size(), f) == blob.size();
+  }
+  fclose(f);
+  if (!ok) return set_error(nullptr, FSUAE_ERR_INVALID, std::string("malformed engine file ") + path);
+  return fsuae_engine_create(&desc, blob.data(), blob.size(), device, precision, height, width, max_chunk_frames, out);
 }
 
 int fsuae_engine_destroy(fsuae_engine* e) {
@@ -258,8 +281,8 @@ int fsuae_engine_run_host(fsuae_engine* e, const void* in_host, void* out_host, 
   size_t in_fb = fmt_frame_bytes(in_fmt, e->H, e->W), out_fb = fmt_frame_bytes(out_fmt, e->H, e->W);
   int it = 0;
   rc = FSUAE_OK;
-  for (int f0 = 0; f0 < n_frames && rc == FSUAE_OK; f0 += e->chunk, ++it) {
-    int n = std::min(e->chunk, n_frames - f0);
+  for (int f0 = 0; f0 < n_frames && rc == FSUAE_OK; f0 += e->host_chunk, ++it) {
+    int n = std::min(e->host_chunk, n_frames - f0);
     int b = it & 1;
     cudaError_t ce = cudaSuccess;
     if (it >= 2) ce = cudaStreamWaitEvent(e->s_in, e->ev_out[b], 0);  // staging pair b is free again

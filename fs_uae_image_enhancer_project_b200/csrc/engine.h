@@ -21,6 +21,7 @@ struct fsuae_engine {
   int precision = 0;
   int H = 0, W = 0;          // full-resolution frame
   int chunk = 1;             // frames per internal pass
+  int host_chunk = 1;        // frames per stage of the host-buffer pipeline
   int sm_count = 148;
   std::string variant;
   std::string last_error;

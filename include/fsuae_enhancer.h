@@ -154,6 +154,12 @@ FSUAE_API int fsuae_abi_version(void);
 FSUAE_API int fsuae_engine_create(const fsuae_net_desc* desc, const float* blob, size_t blob_floats,
                         int device, int precision, int height, int width, int max_chunk_frames,
                         fsuae_engine** out);
+/* Same, from an engine file written by fs_uae_image_enhancer_project_b200/export.py
+ * (bytes: "FSUAEENG" | uint32 abi | uint32 blob_floats | fsuae_net_desc | float32 blob): the
+ * counterpart of loading the exported .onnx at deploy time
+ * (convertion_tools/convert_raw_to_png_using_final_model.py:66). */
+FSUAE_API int fsuae_engine_create_from_file(const char* path, int device, int precision, int height, int width,
+                                  int max_chunk_frames, fsuae_engine** out);
 FSUAE_API int fsuae_engine_destroy(fsuae_engine* e);
 
 /* Asynchronous: enqueue the forward of n_frames frames on `cuda_stream` (a cudaStream_t).

@@ -176,3 +176,36 @@ def test_onnx_wire_reader_roundtrip(tmp_path):
     p.write_bytes(model)
     inits, nodes = ow.read_onnx_initializers(str(p))
     assert np.array_equal(inits["conv1.bias"], arr) and nodes == [("PRelu", ["x", "conv1.bias"], ["y"])]
+
+
+def test_engine_file_roundtrip_and_create_from_file_errors(tmp_path):
+    from fs_uae_image_enhancer_project_b200 import _lib, export, model_pix_shuffle
+    import ctypes as C
+    m = model_pix_shuffle.get_model("lightweight")
+    path = str(tmp_path / "light.fsuae")
+    n = export.export_engine_file(m, path)
+    assert n == os.path.getsize(path)
+    desc, blob = export.read_engine_file(path)
+    assert desc.n_layers == 7 and blob.size >= 136602
+    lib = _lib.load()
+    h = C.c_void_p()
+    rc = lib.fsuae_engine_create_from_file(path.encode(), 0, _lib.PREC_FP32, 576, 752, 4, C.byref(h))
+    if not torch.cuda.is_available():
+        assert rc == _lib.ERR_NO_DEVICE                      # parsed fine, then refused: no CPU path
+    bad = tmp_path / "bad.fsuae"
+    bad.write_bytes(b"NOTANENGINE" * 10)
+    assert lib.fsuae_engine_create_from_file(str(bad).encode(), 0, _lib.PREC_FP32, 576, 752, 4, C.byref(h)) == _lib.ERR_INVALID
+    assert b"malformed" in lib.fsuae_last_error(None)
+    with pytest.raises(ValueError):
+        export.read_engine_file(str(bad))
+
+
+def test_raw_framebuffer_loader_validates_size(tmp_path):
+    from fs_uae_image_enhancer_project_b200 import raw_framebuffer
+    p = tmp_path / "f.raw"
+    np.zeros(752 * 576 * 4 * 2, np.uint8).tofile(p)
+    assert raw_framebuffer.load_raw_rgba(str(p)).shape == (2, 576, 752, 4)
+    np.zeros(1000, np.uint8).tofile(p)
+    with pytest.raises(ValueError, match="Expected raw file"):
+        raw_framebuffer.load_raw_rgba(str(p))
+    assert raw_framebuffer.main(["missing.pt", str(p)]) == 1      # reference tool: print + exit 1

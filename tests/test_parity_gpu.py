@@ -259,3 +259,47 @@ def test_bf16_unsupported_network_fails_loudly():
     with pytest.raises(_lib.EngineError) as ei:
         m(torch.rand(1, 3, 16, 16, device=dev()))
     assert ei.value.code == _lib.ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("grid", [1, 2, 3, 5, 7])
+def test_bf16_partition_independence(grid, monkeypatch):
+    """The persistent CTAs split the strip rows into contiguous ranges; any CTA count must give the
+    same bits (regression: a 2-row segment followed by a longer one once read a stale ring row)."""
+    spec = O.pix_shuffle_preset("lightweight")
+    sd = O.make_pix_shuffle_state_dict(spec, 61)
+    x = torch.rand(1, 3, 8, 752, generator=torch.Generator().manual_seed(5))
+    m = _bf16_model(spec, sd)
+    base = m(x.to(dev())).cpu()
+    assert (base - O.pix_shuffle_forward(sd, spec, x)).abs().max().item() <= BF16_TOL
+    monkeypatch.setenv("FSUAE_DEBUG_GRID", str(grid))
+    assert torch.equal(m(x.to(dev())).cpu(), base)
+
+
+def test_engine_file_and_raw_cli_match_the_module(tmp_path):
+    """Deploy path: engine file -> fsuae_engine_create_from_file -> same bytes as the module; raw CLI works."""
+    import ctypes as C
+    from fs_uae_image_enhancer_project_b200 import _lib, export, raw_framebuffer
+    spec = O.pix_shuffle_preset("lightweight")
+    sd = O.make_pix_shuffle_state_dict(spec, 71)
+    m = build_pkg_pix_shuffle(spec, sd).to(dev())
+    fb = O.synth_framebuffers(2, seed=3, h=64, w=96)
+    want = m.forward_framebuffer(fb.to(dev())).cpu()
+    path = str(tmp_path / "m.fsuae")
+    export.export_engine_file(m, path)
+    lib = _lib.load()
+    h = C.c_void_p()
+    assert lib.fsuae_engine_create_from_file(path.encode(), 0, _lib.PREC_FP32, 64, 96, 4, C.byref(h)) == _lib.OK
+    out = torch.empty_like(fb)
+    flags = _lib.FLAG_GAMMA_IN | _lib.FLAG_GAMMA_OUT
+    assert lib.fsuae_engine_run_host(h, fb.data_ptr(), out.data_ptr(), 2, _lib.FMT_U8_NHWC4, _lib.FMT_U8_NHWC4, flags) == _lib.OK
+    lib.fsuae_engine_destroy(h)
+    assert torch.equal(out, want)
+    # raw CLI (reference: convert_raw_to_png_using_final_model.py)
+    raw = tmp_path / "frames.raw"
+    fb.numpy().tofile(raw)
+    wpath = tmp_path / "w.pt"
+    torch.save(sd, wpath)
+    outp = tmp_path / "out.raw"
+    assert raw_framebuffer.main([str(wpath), str(raw), str(outp), "--width", "96", "--height", "64", "--precision", "fp32"]) == 0
+    got = torch.from_numpy(np.fromfile(outp, dtype=np.uint8).reshape(2, 64, 96, 4))
+    assert torch.equal(got, want)
