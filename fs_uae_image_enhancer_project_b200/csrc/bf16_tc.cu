@@ -37,7 +37,7 @@ namespace {
 
 using namespace tc;
 
-constexpr int MAXC = 112;
+constexpr int MAXC = 128;           // widest N of one launch
 constexpr int STRIP = 126;            // valid output columns per strip row
 constexpr int MROWS = 128;            // MMA M = slots per strip row
 constexpr int PLANE_ROW = MROWS * 16; // bytes of one plane of one strip row
@@ -45,11 +45,12 @@ constexpr int SMEM_LIMIT = 232448 - 2048;
 constexpr int EPI_WG = 4;                       // epilogue warpgroups; group g owns accumulator stage g
 constexpr int NTHREADS = 64 + 128 * EPI_WG;
 
-enum { EPI_STORE = 0, EPI_TAIL_SHUFFLE = 1 };
+enum { EPI_STORE = 0, EPI_TAIL_SHUFFLE = 1, EPI_TAIL_PLAIN = 2 };
 
 struct LayerK {
   int Hw, Ww, PW, S, n_frames, n_blocks;   // n_blocks = n_frames * S * Hw strip rows, ordered (frame, strip, row)
-  int P0, P1, cout;
+  int P0, P1, cout;        // cout: channels this launch produces (a wide layer may be split over launches)
+  int out_planes, dst_plane0, skip_plane0, tail;   // planes written / first plane in dst / first residual plane in the ring / FSUAE_TAIL_*
   unsigned long long fs0, fs1, fs_skip, fs_dst;  // frame strides in bytes
   const unsigned char* src0;
   const unsigned char* src1;
@@ -199,7 +200,7 @@ struct SegIter {
 template <int PT, int NPAD, int COUT, int KIND, class EPI>
 __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_constant__ LayerK P) {
   using C = Cfg<PT, NPAD>;
-  constexpr int OUT_PLANES = (COUT + 7) / 8;
+  constexpr int OUT_PLANES = COUT > 0 ? (COUT + 7) / 8 : 1;   // COUT <= 0: channel count is a run-time parameter
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_w = smem;
   uint8_t* s_ring = smem + C::WBYTES;
@@ -321,7 +322,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
               b_lo += 3 * BSTEP;
             }
             if constexpr (REM == 2) {
-              umma_bf16(d_tmem, ((uint64_t)HI << 32) | (a_lo | L16), ((uint64_t)HI << 32) | b_lo, IDESC, 1);
+              umma_bf16(d_tmem, ((uint64_t)HI << 32) | (a_lo | L16), ((uint64_t)HI << 32) | b_lo, IDESC, acc);
+              acc = 1;
               umma_bf16(d_tmem, ((uint64_t)HI << 32) | ((a_lo + 1) | L16), ((uint64_t)HI << 32) | (b_lo + BSTEP), IDESC, 1);
               b_lo += 2 * BSTEP;
             }
@@ -392,30 +394,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
         }
         mbar_wait(&tfull[stage], spar);
         tc_fence_after();
-        uint4 sk[EPI::kSkip ? OUT_PLANES : 1];
-        if constexpr (EPI::kSkip) {
-          // residual = this layer's input at the same pixel = centre row of the block, still in the ring.
-          // Only touch the ring barriers AFTER tfull: the block's MMAs have consumed rows kc-1..kc+1, so their
-          // fills are complete and cannot be overtaken before we arrive on `empty` -- a waiter that ran a whole
-          // phase ahead of an mbarrier would see its parity test pass on the wrong fill.
-          const uint32_t kc = qrow + (uint32_t)b + 1;
-          const uint32_t slot = kc % C::RING;
-          mbar_wait(&full[slot], (kc / C::RING) & 1);     // already complete: acquires the TMA-written bytes
-          const uint8_t* sp = s_ring + slot * C::ROWBYTES + (m + 1) * 16;
-#pragma unroll
-          for (int c = 0; c < OUT_PLANES; ++c)
-            sk[c] = valid ? *reinterpret_cast<const uint4*>(sp + c * PLANE_ROW) : make_uint4(0, 0, 0, 0);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + stage * NPAD;
+        // residual = this layer's input at the same pixel = centre row of the block, still in the ring.
+        // Only touch the ring barriers AFTER tfull: the block's MMAs have consumed rows kc-1..kc+1, so their
+        // fills are complete and cannot be overtaken before we arrive on `empty` -- a waiter that ran a whole
+        // phase ahead of an mbarrier would see its parity test pass on the wrong fill.
+        const uint32_t kc = qrow + (uint32_t)b + 1;
+        const uint32_t cslot = kc % C::RING;
+        const uint8_t* sp = s_ring + cslot * C::ROWBYTES + (size_t)P.skip_plane0 * PLANE_ROW + (m + 1) * 16;
+        if constexpr (EPI::kSkip) mbar_wait(&full[cslot], (kc / C::RING) & 1);   // already complete: acquires the TMA bytes
+        auto release_rows = [&]() {
           __syncwarp();
           if (lane == 0) {
-            mbar_arrive(&empty[slot]);
+            mbar_arrive(&empty[cslot]);
             if (b == 0) mbar_arrive(&empty[(kc - 1) % C::RING]);          // first row of the segment: no block centres on it
             if (b == rows - 1) mbar_arrive(&empty[(kc + 1) % C::RING]);   // nor on the last one
           }
-        }
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + stage * NPAD;
+        };
 
-        if constexpr (KIND == EPI_STORE) {
-          unsigned char* dp = P.dst + (size_t)f * P.fs_dst + pix;
+        if constexpr (KIND == EPI_STORE && COUT > 0) {
+          // ---- compile-time channel count (flagship preset): fully unrolled, parameters from the constant bank ----
+          uint4 sk[EPI::kSkip ? OUT_PLANES : 1];
+          if constexpr (EPI::kSkip) {
+#pragma unroll
+            for (int c = 0; c < OUT_PLANES; ++c)
+              sk[c] = valid ? *reinterpret_cast<const uint4*>(sp + c * PLANE_ROW) : make_uint4(0, 0, 0, 0);
+            release_rows();
+          }
+          unsigned char* dp = P.dst + (size_t)f * P.fs_dst + pix + (size_t)P.dst_plane0 * plane_pitch;
 #pragma unroll
           for (int c = 0; c < OUT_PLANES; ++c) {
             uint32_t v[8];
@@ -438,6 +444,62 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
               uint4 pk = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
                                     pack_bf16x2(o[6], o[7]));
               *reinterpret_cast<uint4*>(dp + (size_t)c * plane_pitch) = pk;
+            }
+          }
+        } else if constexpr (KIND == EPI_STORE) {
+          // ---- run-time channel count / op-codes (every other network) ----
+          unsigned char* dp = P.dst + (size_t)f * P.fs_dst + pix + (size_t)P.dst_plane0 * plane_pitch;
+          for (int c = 0; c < P.out_planes; ++c) {
+            uint4 skc = make_uint4(0, 0, 0, 0);
+            if constexpr (EPI::kSkip) {
+              if (valid) skc = *reinterpret_cast<const uint4*>(sp + c * PLANE_ROW);
+            }
+            uint32_t v[8];
+            tmem_ld_x8(taddr + c * 8, v);
+            tmem_ld_wait();
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int ch = c * 8 + i;
+              float t = 0.f;
+              if (ch < P.cout) {
+                t = EPI::pre(P, ch, __uint_as_float(v[i]) + P.bias[ch]);
+                if constexpr (EPI::kSkip) {
+                  const uint32_t w = (&skc.x)[i >> 1];
+                  t += (i & 1) ? bf16_hi(w) : bf16_lo(w);
+                }
+                t = EPI::post(P, ch, t);
+              }
+              o[i] = t;
+            }
+            if (valid) {
+              uint4 pk = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                                    pack_bf16x2(o[6], o[7]));
+              *reinterpret_cast<uint4*>(dp + (size_t)c * plane_pitch) = pk;
+            }
+          }
+          if constexpr (EPI::kSkip) release_rows();
+        } else if constexpr (KIND == EPI_TAIL_PLAIN) {
+          // ---- 3-channel full-resolution tail (conv5: as is; conv3: x255 + alpha) straight to the frame ----
+          uint32_t v[8];
+          tmem_ld_x8(taddr, v);
+          tmem_ld_wait();
+          float o[3];
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) o[ch] = EPI::post(P, ch, EPI::pre(P, ch, __uint_as_float(v[ch]) + P.bias[ch]));
+          if (valid) {
+            const size_t fpl = (size_t)P.H * P.W;
+            const size_t p0 = (size_t)y * P.W + x + P.xoff;
+            if (P.out_fmt == FSUAE_FMT_F32_NCHW3) {
+              float* op = (float*)P.frame_out + (size_t)f * 3 * fpl + p0;
+              op[0] = o[0]; op[fpl] = o[1]; op[2 * fpl] = o[2];
+            } else if (P.out_fmt == FSUAE_FMT_F32_NCHW4) {     // model_conv3.py:145-153
+              float* op = (float*)P.frame_out + (size_t)f * 4 * fpl + p0;
+              op[0] = o[0] * 255.0f; op[fpl] = o[1] * 255.0f; op[2 * fpl] = o[2] * 255.0f; op[3 * fpl] = 255.0f;
+            } else {
+              const uint32_t px = (uint32_t)to_u8_fast(o[0], P.gamma_out) | ((uint32_t)to_u8_fast(o[1], P.gamma_out) << 8) |
+                                  ((uint32_t)to_u8_fast(o[2], P.gamma_out) << 16) | 0xFF000000u;
+              *reinterpret_cast<uint32_t*>((unsigned char*)P.frame_out + ((size_t)f * fpl + p0) * 4) = px;
             }
           }
         } else {
@@ -543,6 +605,39 @@ __global__ void head_unshuffle_bf16_kernel(const void* __restrict__ in, unsigned
   }
 }
 
+// head for the full-resolution families (conv3 / conv5): 3 channels -> one plane (5 zero channels)
+__global__ void head_plain_bf16_kernel(const void* __restrict__ in, unsigned char* __restrict__ dst, int n_frames, int in_fmt,
+                                       int H, int W, int xoff, int Hw, int Ww, int PW, unsigned long long fs_dst, int gamma_in) {
+  __shared__ float lut[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    float t = (float)i * (1.0f / 255.0f);
+    lut[i] = gamma_in ? powf(t, 2.2f) : t;
+  }
+  __syncthreads();
+  const size_t plane = (size_t)Hw * Ww, total = (size_t)n_frames * plane;
+  const size_t fpl = (size_t)H * W;
+  const size_t row_pitch = (size_t)PW * 16;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int f = (int)(idx / plane);
+    const int r = (int)(idx - (size_t)f * plane);
+    const int h = r / Ww, w = r - h * Ww;
+    const size_t p0 = (size_t)h * W + w + xoff;
+    float v[3];
+    if (in_fmt == FSUAE_FMT_F32_NCHW3) {
+      const float* ip = (const float*)in + (size_t)f * 3 * fpl + p0;
+      v[0] = ip[0]; v[1] = ip[fpl]; v[2] = ip[2 * fpl];
+    } else if (in_fmt == FSUAE_FMT_U8_NHWC4) {
+      const uint32_t t = *reinterpret_cast<const uint32_t*>((const unsigned char*)in + ((size_t)f * fpl + p0) * 4);
+      v[0] = lut[t & 0xFF]; v[1] = lut[(t >> 8) & 0xFF]; v[2] = lut[(t >> 16) & 0xFF];
+    } else {
+      const unsigned char* ip = (const unsigned char*)in + (size_t)f * 4 * fpl + p0;
+      v[0] = lut[ip[0]]; v[1] = lut[ip[fpl]]; v[2] = lut[ip[2 * fpl]];
+    }
+    unsigned char* dp = dst + (size_t)f * fs_dst + (size_t)(h + 1) * row_pitch + (size_t)(w + 1) * 16;
+    *reinterpret_cast<uint4*>(dp) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], 0.f), 0u, 0u);
+  }
+}
+
 __global__ void black_columns_bf16_kernel(void* __restrict__ out, int n_frames, int out_fmt, int H, int W, int ncols) {
   const size_t total = (size_t)n_frames * H * ncols;
   const size_t fplane = (size_t)H * W;
@@ -555,8 +650,9 @@ __global__ void black_columns_bf16_kernel(void* __restrict__ out, int n_frames, 
     if (out_fmt == FSUAE_FMT_U8_NHWC4) {
       ((uchar4*)out)[(size_t)f * fplane + pix] = make_uchar4(0, 0, 0, 255);
     } else {
-      float* o = (float*)out + (size_t)f * 3 * fplane + pix;
-      o[0] = 0.f; o[fplane] = 0.f; o[2 * fplane] = 0.f;
+      const int C = out_fmt == FSUAE_FMT_F32_NCHW4 ? 4 : 3;
+      float* o = (float*)out + (size_t)f * C * fplane + pix;
+      for (int c = 0; c < C; ++c) o[(size_t)c * fplane] = c == 3 ? 255.0f : 0.f;
     }
   }
 }
@@ -603,16 +699,20 @@ std::vector<uint16_t> pack_weights(const float* w, int cout, int cin0, int cin1,
 typedef void (*KernelFn)(const LayerK);
 
 struct Variant {
-  int PT, NPAD, COUT, KIND;
-  int pre0, pre1, post0, post1, skip;   // -1 = generic (runtime op-codes)
+  int PT, NPAD, COUT, KIND;             // COUT <= 0: run-time channel count
+  int pre0, pre1, post0, post1, skip;   // -1 = run-time op-codes
   KernelFn fn;
   int smem;
 };
 
-template <int PT, int NPAD, int OP, int KIND, class EPI>
+template <int PT, int NPAD, int COUT, int KIND, class EPI>
 Variant make_variant(int a, int b, int c, int d, int skip) {
-  Variant v{PT, NPAD, OP, KIND, a, b, c, d, skip, conv3x3_tc_kernel<PT, NPAD, OP, KIND, EPI>, Cfg<PT, NPAD>::SMEM};
+  Variant v{PT, NPAD, COUT, KIND, a, b, c, d, skip, conv3x3_tc_kernel<PT, NPAD, COUT, KIND, EPI>, Cfg<PT, NPAD>::SMEM};
   return v;
+}
+template <int PT, int NPAD, int KIND, bool SKIP>
+Variant generic_variant() {
+  return make_variant<PT, NPAD, -1, KIND, Epi<-1, -1, -1, -1, SKIP>>(-1, -1, -1, -1, SKIP ? 1 : 0);
 }
 
 #define A(x) FSUAE_ACT_##x
@@ -626,124 +726,44 @@ const std::vector<Variant>& variants() {
       make_variant<9, 48, 36, EPI_STORE, Epi<0, 0, 0, 0, false>>(0, 0, 0, 0, 0),
       make_variant<10, 48, 36, EPI_STORE, Epi<A(MISH), A(RELU6), 0, 0, false>>(A(MISH), A(RELU6), 0, 0, 0),
       make_variant<5, 16, 12, EPI_TAIL_SHUFFLE, Epi<A(BIASED_PRELU), 0, 0, 0, false>>(A(BIASED_PRELU), 0, 0, 0, 0),
-      // ---- generic epilogues (any activation chain of the registry except channel softmax) ----
-      make_variant<2, 48, 36, EPI_STORE, Epi<-1, -1, -1, -1, false>>(-1, -1, -1, -1, 0),
-      make_variant<5, 48, 36, EPI_STORE, Epi<-1, -1, -1, -1, false>>(-1, -1, -1, -1, 0),
-      make_variant<5, 48, 36, EPI_STORE, Epi<-1, -1, -1, -1, true>>(-1, -1, -1, -1, 1),
-      make_variant<5, 80, 72, EPI_STORE, Epi<-1, -1, -1, -1, false>>(-1, -1, -1, -1, 0),
-      make_variant<9, 80, 72, EPI_STORE, Epi<-1, -1, -1, -1, true>>(-1, -1, -1, -1, 1),
-      make_variant<9, 80, 72, EPI_STORE, Epi<-1, -1, -1, -1, false>>(-1, -1, -1, -1, 0),
-      make_variant<9, 48, 36, EPI_STORE, Epi<-1, -1, -1, -1, false>>(-1, -1, -1, -1, 0),
-      make_variant<10, 48, 36, EPI_STORE, Epi<-1, -1, -1, -1, false>>(-1, -1, -1, -1, 0),
-      make_variant<5, 16, 12, EPI_TAIL_SHUFFLE, Epi<-1, -1, -1, -1, false>>(-1, -1, -1, -1, 0),
+      // ---- run-time epilogues: any activation chain of the registry (except channel softmax), any Cout <= NPAD ----
+      // pix_shuffle channel plans (36/72 and the heavyweight 108)
+      generic_variant<2, 48, EPI_STORE, false>(), generic_variant<5, 48, EPI_STORE, false>(), generic_variant<5, 48, EPI_STORE, true>(),
+      generic_variant<5, 80, EPI_STORE, false>(), generic_variant<9, 80, EPI_STORE, true>(), generic_variant<9, 80, EPI_STORE, false>(),
+      generic_variant<9, 48, EPI_STORE, false>(), generic_variant<10, 48, EPI_STORE, false>(),
+      generic_variant<5, 112, EPI_STORE, false>(), generic_variant<14, 48, EPI_STORE, true>(), generic_variant<14, 48, EPI_STORE, false>(),
+      generic_variant<5, 16, EPI_TAIL_SHUFFLE, false>(),
+      // conv3 / conv5 lightweight (32/64) and conv5 heavyweight (64/128)
+      generic_variant<1, 32, EPI_STORE, false>(), generic_variant<4, 64, EPI_STORE, false>(), generic_variant<4, 32, EPI_STORE, true>(),
+      generic_variant<8, 64, EPI_STORE, true>(), generic_variant<1, 64, EPI_STORE, false>(), generic_variant<8, 128, EPI_STORE, false>(),
+      generic_variant<16, 32, EPI_STORE, true>(),
+      generic_variant<8, 16, EPI_TAIL_PLAIN, false>(), generic_variant<16, 16, EPI_TAIL_PLAIN, false>(),
   };
   return v;
 }
 #undef A
 
-struct LayerPlan {
+struct Launch {
   const Variant* var = nullptr;
   unsigned char* d_w = nullptr;
-  int P0 = 0, P1 = 0, NPAD = 0, out_planes = 0;
   LayerK k{};   // geometry-independent fields prefilled
+};
+
+struct LayerPlan {
+  std::vector<Launch> launches;   // a wide layer is split over output-channel groups (A is re-read per group)
 };
 
 }  // namespace
 
 struct Bf16Plan {
   std::vector<LayerPlan> layers;
-  std::vector<unsigned char*> buf;     // chunk-planar activation buffers, id 0..n_layers-1 (last layer writes the frame)
+  std::vector<unsigned char*> buf;     // chunk-planar activation buffers, id 0..n_layers-1 (the last layer writes the frame)
   std::vector<int> planes;
   std::vector<size_t> buf_bytes;
   int zero_Hw = -1, zero_Ww = -1;      // geometry the borders are currently valid for
 };
 
 static int planes_of(int c) { return (c + 7) / 8; }
-
-int bf16_create(fsuae_engine* e) {
-  const fsuae_net_desc& d = e->desc;
-  if (d.head != FSUAE_HEAD_UNSHUFFLE2 || d.tail != FSUAE_TAIL_SHUFFLE2_RESIDUAL_RELU)
-    return set_error(e, FSUAE_ERR_UNSUPPORTED, "bf16 build: only the pix_shuffle family (unshuffle head / shuffle tail) is implemented");
-  Bf16Plan* plan = new Bf16Plan();
-  e->bf16 = plan;
-  std::vector<int> ch(d.n_layers + 1);
-  ch[0] = 12;
-  for (int i = 0; i < d.n_layers; ++i) ch[i + 1] = d.layers[i].cout;
-
-  plan->layers.resize(d.n_layers);
-  for (int i = 0; i < d.n_layers; ++i) {
-    const fsuae_layer_desc& L = d.layers[i];
-    LayerPlan& lp = plan->layers[i];
-    const bool last = i == d.n_layers - 1;
-    lp.P0 = planes_of(L.cin0);
-    lp.P1 = L.cin1 > 0 ? planes_of(L.cin1) : 0;
-    lp.NPAD = (L.cout + 15) / 16 * 16;
-    lp.out_planes = planes_of(L.cout);
-    if (L.cout > MAXC) return set_error(e, FSUAE_ERR_UNSUPPORTED, "bf16 build: more than 112 output channels");
-    int ops[4] = {0, 0, 0, 0};
-    for (int k = 0; k < L.n_pre + L.n_post; ++k) {
-      const fsuae_act_desc& a = k < L.n_pre ? L.pre[k] : L.post[k - L.n_pre];
-      if (act_is_softmax(a.op)) return set_error(e, FSUAE_ERR_UNSUPPORTED, "bf16 build: channel softmax slots are not implemented (use the fp32 build)");
-    }
-    if (L.n_pre > 2 || L.n_post > 2) return set_error(e, FSUAE_ERR_UNSUPPORTED, "bf16 build: at most 2 activation slots before and after the skip add");
-    for (int k = 0; k < L.n_pre; ++k) ops[k] = L.pre[k].op;
-    for (int k = 0; k < L.n_post; ++k) ops[2 + k] = L.post[k].op;
-    const int kind = last ? EPI_TAIL_SHUFFLE : EPI_STORE;
-    const int skip = L.skip_src >= 0 ? 1 : 0;
-    if (skip && (L.skip_src != L.src0 || L.cin1 > 0))
-      return set_error(e, FSUAE_ERR_UNSUPPORTED, "bf16 build: the residual must be the layer's own input (true for every reference model)");
-    const Variant* exact = nullptr;
-    const Variant* generic = nullptr;
-    for (const Variant& v : variants()) {
-      if (v.PT != lp.P0 + lp.P1 || v.NPAD != lp.NPAD || v.COUT != L.cout || v.KIND != kind || v.skip != skip) continue;
-      if (v.pre0 == ops[0] && v.pre1 == ops[1] && v.post0 == ops[2] && v.post1 == ops[3]) exact = &v;
-      if (v.pre0 == -1) generic = &v;
-    }
-    lp.var = exact ? exact : generic;
-    if (!lp.var)
-      return set_error(e, FSUAE_ERR_UNSUPPORTED,
-                       "bf16 build: no tensor-core kernel instantiated for layer " + std::to_string(i + 1) + " (planes " +
-                           std::to_string(lp.P0 + lp.P1) + ", N " + std::to_string(lp.NPAD) + "); use the fp32 build");
-    // weights
-    std::vector<uint16_t> wp = pack_weights(e->h_blob.data() + L.w_off, L.cout, L.cin0, L.cin1, lp.P0, lp.P1, lp.NPAD);
-    FSUAE_CUDA_CHECK(e, cudaMalloc(&lp.d_w, wp.size() * 2));
-    FSUAE_CUDA_CHECK(e, cudaMemcpy(lp.d_w, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
-    e->device_bytes += wp.size() * 2;
-    FSUAE_CUDA_CHECK(e, cudaFuncSetAttribute((const void*)lp.var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, lp.var->smem));
-    // epilogue parameters, expanded per channel
-    LayerK& k = lp.k;
-    std::memset(&k, 0, sizeof(k));
-    k.P0 = lp.P0; k.P1 = lp.P1; k.cout = L.cout;
-    k.wpack = lp.d_w;
-    k.n_pre = L.n_pre; k.n_post = L.n_post;
-    for (int c = 0; c < MAXC; ++c) k.bias[c] = (c < L.cout && L.b_off >= 0) ? e->h_blob[L.b_off + c] : 0.f;
-    for (int s = 0; s < 4; ++s) {
-      k.op[s] = ops[s];
-      const fsuae_act_desc* a = nullptr;
-      if (s < 2 && s < L.n_pre) a = &L.pre[s];
-      if (s >= 2 && s - 2 < L.n_post) a = &L.post[s - 2];
-      for (int c = 0; c < MAXC; ++c) {
-        k.p0[s][c] = (a && a->n0 > 0) ? e->h_blob[a->p0_off + (a->n0 == 1 ? 0 : std::min(c, a->n0 - 1))] : 0.f;
-        k.p1[s][c] = (a && a->n1 > 0) ? e->h_blob[a->p1_off + (a->n1 == 1 ? 0 : std::min(c, a->n1 - 1))] : 0.f;
-      }
-    }
-  }
-  // activation buffers at the largest geometry (no crop)
-  const int Hw = e->H / 2, Ww = e->W / 2;
-  const int S = (Ww + STRIP - 1) / STRIP, PW = STRIP * (S - 1) + MROWS;
-  plan->buf.assign(d.n_layers, nullptr);
-  plan->planes.assign(d.n_layers, 0);
-  plan->buf_bytes.assign(d.n_layers, 0);
-  for (int i = 0; i < d.n_layers; ++i) {
-    plan->planes[i] = i == 0 ? 2 : planes_of(ch[i]);
-    size_t bytes = (size_t)e->chunk * plan->planes[i] * (Hw + 2) * PW * 16 + 256;
-    FSUAE_CUDA_CHECK(e, cudaMalloc(&plan->buf[i], bytes));
-    plan->buf_bytes[i] = bytes;
-    e->device_bytes += bytes;
-  }
-  e->variant = "bf16_tcgen05";
-  return FSUAE_OK;
-}
 
 // debugging aid (not part of the public header): raw chunk-planar bytes of activation buffer `id`
 extern "C" __attribute__((visibility("default"))) long long fsuae_debug_read_bf16_buffer(fsuae_engine* e, int id, void* dst,
@@ -755,10 +775,109 @@ extern "C" __attribute__((visibility("default"))) long long fsuae_debug_read_bf1
   return n;
 }
 
+int bf16_create(fsuae_engine* e) {
+  const fsuae_net_desc& d = e->desc;
+  const bool unshuffle = d.head == FSUAE_HEAD_UNSHUFFLE2;
+  Bf16Plan* plan = new Bf16Plan();
+  e->bf16 = plan;
+  std::vector<int> ch(d.n_layers + 1);
+  ch[0] = unshuffle ? 12 : 3;
+  for (int i = 0; i < d.n_layers; ++i) ch[i + 1] = d.layers[i].cout;
+
+  plan->layers.resize(d.n_layers);
+  for (int i = 0; i < d.n_layers; ++i) {
+    const fsuae_layer_desc& L = d.layers[i];
+    LayerPlan& lp = plan->layers[i];
+    const bool last = i == d.n_layers - 1;
+    const std::string tag = "bf16 build: layer " + std::to_string(i + 1) + ": ";
+    const int P0 = planes_of(L.cin0), P1 = L.cin1 > 0 ? planes_of(L.cin1) : 0, PT = P0 + P1;
+    int ops[4] = {0, 0, 0, 0};
+    for (int k = 0; k < L.n_pre + L.n_post; ++k) {
+      const fsuae_act_desc& a = k < L.n_pre ? L.pre[k] : L.post[k - L.n_pre];
+      if (act_is_softmax(a.op)) return set_error(e, FSUAE_ERR_UNSUPPORTED, tag + "channel softmax slots are not implemented (use the fp32 build)");
+    }
+    if (L.n_pre > 2 || L.n_post > 2) return set_error(e, FSUAE_ERR_UNSUPPORTED, tag + "at most 2 activation slots before and after the skip add");
+    for (int k = 0; k < L.n_pre; ++k) ops[k] = L.pre[k].op;
+    for (int k = 0; k < L.n_post; ++k) ops[2 + k] = L.post[k].op;
+    const int kind = !last ? EPI_STORE : (d.tail == FSUAE_TAIL_SHUFFLE2_RESIDUAL_RELU ? EPI_TAIL_SHUFFLE : EPI_TAIL_PLAIN);
+    const int skip = L.skip_src >= 0 ? 1 : 0;
+    if (skip && (L.skip_src != L.src0 || L.cin1 > 0))
+      return set_error(e, FSUAE_ERR_UNSUPPORTED, tag + "the residual must be the layer's own input (true for every reference model)");
+
+    // pick the kernel: exact compile-time epilogue if there is one, else the run-time one; a layer wider than the
+    // widest instantiated N for its input plane count is split into output-channel groups
+    const int need = (L.cout + 15) / 16 * 16;
+    const Variant* exact = nullptr;
+    const Variant* fit = nullptr;    // smallest generic NPAD >= need
+    const Variant* widest = nullptr; // widest generic NPAD
+    for (const Variant& v : variants()) {
+      if (v.PT != PT || v.KIND != kind || v.skip != skip) continue;
+      if (v.COUT == L.cout && v.pre0 == ops[0] && v.pre1 == ops[1] && v.post0 == ops[2] && v.post1 == ops[3]) exact = &v;
+      if (v.pre0 != -1) continue;
+      if (v.NPAD >= need && (!fit || v.NPAD < fit->NPAD)) fit = &v;
+      if (!widest || v.NPAD > widest->NPAD) widest = &v;
+    }
+    const Variant* var = exact ? exact : (fit ? fit : widest);
+    if (!var || (kind != EPI_STORE && var->NPAD < need))
+      return set_error(e, FSUAE_ERR_UNSUPPORTED,
+                       tag + "no tensor-core kernel instantiated for " + std::to_string(PT) + " input planes / " +
+                           std::to_string(L.cout) + " output channels; use the fp32 build");
+    for (int c0 = 0; c0 < L.cout; c0 += var->NPAD) {
+      const int cg = std::min(var->NPAD, L.cout - c0);
+      Launch ln;
+      ln.var = var;
+      std::vector<uint16_t> wp = pack_weights(e->h_blob.data() + L.w_off + (size_t)c0 * (L.cin0 + L.cin1) * 9, cg, L.cin0,
+                                              L.cin1, P0, P1, var->NPAD);
+      FSUAE_CUDA_CHECK(e, cudaMalloc(&ln.d_w, wp.size() * 2));
+      FSUAE_CUDA_CHECK(e, cudaMemcpy(ln.d_w, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
+      e->device_bytes += wp.size() * 2;
+      LayerK& k = ln.k;
+      std::memset(&k, 0, sizeof(k));
+      k.P0 = P0; k.P1 = P1; k.cout = cg;
+      k.out_planes = planes_of(cg);
+      k.dst_plane0 = c0 / 8;
+      k.skip_plane0 = c0 / 8;
+      k.tail = d.tail;
+      k.wpack = ln.d_w;
+      k.n_pre = L.n_pre; k.n_post = L.n_post;
+      for (int c = 0; c < MAXC; ++c) k.bias[c] = (c < cg && L.b_off >= 0) ? e->h_blob[L.b_off + c0 + c] : 0.f;
+      for (int s = 0; s < 4; ++s) {
+        k.op[s] = ops[s];
+        const fsuae_act_desc* a = nullptr;
+        if (s < 2 && s < L.n_pre) a = &L.pre[s];
+        if (s >= 2 && s - 2 < L.n_post) a = &L.post[s - 2];
+        for (int c = 0; c < MAXC; ++c) {
+          const int cc = std::min(c0 + c, L.cout - 1);
+          k.p0[s][c] = (a && a->n0 > 0) ? e->h_blob[a->p0_off + (a->n0 == 1 ? 0 : cc)] : 0.f;
+          k.p1[s][c] = (a && a->n1 > 0) ? e->h_blob[a->p1_off + (a->n1 == 1 ? 0 : cc)] : 0.f;
+        }
+      }
+      lp.launches.push_back(ln);
+    }
+    FSUAE_CUDA_CHECK(e, cudaFuncSetAttribute((const void*)var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, var->smem));
+  }
+  // activation buffers at the largest geometry (no crop)
+  const int Hw = unshuffle ? e->H / 2 : e->H, Ww = unshuffle ? e->W / 2 : e->W;
+  const int S = (Ww + STRIP - 1) / STRIP, PW = STRIP * (S - 1) + MROWS;
+  plan->buf.assign(d.n_layers, nullptr);
+  plan->planes.assign(d.n_layers, 0);
+  plan->buf_bytes.assign(d.n_layers, 0);
+  for (int i = 0; i < d.n_layers; ++i) {
+    plan->planes[i] = i == 0 ? (unshuffle ? 2 : 1) : planes_of(ch[i]);
+    size_t bytes = (size_t)e->chunk * plan->planes[i] * (Hw + 2) * PW * 16 + 256;
+    FSUAE_CUDA_CHECK(e, cudaMalloc(&plan->buf[i], bytes));
+    plan->buf_bytes[i] = bytes;
+    e->device_bytes += bytes;
+  }
+  e->variant = "bf16_tcgen05";
+  return FSUAE_OK;
+}
+
 void bf16_destroy(fsuae_engine* e) {
   if (!e->bf16) return;
   for (auto& lp : e->bf16->layers)
-    if (lp.d_w) cudaFree(lp.d_w);
+    for (auto& ln : lp.launches)
+      if (ln.d_w) cudaFree(ln.d_w);
   for (unsigned char* p : e->bf16->buf)
     if (p) cudaFree(p);
   delete e->bf16;
@@ -778,38 +897,44 @@ int bf16_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in
   }
   auto fstride = [&](int id) { return (unsigned long long)plan->planes[id] * (g.Hw + 2) * PW * 16; };
 
-  head_unshuffle_bf16_kernel<<<e->sm_count * 8, 256, 0, st>>>(in, plan->buf[0], n, in_fmt, g.H, g.W, g.xoff, g.Hw, g.Ww, PW,
-                                                              fstride(0), (flags & FSUAE_FLAG_GAMMA_IN) ? 1 : 0);
+  const int gin = (flags & FSUAE_FLAG_GAMMA_IN) ? 1 : 0;
+  if (d.head == FSUAE_HEAD_UNSHUFFLE2)
+    head_unshuffle_bf16_kernel<<<e->sm_count * 8, 256, 0, st>>>(in, plan->buf[0], n, in_fmt, g.H, g.W, g.xoff, g.Hw, g.Ww, PW,
+                                                                fstride(0), gin);
+  else
+    head_plain_bf16_kernel<<<e->sm_count * 8, 256, 0, st>>>(in, plan->buf[0], n, in_fmt, g.H, g.W, g.xoff, g.Hw, g.Ww, PW,
+                                                            fstride(0), gin);
   e->launches++;
 
   for (int i = 0; i < d.n_layers; ++i) {
     const fsuae_layer_desc& L = d.layers[i];
-    LayerPlan& lp = plan->layers[i];
-    LayerK k = lp.k;
-    k.Hw = g.Hw; k.Ww = g.Ww; k.PW = PW; k.S = S; k.n_frames = n;
-    k.n_blocks = n * S * g.Hw;
-    k.src0 = plan->buf[L.src0]; k.fs0 = fstride(L.src0);
-    if (L.cin1 > 0) { k.src1 = plan->buf[L.src1]; k.fs1 = fstride(L.src1); }
-    if (L.skip_src >= 0) { k.skip = plan->buf[L.skip_src]; k.fs_skip = fstride(L.skip_src); }
-    if (i < d.n_layers - 1) { k.dst = plan->buf[i + 1]; k.fs_dst = fstride(i + 1); }
-    k.frame_in = in; k.frame_out = out; k.in_fmt = in_fmt; k.out_fmt = out_fmt;
-    k.H = g.H; k.W = g.W; k.xoff = g.xoff;
-    k.gamma_in = (flags & FSUAE_FLAG_GAMMA_IN) ? 1 : 0;
-    k.gamma_out = (flags & FSUAE_FLAG_GAMMA_OUT) ? 1 : 0;
-    int grid = std::min(k.n_blocks, e->sm_count);
-    if (const char* g_env = getenv("FSUAE_DEBUG_GRID")) grid = std::max(1, std::min(k.n_blocks, atoi(g_env)));   // debugging aid: force the CTA count
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(NTHREADS);
-    cfg.dynamicSmemBytes = lp.var->smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    FSUAE_CUDA_CHECK(e, cudaLaunchKernelEx(&cfg, lp.var->fn, k));
-    e->launches++;
+    for (Launch& ln : plan->layers[i].launches) {
+      LayerK k = ln.k;
+      k.Hw = g.Hw; k.Ww = g.Ww; k.PW = PW; k.S = S; k.n_frames = n;
+      k.n_blocks = n * S * g.Hw;
+      k.src0 = plan->buf[L.src0]; k.fs0 = fstride(L.src0);
+      if (L.cin1 > 0) { k.src1 = plan->buf[L.src1]; k.fs1 = fstride(L.src1); }
+      if (L.skip_src >= 0) { k.skip = plan->buf[L.skip_src]; k.fs_skip = fstride(L.skip_src); }
+      if (i < d.n_layers - 1) { k.dst = plan->buf[i + 1]; k.fs_dst = fstride(i + 1); }
+      k.frame_in = in; k.frame_out = out; k.in_fmt = in_fmt; k.out_fmt = out_fmt;
+      k.H = g.H; k.W = g.W; k.xoff = g.xoff;
+      k.gamma_in = gin;
+      k.gamma_out = (flags & FSUAE_FLAG_GAMMA_OUT) ? 1 : 0;
+      int grid = std::min(k.n_blocks, e->sm_count);
+      if (const char* g_env = getenv("FSUAE_DEBUG_GRID")) grid = std::max(1, std::min(k.n_blocks, atoi(g_env)));   // debugging aid: force the CTA count
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(grid);
+      cfg.blockDim = dim3(NTHREADS);
+      cfg.dynamicSmemBytes = ln.var->smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      FSUAE_CUDA_CHECK(e, cudaLaunchKernelEx(&cfg, ln.var->fn, k));
+      e->launches++;
+    }
   }
   if (g.xoff > 0) {
     black_columns_bf16_kernel<<<64, 256, 0, st>>>(out, n, out_fmt, g.H, g.W, g.xoff);

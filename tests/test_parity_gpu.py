@@ -254,11 +254,63 @@ def test_bf16_full_size_float_and_batch_properties():
 
 
 def test_bf16_unsupported_network_fails_loudly():
-    from fs_uae_image_enhancer_project_b200 import _lib, model_conv5
-    m = model_conv5.get_model("lightweight").to(dev()).set_precision("bf16")
+    """conv3 heavyweight (192/256 channels: 48 KB ring rows) has no tensor-core kernel yet: explicit error, no fallback."""
+    from fs_uae_image_enhancer_project_b200 import _lib, model_conv3
+    m = model_conv3.get_model("heavyweight").to(dev()).set_precision("bf16")
     with pytest.raises(_lib.EngineError) as ei:
-        m(torch.rand(1, 3, 16, 16, device=dev()))
+        m(torch.zeros(1, 4, 16, 16, dtype=torch.uint8, device=dev()))
     assert ei.value.code == _lib.ERR_UNSUPPORTED
+    spec = gold_spec("vocab_b")                                   # channel softmax slot
+    mb = _bf16_model(spec, O.make_pix_shuffle_state_dict(spec, 1))
+    with pytest.raises(_lib.EngineError):
+        mb(torch.rand(1, 3, 16, 16, device=dev()))
+
+
+def test_bf16_pix_shuffle_heavyweight_matches_reference_vectors():
+    """108-channel conv4 is split over three output-channel groups (packed weights would not fit otherwise)."""
+    g = load_gold("pix_shuffle_heavyweight")
+    spec = gold_spec("heavyweight")
+    sd = O.make_pix_shuffle_state_dict(spec, int(g["seed"]))
+    got = _bf16_model(spec, sd)(torch.from_numpy(g["x"]).to(dev())).cpu()
+    want = torch.from_numpy(g["y"])
+    assert (got - want).abs().max().item() <= BF16_TOL and O.psnr(got, want, 1.0) >= BF16_PSNR
+    x = torch.rand(1, 3, 64, 600, generator=torch.Generator().manual_seed(4))      # three strips
+    got = _bf16_model(spec, sd)(x.to(dev())).cpu()
+    want = O.pix_shuffle_forward(sd, spec, x)
+    assert (got - want).abs().max().item() <= BF16_TOL and O.psnr(got, want, 1.0) >= BF16_PSNR
+
+
+def test_bf16_conv3_lightweight_matches_reference_vectors_and_screenshot():
+    from fs_uae_image_enhancer_project_b200 import model_conv3
+    g = load_gold("conv3_lightweight")
+    m = model_conv3.get_model("lightweight")
+    m.load_state_dict(O.make_bn_state_dict(O.conv3_channels("lightweight"), int(g["seed"])))
+    m = m.to(dev()).set_precision("bf16")
+    y = m(torch.from_numpy(g["x"]).to(dev())).float().cpu()
+    want = torch.from_numpy(g["y"])
+    assert y.shape == want.shape and (y[:, 3] == 255.0).all()
+    assert (y - want).abs().max().item() <= 255 * BF16_TOL and O.psnr(y, want, 255.0) >= 50.0
+    # trained weights on a real screenshot, full frame (6 strips at full resolution)
+    m = model_conv3.get_model("lightweight")
+    m.load_state_dict(trained_conv3_sd())
+    m = m.to(dev()).set_precision("bf16")
+    x = load_png_rgba(os.path.join(GOLD, "samples", "sample5.png")).permute(0, 3, 1, 2).contiguous()
+    want = load_png_rgba(os.path.join(GOLD, "predicted_conv3", "sample5.png")).permute(0, 3, 1, 2)
+    got = m(x.to(dev())).float().cpu().clamp(0, 255).to(torch.uint8)
+    assert (got.int() - want.int()).abs().max().item() <= 4 and O.psnr(got, want, 255.0) >= 48.0
+
+
+@pytest.mark.parametrize("preset", ["lightweight", "heavyweight"])
+def test_bf16_conv5_matches_reference_vectors(preset):
+    """conv5 heavyweight's 128->128 layer runs as four 32-channel groups."""
+    from fs_uae_image_enhancer_project_b200 import model_conv5
+    g = load_gold(f"conv5_{preset}")
+    m = model_conv5.get_model(preset)
+    m.load_state_dict(O.make_bn_state_dict(O.conv5_channels(preset), int(g["seed"])))
+    m = m.to(dev()).set_precision("bf16")
+    y = m(torch.from_numpy(g["x"]).to(dev())).cpu()
+    want = torch.from_numpy(g["y"])
+    assert (y - want).abs().max().item() <= BF16_TOL and O.psnr(y, want, 1.0) >= BF16_PSNR
 
 
 @pytest.mark.parametrize("grid", [1, 2, 3, 5, 7])
