@@ -69,12 +69,13 @@ struct LayerK {
   float p1[4][MAXC];
 };
 
-template <int PT, int NPAD>
+template <int PT, int NPAD, int CTAS = 1>   // CTAS = 2: CTA pair (cta_group::2), each CTA holds half of the weight rows
 struct Cfg {
   static constexpr int UNITS_ROW = 3 * PT;                 // (chunk, dx) units of one input row
   static constexpr int STEPS_ROW = (UNITS_ROW + 1) / 2;    // K=16 instructions per input row
   static constexpr int STEPS = 3 * STEPS_ROW;
-  static constexpr int WBYTES = STEPS * NPAD * 32;
+  static constexpr int NB = NPAD / CTAS;                   // weight rows (output channels) resident in this CTA
+  static constexpr int WBYTES = STEPS * NB * 32;
   static constexpr int ROWBYTES = PT * PLANE_ROW;
   static constexpr int RING_FIT = (SMEM_LIMIT - WBYTES - 64 - 512) / ROWBYTES;
   static constexpr int RING = RING_FIT > 10 ? 10 : RING_FIT;
@@ -83,6 +84,7 @@ struct Cfg {
   static constexpr int SMEM = BAR_OFF + 512;
   static_assert(RING >= 4, "layer does not fit: weights + 4 ring rows exceed shared memory");
   static_assert(STAGES * NPAD <= 512, "accumulator stages exceed TMEM");
+  static_assert(NB % 8 == 0, "each CTA of a pair needs whole 8-row core matrices of B");
 };
 
 // ---- fast activation math for the bf16 build (error well below bf16 resolution) ----------------
@@ -107,9 +109,9 @@ __device__ __forceinline__ float act_rt(int op, float x, float p0, float p1) {
     case FSUAE_ACT_SIGMOID: return sigmoid_fast(x);
     case FSUAE_ACT_SILU: return x * sigmoid_fast(x);
     case FSUAE_ACT_MISH: {   // x * tanh(softplus(x)) = x * w / (w + 2) = x - 2x / (w + 2), w = e^x (e^x + 2)
-      float n = __expf(x);   // overflow is benign: w = inf -> 1/(w+2) = 0 -> x
-      float w = n * (n + 2.f);
-      return fmaf(x * rcp_fast(w + 2.f), -2.f, x);
+      float n = __expf(x);                     // overflow is benign: d = inf -> 1/d = 0 -> x
+      float d = fmaf(n, n + 2.f, 2.f);         // w + 2
+      return fmaf(x * rcp_fast(d), -2.f, x);
     }
     case FSUAE_ACT_GELU: return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
     case FSUAE_ACT_ELU: return x > 0.f ? x : p0 * (__expf(x) - 1.f);
@@ -118,14 +120,14 @@ __device__ __forceinline__ float act_rt(int op, float x, float p0, float p1) {
       return bx > p1 ? x : __fdividef(__logf(1.f + __expf(bx)), p0);
     }
     case FSUAE_ACT_LEAKY_RELU: return x >= 0.f ? x : p0 * x;
-    case FSUAE_ACT_PRELU: return x >= 0.f ? x : p0 * x;
+    case FSUAE_ACT_PRELU: return fmaf(p0 - 1.f, fminf(x, 0.f), x);     // x + (slope - 1) * min(x, 0)
     case FSUAE_ACT_SCALED_TANH: return fmaf(tanh_fast(x), 0.5f, 0.5f);
     case FSUAE_ACT_TELU: return x * tanh_fast(__expf(x));
     case FSUAE_ACT_SINLU: return sigmoid_fast(x) * fmaf(p0, __sinf(p1 * x), x);
     case FSUAE_ACT_BIASED_RELU: return fmaxf(x - p0, 0.f);
-    case FSUAE_ACT_BIASED_PRELU: {
+    case FSUAE_ACT_BIASED_PRELU: {   // p1 holds (slope - 1), prepared on the host: y + (slope - 1) * min(y, 0)
       float y = x - p0;
-      return y >= 0.f ? y : p1 * y;
+      return fmaf(p1, fminf(y, 0.f), y);
     }
     default: return x;
   }
@@ -175,17 +177,21 @@ __device__ __forceinline__ uint8_t to_u8_fast(float v, int gamma_out) {
 // ------------------------------------------------------------------------------------------------
 struct Seg { int f, s, y0, rows; };
 
+// With CTA pairs the unit of work is a pair of frames: both CTAs of a pair walk the same segment
+// sequence in lockstep (same ring slot, same TMEM stage), CTA `rank` on frame 2*fp + rank.
 struct SegIter {
-  int cur, end;
-  __device__ SegIter(const LayerK& P) {
-    cur = (int)((long long)P.n_blocks * blockIdx.x / gridDim.x);
-    end = (int)((long long)P.n_blocks * (blockIdx.x + 1) / gridDim.x);
+  int cur, end, ctas, rank;
+  __device__ SegIter(const LayerK& P, int ctas_, int rank_) : ctas(ctas_), rank(rank_) {
+    const int unit = blockIdx.x / ctas, units = gridDim.x / ctas;
+    cur = (int)((long long)P.n_blocks * unit / units);
+    end = (int)((long long)P.n_blocks * (unit + 1) / units);
   }
   __device__ bool next(const LayerK& P, Seg& g) {
     if (cur >= end) return false;
     const int per_frame = P.S * P.Hw;
-    g.f = cur / per_frame;
-    const int r = cur - g.f * per_frame;
+    const int fp = cur / per_frame;
+    g.f = min(fp * ctas + rank, P.n_frames - 1);   // odd frame count: the last pair computes its frame twice (same bits)
+    const int r = cur - fp * per_frame;
     g.s = r / P.Hw;
     g.y0 = r - g.s * P.Hw;
     g.rows = min(P.Hw - g.y0, end - cur);
@@ -197,9 +203,10 @@ struct SegIter {
 // ------------------------------------------------------------------------------------------------
 // the layer kernel
 // ------------------------------------------------------------------------------------------------
-template <int PT, int NPAD, int COUT, int KIND, class EPI>
+template <int PT, int NPAD, int COUT, int KIND, class EPI, int CTAS = 1>
 __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_constant__ LayerK P) {
-  using C = Cfg<PT, NPAD>;
+  using C = Cfg<PT, NPAD, CTAS>;
+  const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;   // rank 0 of a pair issues the MMAs
   constexpr int OUT_PLANES = COUT > 0 ? (COUT + 7) / 8 : 1;   // COUT <= 0: channel count is a run-time parameter
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_w = smem;
@@ -210,7 +217,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
   uint64_t* tfull = bars + 2 * C::RING;        // [STAGES] MMA -> epilogue
   uint64_t* tempty = tfull + C::STAGES;        // [STAGES] epilogue -> MMA
   uint64_t* wbar = tempty + C::STAGES;         // weights landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+  uint64_t* pfull = wbar + 1;                  // [RING]  pair only, leader: the peer CTA's ring row has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pfull + C::RING);
   __shared__ float s_lut[256];
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -218,12 +226,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
 
   if (threadIdx.x == 0) {
     // a ring row is released by the MMA commit and, when the residual is read from it, by the 4 epilogue warps
-    for (int i = 0; i < C::RING; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], EPI::kSkip ? 5 : 1); }
-    for (int i = 0; i < C::STAGES; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < C::RING; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], EPI::kSkip ? 5 : 1); mbar_init(&pfull[i], 1); }
+    for (int i = 0; i < C::STAGES; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * CTAS); }   // pair: both CTAs' epilogues
     mbar_init(wbar, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) {
+    if constexpr (CTAS == 2) tmem_alloc_2cta(tmem_slot, 512); else tmem_alloc(tmem_slot, 512);
+  }
   if (threadIdx.x >= 64 && threadIdx.x < 64 + 16) {   // zero the 64-byte overrun pad behind the ring
     reinterpret_cast<uint32_t*>(s_ring + C::RING * C::ROWBYTES)[threadIdx.x - 64] = 0u;
   }
@@ -236,6 +246,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all();     // the peer's barriers exist before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -251,10 +262,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
     // ======================= TMA producer =======================
     if (elect_one()) {
       mbar_arrive_expect_tx(wbar, C::WBYTES);
-      tma_load_1d(s_w, P.wpack, C::WBYTES, wbar);      // weights are constants: fetch before the dependency wait
+      tma_load_1d(s_w, P.wpack + (size_t)rank * C::WBYTES, C::WBYTES, wbar);   // constants: fetch before the dependency wait
       asm volatile("griddepcontrol.wait;" ::: "memory");
       uint32_t slot = 0, par = 1;   // waiting on parity 1 of a fresh barrier passes immediately
-      SegIter it(P);
+      SegIter it(P, CTAS, (int)rank);
       Seg sg;
       while (it.next(P, sg)) {
         const int f = sg.f, s = sg.s, y0 = sg.y0, rows = sg.rows;
@@ -272,28 +283,53 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
         }
       }
     }
-  } else if (warp == 1) {
-    // ======================= MMA issuer =======================
+  } else if (warp == 1 && rank != 0) {
+    // ======================= peer CTA of a pair: relay "my ring row has landed" to the leader =======================
     if (elect_one()) {
-      constexpr uint32_t IDESC = umma_idesc_bf16(MROWS, NPAD);
+      uint32_t wslot = 0, wpar = 0;
+      mbar_wait(wbar, 0);                 // my half of the weights is part of every MMA the leader issues
+      SegIter it(P, CTAS, (int)rank);
+      Seg sg;
+      while (it.next(P, sg)) {
+        for (int k = 0; k < sg.rows + 2; ++k) {
+          mbar_wait(&full[wslot], wpar);
+          mbar_arrive_cluster(&pfull[wslot], 0);
+          if (++wslot == C::RING) { wslot = 0; wpar ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer (leader CTA of a pair, or the only CTA) =======================
+    if (elect_one()) {
+      constexpr uint32_t IDESC = umma_idesc_bf16(MROWS * CTAS, NPAD);
+      auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+        if constexpr (CTAS == 2) umma_bf16_2cta(d, a, b, idesc, acc); else umma_bf16(d, a, b, idesc, acc);
+      };
+      auto commit = [](uint64_t* bar) {
+        if constexpr (CTAS == 2) umma_commit_2cta(bar); else umma_commit(bar);
+      };
+      auto wait_row = [&](uint32_t slot, uint32_t par) {
+        mbar_wait(&full[slot], par);
+        if constexpr (CTAS == 2) mbar_wait(&pfull[slot], par);   // signal only: the data is consumed through the async proxy
+      };
       const uint32_t ring_lo = (smem_u32(s_ring) & 0x3FFFFu) >> 4;
-      const uint32_t w_lo = ((smem_u32(s_w) & 0x3FFFFu) >> 4) | ((uint32_t)((NPAD * 16) >> 4) << 16);
+      const uint32_t w_lo = ((smem_u32(s_w) & 0x3FFFFu) >> 4) | ((uint32_t)((C::NB * 16) >> 4) << 16);   // LBO = one K half of this CTA's rows
       constexpr uint32_t HI = (uint32_t)((128u >> 4)) | (1u << 14);   // SBO = 128 B, descriptor version 1
       mbar_wait(wbar, 0);
       uint32_t wslot = 0, wpar = 0;       // next ring slot to wait for
       uint32_t stage = 0, spar = 1;       // accumulator stage / parity for tempty
-      SegIter it(P);
+      SegIter it(P, CTAS, (int)rank);
       Seg sg;
       while (it.next(P, sg)) {
         const int rows = sg.rows;
         uint32_t s0 = wslot;              // slot of the block's first input row
         // first two rows of the item
         for (int k = 0; k < 2; ++k) {
-          mbar_wait(&full[wslot], wpar);
+          wait_row(wslot, wpar);
           if (++wslot == C::RING) { wslot = 0; wpar ^= 1; }
         }
         for (int b = 0; b < rows; ++b) {
-          mbar_wait(&full[wslot], wpar);
+          wait_row(wslot, wpar);
           if (++wslot == C::RING) { wslot = 0; wpar ^= 1; }
           mbar_wait(&tempty[stage], spar);
           tc_fence_after();
@@ -304,7 +340,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
           // is odd the last instruction re-reads unit 3*PT-2 against zero weights in its first half and
           // carries unit 3*PT-1 in its second, so both halves always point at landed, finite data --
           // anything else could turn never-written shared memory into 0 * NaN.
-          constexpr uint32_t BSTEP = (NPAD * 32) >> 4;
+          constexpr uint32_t BSTEP = (C::NB * 32) >> 4;
           constexpr uint32_t L16 = 1u << 16, L2K = (uint32_t)((PLANE_ROW >> 4) - 2) << 16;
           constexpr int G3 = C::STEPS_ROW / 3, REM = C::STEPS_ROW % 3;
           static_assert(REM == 0 || REM == 2, "unexpected instruction count per row");
@@ -314,28 +350,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
             uint32_t a_lo = ring_lo + rs * (C::ROWBYTES >> 4);
 #pragma unroll 1
             for (int g3 = 0; g3 < G3; ++g3) {
-              umma_bf16(d_tmem, ((uint64_t)HI << 32) | (a_lo | L16), ((uint64_t)HI << 32) | b_lo, IDESC, acc);
-              umma_bf16(d_tmem, ((uint64_t)HI << 32) | ((a_lo + 2) | L2K), ((uint64_t)HI << 32) | (b_lo + BSTEP), IDESC, 1);
-              umma_bf16(d_tmem, ((uint64_t)HI << 32) | ((a_lo + (PLANE_ROW >> 4) + 1) | L16), ((uint64_t)HI << 32) | (b_lo + 2 * BSTEP), IDESC, 1);
+              mma(d_tmem, ((uint64_t)HI << 32) | (a_lo | L16), ((uint64_t)HI << 32) | b_lo, IDESC, acc);
+              mma(d_tmem, ((uint64_t)HI << 32) | ((a_lo + 2) | L2K), ((uint64_t)HI << 32) | (b_lo + BSTEP), IDESC, 1);
+              mma(d_tmem, ((uint64_t)HI << 32) | ((a_lo + (PLANE_ROW >> 4) + 1) | L16), ((uint64_t)HI << 32) | (b_lo + 2 * BSTEP), IDESC, 1);
               acc = 1;
               a_lo += 2 * (PLANE_ROW >> 4);
               b_lo += 3 * BSTEP;
             }
             if constexpr (REM == 2) {
-              umma_bf16(d_tmem, ((uint64_t)HI << 32) | (a_lo | L16), ((uint64_t)HI << 32) | b_lo, IDESC, acc);
+              mma(d_tmem, ((uint64_t)HI << 32) | (a_lo | L16), ((uint64_t)HI << 32) | b_lo, IDESC, acc);
               acc = 1;
-              umma_bf16(d_tmem, ((uint64_t)HI << 32) | ((a_lo + 1) | L16), ((uint64_t)HI << 32) | (b_lo + BSTEP), IDESC, 1);
+              mma(d_tmem, ((uint64_t)HI << 32) | ((a_lo + 1) | L16), ((uint64_t)HI << 32) | (b_lo + BSTEP), IDESC, 1);
               b_lo += 2 * BSTEP;
             }
             if (++rs == C::RING) rs = 0;
           }
-          umma_commit(&tfull[stage]);
-          umma_commit(&empty[s0]);            // the block's first row is not needed again
+          commit(&tfull[stage]);
+          commit(&empty[s0]);            // the block's first row is not needed again
           if (b == rows - 1) {                // item done: release its last two rows as well
             uint32_t s1 = s0 + 1 == C::RING ? 0 : s0 + 1;
             uint32_t s2 = s1 + 1 == C::RING ? 0 : s1 + 1;
-            umma_commit(&empty[s1]);
-            umma_commit(&empty[s2]);
+            commit(&empty[s1]);
+            commit(&empty[s2]);
           }
           if (++s0 == C::RING) s0 = 0;
           if (++stage == C::STAGES) { stage = 0; spar ^= 1; }
@@ -349,7 +385,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
     const uint32_t stage = (uint32_t)(warp - 2) >> 2;   // this warpgroup's accumulator stage
     asm volatile("griddepcontrol.wait;" ::: "memory");   // epilogues read the frame / write buffers earlier layers still read
     uint32_t spar = 0, blk = 0, qrow = 0;      // qrow: ring-row counter at the start of the item
-    SegIter it(P);
+    SegIter it(P, CTAS, (int)rank);
     Seg sg;
     while (it.next(P, sg)) {
       const int f = sg.f, s = sg.s, y0 = sg.y0, rows = sg.rows;
@@ -359,8 +395,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
         if ((blk & (EPI_WG - 1)) != stage) continue;
         const int y = y0 + b;
         const size_t pix = (size_t)(y + 1) * row_pitch + (size_t)(x + 1) * 16;
-        // tail: fetch the input pixels of the global residual while the MMAs of this row are still running
-        float idv[KIND == EPI_TAIL_SHUFFLE ? 2 : 1][3][2];
+        // tail: issue the loads of the input pixels (global residual) now, consume them only after the accumulator
+        // is ready, so their latency hides behind the MMAs of this row
+        uint32_t raw[KIND == EPI_TAIL_SHUFFLE ? 2 : 1][6];     // per output row dy: 2 pixels x 3 channels (f32 bits or u8)
         if constexpr (KIND == EPI_TAIL_SHUFFLE) {
           if (valid) {
             const size_t fpl = (size_t)P.H * P.W;
@@ -372,22 +409,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                   float2 t2 = __ldg(reinterpret_cast<const float2*>(ip + c * fpl));
-                  idv[dy][c][0] = t2.x; idv[dy][c][1] = t2.y;
+                  raw[dy][2 * c] = __float_as_uint(t2.x); raw[dy][2 * c + 1] = __float_as_uint(t2.y);
                 }
               } else if (P.in_fmt == FSUAE_FMT_U8_NHWC4) {
                 uint2 t2 = __ldg(reinterpret_cast<const uint2*>((const unsigned char*)P.frame_in + ((size_t)f * fpl + p0) * 4));
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                  idv[dy][c][0] = s_lut[(t2.x >> (8 * c)) & 0xFF];
-                  idv[dy][c][1] = s_lut[(t2.y >> (8 * c)) & 0xFF];
-                }
+                raw[dy][0] = t2.x; raw[dy][1] = t2.y;
               } else {
                 const unsigned char* ip = (const unsigned char*)P.frame_in + (size_t)f * 4 * fpl + p0;
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                  idv[dy][c][0] = s_lut[ip[c * fpl]];
-                  idv[dy][c][1] = s_lut[ip[c * fpl + 1]];
-                }
+                for (int c = 0; c < 3; ++c) { raw[dy][2 * c] = __ldg(ip + c * fpl); raw[dy][2 * c + 1] = __ldg(ip + c * fpl + 1); }
               }
             }
           }
@@ -419,7 +449,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
 #pragma unroll
             for (int c = 0; c < OUT_PLANES; ++c)
               sk[c] = valid ? *reinterpret_cast<const uint4*>(sp + c * PLANE_ROW) : make_uint4(0, 0, 0, 0);
-            release_rows();
           }
           unsigned char* dp = P.dst + (size_t)f * P.fs_dst + pix + (size_t)P.dst_plane0 * plane_pitch;
 #pragma unroll
@@ -446,6 +475,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
               *reinterpret_cast<uint4*>(dp + (size_t)c * plane_pitch) = pk;
             }
           }
+          // Release the ring rows only now: every residual value has been consumed, so no shared-memory load of
+          // this row can still be in flight when the producer's TMA refills the slot (an arrive issued right
+          // behind the LDS instructions does not wait for them).
+          if constexpr (EPI::kSkip) release_rows();
         } else if constexpr (KIND == EPI_STORE) {
           // ---- run-time channel count / op-codes (every other network) ----
           unsigned char* dp = P.dst + (size_t)f * P.fs_dst + pix + (size_t)P.dst_plane0 * plane_pitch;
@@ -515,6 +548,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
           }
           if (valid) {
             const size_t fpl = (size_t)P.H * P.W;
+            float idv[2][3][2];
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                if (P.in_fmt == FSUAE_FMT_F32_NCHW3) {
+                  idv[dy][c][0] = __uint_as_float(raw[dy][2 * c]); idv[dy][c][1] = __uint_as_float(raw[dy][2 * c + 1]);
+                } else if (P.in_fmt == FSUAE_FMT_U8_NHWC4) {
+                  idv[dy][c][0] = s_lut[(raw[dy][0] >> (8 * c)) & 0xFF]; idv[dy][c][1] = s_lut[(raw[dy][1] >> (8 * c)) & 0xFF];
+                } else {
+                  idv[dy][c][0] = s_lut[raw[dy][2 * c] & 0xFF]; idv[dy][c][1] = s_lut[raw[dy][2 * c + 1] & 0xFF];
+                }
+              }
 #pragma unroll
             for (int dy = 0; dy < 2; ++dy) {
               const int Y = 2 * y + dy, X = 2 * x + P.xoff;
@@ -541,7 +587,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[stage]);
+        if (lane == 0) {
+          if constexpr (CTAS == 2) mbar_arrive_cluster(&tempty[stage], 0); else mbar_arrive(&tempty[stage]);
+        }
         spar ^= 1;
       }
       qrow += (uint32_t)rows + 2;
@@ -549,7 +597,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if constexpr (CTAS == 2) cluster_sync_all();     // nobody leaves while the peer may still signal or read
+  if (warp == 1) {
+    if constexpr (CTAS == 2) tmem_dealloc_2cta(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -671,9 +722,10 @@ uint16_t f2bf(float f) {   // round to nearest even, like __float2bfloat16_rn
 
 // B operand of instruction (dy, st): [2 halves][NPAD rows][8 k]; half h <-> unit u = 2 st + h (see the kernel for the odd tail),
 // chunk j = u / 3 (plane of the concatenated sources), tap dx = u % 3, channels 8j .. 8j+7.
-std::vector<uint16_t> pack_weights(const float* w, int cout, int cin0, int cin1, int P0, int P1, int NPAD) {
+std::vector<uint16_t> pack_weights(const float* w, int cout, int cin0, int cin1, int P0, int P1, int NPAD, int ctas = 1) {
   const int PT = P0 + P1, cin = cin0 + cin1;
   const int steps_row = (3 * PT + 1) / 2;
+  const int NB = NPAD / ctas;   // rows per CTA; CTA r of a pair holds output channels [r*NB, (r+1)*NB), stored [rank][step][half][NB][8]
   std::vector<uint16_t> out((size_t)3 * steps_row * NPAD * 16, 0);
   for (int dy = 0; dy < 3; ++dy)
     for (int st = 0; st < steps_row; ++st)
@@ -690,7 +742,7 @@ std::vector<uint16_t> pack_weights(const float* w, int cout, int cin0, int cin1,
             if (j < P0) { ci = j * 8 + k; if (ci >= cin0) continue; }
             else { ci = (j - P0) * 8 + k; if (ci >= cin1) continue; ci += cin0; }
             const float v = w[((size_t)n * cin + ci) * 9 + dy * 3 + dx];
-            out[(((size_t)(dy * steps_row + st) * 2 + h) * NPAD + n) * 8 + k] = f2bf(v);
+            out[(size_t)(n / NB) * 3 * steps_row * NB * 16 + (((size_t)(dy * steps_row + st) * 2 + h) * NB + n % NB) * 8 + k] = f2bf(v);
           }
       }
   return out;
@@ -699,15 +751,16 @@ std::vector<uint16_t> pack_weights(const float* w, int cout, int cin0, int cin1,
 typedef void (*KernelFn)(const LayerK);
 
 struct Variant {
+  int CTAS;                             // 2: CTA-pair kernel (cta_group::2), used when a launch has >= 2 frames
   int PT, NPAD, COUT, KIND;             // COUT <= 0: run-time channel count
   int pre0, pre1, post0, post1, skip;   // -1 = run-time op-codes
   KernelFn fn;
   int smem;
 };
 
-template <int PT, int NPAD, int COUT, int KIND, class EPI>
+template <int PT, int NPAD, int COUT, int KIND, class EPI, int CTAS = 1>
 Variant make_variant(int a, int b, int c, int d, int skip) {
-  Variant v{PT, NPAD, COUT, KIND, a, b, c, d, skip, conv3x3_tc_kernel<PT, NPAD, COUT, KIND, EPI>, Cfg<PT, NPAD>::SMEM};
+  Variant v{CTAS, PT, NPAD, COUT, KIND, a, b, c, d, skip, conv3x3_tc_kernel<PT, NPAD, COUT, KIND, EPI, CTAS>, Cfg<PT, NPAD, CTAS>::SMEM};
   return v;
 }
 template <int PT, int NPAD, int KIND, bool SKIP>
@@ -726,6 +779,14 @@ const std::vector<Variant>& variants() {
       make_variant<9, 48, 36, EPI_STORE, Epi<0, 0, 0, 0, false>>(0, 0, 0, 0, 0),
       make_variant<10, 48, 36, EPI_STORE, Epi<A(MISH), A(RELU6), 0, 0, false>>(A(MISH), A(RELU6), 0, 0, 0),
       make_variant<5, 16, 12, EPI_TAIL_SHUFFLE, Epi<A(BIASED_PRELU), 0, 0, 0, false>>(A(BIASED_PRELU), 0, 0, 0, 0),
+      // ---- the same seven layers as CTA-pair kernels (two frames in lockstep, B operand split across the pair) ----
+      make_variant<2, 48, 36, EPI_STORE, Epi<A(SINLU), A(RELU6), 0, 0, false>, 2>(A(SINLU), A(RELU6), 0, 0, 0),
+      make_variant<5, 48, 36, EPI_STORE, Epi<A(TELU), 0, A(SINLU), A(BIASED_PRELU), true>, 2>(A(TELU), 0, A(SINLU), A(BIASED_PRELU), 1),
+      make_variant<5, 80, 72, EPI_STORE, Epi<0, 0, 0, 0, false>, 2>(0, 0, 0, 0, 0),
+      make_variant<9, 80, 72, EPI_STORE, Epi<A(MISH), A(BIASED_PRELU), A(TANH), A(RELU), true>, 2>(A(MISH), A(BIASED_PRELU), A(TANH), A(RELU), 1),
+      make_variant<9, 48, 36, EPI_STORE, Epi<0, 0, 0, 0, false>, 2>(0, 0, 0, 0, 0),
+      make_variant<10, 48, 36, EPI_STORE, Epi<A(MISH), A(RELU6), 0, 0, false>, 2>(A(MISH), A(RELU6), 0, 0, 0),
+      make_variant<5, 16, 12, EPI_TAIL_SHUFFLE, Epi<A(BIASED_PRELU), 0, 0, 0, false>, 2>(A(BIASED_PRELU), 0, 0, 0, 0),
       // ---- run-time epilogues: any activation chain of the registry (except channel softmax), any Cout <= NPAD ----
       // pix_shuffle channel plans (36/72 and the heavyweight 108)
       generic_variant<2, 48, EPI_STORE, false>(), generic_variant<5, 48, EPI_STORE, false>(), generic_variant<5, 48, EPI_STORE, true>(),
@@ -746,6 +807,8 @@ const std::vector<Variant>& variants() {
 struct Launch {
   const Variant* var = nullptr;
   unsigned char* d_w = nullptr;
+  const Variant* var2 = nullptr;   // CTA-pair kernel for the same layer (weights packed per CTA), if instantiated
+  unsigned char* d_w2 = nullptr;
   LayerK k{};   // geometry-independent fields prefilled
 };
 
@@ -811,7 +874,7 @@ int bf16_create(fsuae_engine* e) {
     const Variant* fit = nullptr;    // smallest generic NPAD >= need
     const Variant* widest = nullptr; // widest generic NPAD
     for (const Variant& v : variants()) {
-      if (v.PT != PT || v.KIND != kind || v.skip != skip) continue;
+      if (v.CTAS != 1 || v.PT != PT || v.KIND != kind || v.skip != skip) continue;
       if (v.COUT == L.cout && v.pre0 == ops[0] && v.pre1 == ops[1] && v.post0 == ops[2] && v.post1 == ops[3]) exact = &v;
       if (v.pre0 != -1) continue;
       if (v.NPAD >= need && (!fit || v.NPAD < fit->NPAD)) fit = &v;
@@ -850,6 +913,20 @@ int bf16_create(fsuae_engine* e) {
           const int cc = std::min(c0 + c, L.cout - 1);
           k.p0[s][c] = (a && a->n0 > 0) ? e->h_blob[a->p0_off + (a->n0 == 1 ? 0 : cc)] : 0.f;
           k.p1[s][c] = (a && a->n1 > 0) ? e->h_blob[a->p1_off + (a->n1 == 1 ? 0 : cc)] : 0.f;
+          if (a && a->op == FSUAE_ACT_BIASED_PRELU) k.p1[s][c] -= 1.f;   // the kernel evaluates y + (slope - 1) * min(y, 0)
+        }
+      }
+      if (var == exact && !getenv("FSUAE_NO_PAIRS")) {
+        for (const Variant& v : variants())
+          if (v.CTAS == 2 && v.PT == var->PT && v.NPAD == var->NPAD && v.COUT == var->COUT && v.KIND == var->KIND &&
+              v.skip == var->skip && v.pre0 == var->pre0 && v.pre1 == var->pre1 && v.post0 == var->post0 && v.post1 == var->post1)
+            ln.var2 = &v;
+        if (ln.var2) {
+          std::vector<uint16_t> wp2 = pack_weights(e->h_blob.data() + L.w_off, cg, L.cin0, L.cin1, P0, P1, var->NPAD, 2);
+          FSUAE_CUDA_CHECK(e, cudaMalloc(&ln.d_w2, wp2.size() * 2));
+          FSUAE_CUDA_CHECK(e, cudaMemcpy(ln.d_w2, wp2.data(), wp2.size() * 2, cudaMemcpyHostToDevice));
+          e->device_bytes += wp2.size() * 2;
+          FSUAE_CUDA_CHECK(e, cudaFuncSetAttribute((const void*)ln.var2->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ln.var2->smem));
         }
       }
       lp.launches.push_back(ln);
@@ -877,7 +954,7 @@ void bf16_destroy(fsuae_engine* e) {
   if (!e->bf16) return;
   for (auto& lp : e->bf16->layers)
     for (auto& ln : lp.launches)
-      if (ln.d_w) cudaFree(ln.d_w);
+      { if (ln.d_w) cudaFree(ln.d_w); if (ln.d_w2) cudaFree(ln.d_w2); }
   for (unsigned char* p : e->bf16->buf)
     if (p) cudaFree(p);
   delete e->bf16;
@@ -911,7 +988,10 @@ int bf16_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in
     for (Launch& ln : plan->layers[i].launches) {
       LayerK k = ln.k;
       k.Hw = g.Hw; k.Ww = g.Ww; k.PW = PW; k.S = S; k.n_frames = n;
-      k.n_blocks = n * S * g.Hw;
+      const bool pair = ln.var2 != nullptr && n >= 2;      // CTA pairs process two frames in lockstep
+      const Variant* var = pair ? ln.var2 : ln.var;
+      if (pair) k.wpack = ln.d_w2;
+      k.n_blocks = (pair ? (n + 1) / 2 : n) * S * g.Hw;
       k.src0 = plan->buf[L.src0]; k.fs0 = fstride(L.src0);
       if (L.cin1 > 0) { k.src1 = plan->buf[L.src1]; k.fs1 = fstride(L.src1); }
       if (L.skip_src >= 0) { k.skip = plan->buf[L.skip_src]; k.fs_skip = fstride(L.skip_src); }
@@ -920,19 +1000,25 @@ int bf16_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in
       k.H = g.H; k.W = g.W; k.xoff = g.xoff;
       k.gamma_in = gin;
       k.gamma_out = (flags & FSUAE_FLAG_GAMMA_OUT) ? 1 : 0;
-      int grid = std::min(k.n_blocks, e->sm_count);
-      if (const char* g_env = getenv("FSUAE_DEBUG_GRID")) grid = std::max(1, std::min(k.n_blocks, atoi(g_env)));   // debugging aid: force the CTA count
+      const int ctas = pair ? 2 : 1;
+      int grid = std::min(k.n_blocks * ctas, e->sm_count / ctas * ctas);
+      if (const char* g_env = getenv("FSUAE_DEBUG_GRID")) grid = std::max(ctas, std::min(k.n_blocks * ctas, atoi(g_env) / ctas * ctas));   // debugging aid: force the CTA count
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(grid);
       cfg.blockDim = dim3(NTHREADS);
-      cfg.dynamicSmemBytes = ln.var->smem;
+      cfg.dynamicSmemBytes = var->smem;
       cfg.stream = st;
-      cudaLaunchAttribute attr[1];
+      cudaLaunchAttribute attr[2];
       attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       attr[0].val.programmaticStreamSerializationAllowed = 1;
-      cfg.attrs = attr;
       cfg.numAttrs = 1;
-      FSUAE_CUDA_CHECK(e, cudaLaunchKernelEx(&cfg, ln.var->fn, k));
+      if (pair) {
+        attr[1].id = cudaLaunchAttributeClusterDimension;
+        attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+        cfg.numAttrs = 2;
+      }
+      cfg.attrs = attr;
+      FSUAE_CUDA_CHECK(e, cudaLaunchKernelEx(&cfg, var->fn, k));
       e->launches++;
     }
   }
