@@ -169,7 +169,7 @@ int fsuae_engine_create(const fsuae_net_desc* desc, const float* blob, size_t bl
   }
 
   // host-pipeline staging: sized for the widest formats
-  e->host_chunk = std::min(e->chunk, 8);   // finer pipeline stages than the device chunk: H2D / compute / D2H overlap
+  e->host_chunk = std::min(e->chunk, 16);  // largest stage of the host-buffer pipeline (H2D / compute / D2H overlap)
   size_t in_b = (size_t)e->host_chunk * 12 * height * width, out_b = (size_t)e->host_chunk * 16 * height * width;
   for (int i = 0; i < 2 && ce == cudaSuccess; ++i) {
     ce = cudaMalloc(&e->d_stage_in[i], in_b);
@@ -281,8 +281,23 @@ int fsuae_engine_run_host(fsuae_engine* e, const void* in_host, void* out_host, 
   size_t in_fb = fmt_frame_bytes(in_fmt, e->H, e->W), out_fb = fmt_frame_bytes(out_fmt, e->H, e->W);
   int it = 0;
   rc = FSUAE_OK;
-  for (int f0 = 0; f0 < n_frames && rc == FSUAE_OK; f0 += e->host_chunk, ++it) {
-    int n = std::min(e->host_chunk, n_frames - f0);
+  // Stage sizes ramp up (4, 8, 16, 16, ... 4): compute starts after a short first upload and the last download is
+  // short -- the call is synchronous, so pipeline fill and drain are paid on every call.
+  std::vector<int> stages;
+  {
+    int rem = n_frames, step = std::min(4, e->host_chunk);
+    const int tail = n_frames >= 24 ? 4 : 0;
+    rem -= tail;
+    while (rem > 0) {
+      const int take = std::min(step, rem);
+      stages.push_back(take);
+      rem -= take;
+      step = std::min(step * 2, e->host_chunk);
+    }
+    if (tail) stages.push_back(tail);
+  }
+  for (int f0 = 0, n = 0; it < (int)stages.size() && rc == FSUAE_OK; f0 += n, ++it) {
+    n = stages[it];
     int b = it & 1;
     cudaError_t ce = cudaSuccess;
     if (it >= 2) ce = cudaStreamWaitEvent(e->s_in, e->ev_out[b], 0);  // staging pair b is free again
