@@ -3,8 +3,8 @@
 // epilogue fused behind the accumulator read-back (tcgen05.ld).
 //
 // Data layout ("chunk-planar"): an activation map with C channels is ceil(C/8) planes; a plane is
-// (Hw+2) rows x PW slots of 16 bytes (8 bf16 channels of one pixel), with a zero border of one
-// pixel baked in (row 0, row Hw+1, column 0, columns > Ww) so the per-layer zero padding of
+// (Hw+4) rows x PW slots of 16 bytes (8 bf16 channels of one pixel), with a zero border of two
+// pixels baked in on every side so the per-layer zero padding of
 // nn.Conv2d(padding=1) needs no special case anywhere: borders are never written.
 //
 // Implicit GEMM: M = 128 consecutive pixels of one image row (a "strip row": 126 valid outputs +
@@ -41,6 +41,8 @@ constexpr int MAXC = 128;           // widest N of one launch
 constexpr int STRIP = 126;            // valid output columns per strip row
 constexpr int MROWS = 128;            // MMA M = slots per strip row
 constexpr int PLANE_ROW = MROWS * 16; // bytes of one plane of one strip row
+constexpr int BORDER = 2;             // zero pixels baked in on every side of a plane (1 for a layer, 2 for a fused pair)
+__host__ __device__ constexpr int plane_width(int S) { return STRIP * S + 2 * BORDER; }   // slots per padded row (PW)
 constexpr int SMEM_LIMIT = 232448 - 2048;
 constexpr int EPI_WG = 4;                       // epilogue warpgroups; group g owns accumulator stage g
 constexpr int NTHREADS = 64 + 128 * EPI_WG;
@@ -256,7 +258,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const size_t row_pitch = (size_t)P.PW * 16;                  // bytes of one padded image row of one plane
-  const size_t plane_pitch = (size_t)(P.Hw + 2) * row_pitch;
+  const size_t plane_pitch = (size_t)(P.Hw + 2 * BORDER) * row_pitch;
 
   if (warp == 0) {
     // ======================= TMA producer =======================
@@ -269,8 +271,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
       Seg sg;
       while (it.next(P, sg)) {
         const int f = sg.f, s = sg.s, y0 = sg.y0, rows = sg.rows;
-        const unsigned char* g0 = P.src0 + (size_t)f * P.fs0 + (size_t)y0 * row_pitch + (size_t)s * STRIP * 16;
-        const unsigned char* g1 = P.P1 ? P.src1 + (size_t)f * P.fs1 + (size_t)y0 * row_pitch + (size_t)s * STRIP * 16 : nullptr;
+        const size_t org = (size_t)(y0 - 1 + BORDER) * row_pitch + (size_t)(s * STRIP - 1 + BORDER) * 16;   // pixel (y0-1, x0-1)
+        const unsigned char* g0 = P.src0 + (size_t)f * P.fs0 + org;
+        const unsigned char* g1 = P.P1 ? P.src1 + (size_t)f * P.fs1 + org : nullptr;
         for (int k = 0; k < rows + 2; ++k) {          // padded rows y0 .. y0+rows+1
           mbar_wait(&empty[slot], par);
           mbar_arrive_expect_tx(&full[slot], C::ROWBYTES);
@@ -394,7 +397,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
       for (int b = 0; b < rows; ++b, ++blk) {
         if ((blk & (EPI_WG - 1)) != stage) continue;
         const int y = y0 + b;
-        const size_t pix = (size_t)(y + 1) * row_pitch + (size_t)(x + 1) * 16;
+        const size_t pix = (size_t)(y + BORDER) * row_pitch + (size_t)(x + BORDER) * 16;
         // tail: issue the loads of the input pixels (global residual) now, consume them only after the accumulator
         // is ready, so their latency hides behind the MMAs of this row
         uint32_t raw[KIND == EPI_TAIL_SHUFFLE ? 2 : 1][6];     // per output row dy: 2 pixels x 3 channels (f32 bits or u8)
@@ -617,7 +620,7 @@ __global__ void head_unshuffle_bf16_kernel(const void* __restrict__ in, unsigned
   __syncthreads();
   const size_t plane = (size_t)Hw * Ww, total = (size_t)n_frames * plane;
   const size_t fpl = (size_t)H * W;
-  const size_t row_pitch = (size_t)PW * 16, plane_pitch = (size_t)(Hw + 2) * row_pitch;
+  const size_t row_pitch = (size_t)PW * 16, plane_pitch = (size_t)(Hw + 2 * BORDER) * row_pitch;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int f = (int)(idx / plane);
     const int r = (int)(idx - (size_t)f * plane);
@@ -649,7 +652,7 @@ __global__ void head_unshuffle_bf16_kernel(const void* __restrict__ in, unsigned
         }
       }
     }
-    unsigned char* dp = dst + (size_t)f * fs_dst + (size_t)(h + 1) * row_pitch + (size_t)(w + 1) * 16;
+    unsigned char* dp = dst + (size_t)f * fs_dst + (size_t)(h + BORDER) * row_pitch + (size_t)(w + BORDER) * 16;
     *reinterpret_cast<uint4*>(dp) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
                                                pack_bf16x2(v[6], v[7]));
     *reinterpret_cast<uint4*>(dp + plane_pitch) = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), 0u, 0u);
@@ -684,7 +687,7 @@ __global__ void head_plain_bf16_kernel(const void* __restrict__ in, unsigned cha
       const unsigned char* ip = (const unsigned char*)in + (size_t)f * 4 * fpl + p0;
       v[0] = lut[ip[0]]; v[1] = lut[ip[fpl]]; v[2] = lut[ip[2 * fpl]];
     }
-    unsigned char* dp = dst + (size_t)f * fs_dst + (size_t)(h + 1) * row_pitch + (size_t)(w + 1) * 16;
+    unsigned char* dp = dst + (size_t)f * fs_dst + (size_t)(h + BORDER) * row_pitch + (size_t)(w + BORDER) * 16;
     *reinterpret_cast<uint4*>(dp) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], 0.f), 0u, 0u);
   }
 }
@@ -935,13 +938,13 @@ int bf16_create(fsuae_engine* e) {
   }
   // activation buffers at the largest geometry (no crop)
   const int Hw = unshuffle ? e->H / 2 : e->H, Ww = unshuffle ? e->W / 2 : e->W;
-  const int S = (Ww + STRIP - 1) / STRIP, PW = STRIP * (S - 1) + MROWS;
+  const int S = (Ww + STRIP - 1) / STRIP, PW = plane_width(S);
   plan->buf.assign(d.n_layers, nullptr);
   plan->planes.assign(d.n_layers, 0);
   plan->buf_bytes.assign(d.n_layers, 0);
   for (int i = 0; i < d.n_layers; ++i) {
     plan->planes[i] = i == 0 ? (unshuffle ? 2 : 1) : planes_of(ch[i]);
-    size_t bytes = (size_t)e->chunk * plan->planes[i] * (Hw + 2) * PW * 16 + 256;
+    size_t bytes = (size_t)e->chunk * plan->planes[i] * (Hw + 2 * BORDER) * PW * 16 + 256;
     FSUAE_CUDA_CHECK(e, cudaMalloc(&plan->buf[i], bytes));
     plan->buf_bytes[i] = bytes;
     e->device_bytes += bytes;
@@ -966,13 +969,13 @@ int bf16_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in
   Bf16Plan* plan = e->bf16;
   const fsuae_net_desc& d = e->desc;
   const Geom g = make_geom(e, flags);
-  const int S = (g.Ww + STRIP - 1) / STRIP, PW = STRIP * (S - 1) + MROWS;
+  const int S = (g.Ww + STRIP - 1) / STRIP, PW = plane_width(S);
   if (plan->zero_Hw != g.Hw || plan->zero_Ww != g.Ww) {   // (re)establish the zero borders for this geometry
     for (size_t i = 0; i < plan->buf.size(); ++i) FSUAE_CUDA_CHECK(e, cudaMemsetAsync(plan->buf[i], 0, plan->buf_bytes[i], st));
     plan->zero_Hw = g.Hw;
     plan->zero_Ww = g.Ww;
   }
-  auto fstride = [&](int id) { return (unsigned long long)plan->planes[id] * (g.Hw + 2) * PW * 16; };
+  auto fstride = [&](int id) { return (unsigned long long)plan->planes[id] * (g.Hw + 2 * BORDER) * PW * 16; };
 
   const int gin = (flags & FSUAE_FLAG_GAMMA_IN) ? 1 : 0;
   if (d.head == FSUAE_HEAD_UNSHUFFLE2)

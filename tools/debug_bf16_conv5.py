@@ -19,15 +19,15 @@ cv = lambda i, t: F.conv2d(t, sd[f"conv{i}.weight"], None, 1, 1)
 l1 = torch.relu(bn(1, cv(1, x))); l2 = torch.relu(l1 + bn(2, cv(2, l1))); l3 = torch.relu(bn(3, cv(3, l2))); l4 = torch.relu(l3 + bn(4, cv(4, l3)))
 y = torch.sigmoid(bn(5, cv(5, l4)))
 refs = [x, l1, l2, l3, l4]
-S = (W + 125) // 126; PW = 126 * (S - 1) + 128
+S = (W + 125) // 126; PW = 126 * S + 4
 for i, ref in enumerate(refs):
     C = ref.shape[1]; NP = (C + 7) // 8
-    nbytes = NP * (H + 2) * PW * 16
+    nbytes = NP * (H + 4) * PW * 16
     buf = np.zeros(nbytes, dtype=np.uint8)
     lib.fsuae_debug_read_bf16_buffer(eng._h, i, buf.ctypes.data, nbytes)
     u16 = torch.from_numpy(buf.view(np.uint16).astype(np.int32))
-    f32 = (u16 << 16).view(torch.int32).view(torch.float32).view(NP, H + 2, PW, 8)
-    mine = f32[:, 1:H + 1, 1:W + 1, :].permute(0, 3, 1, 2).reshape(NP * 8, H, W)[:C]
+    f32 = (u16 << 16).view(torch.int32).view(torch.float32).view(NP, H + 4, PW, 8)
+    mine = f32[:, 2:H + 2, 2:W + 2, :].permute(0, 3, 1, 2).reshape(NP * 8, H, W)[:C]
     e = (mine - ref[0]).abs()
     rel = e.max().item() / ref.abs().max().item()
     worst_c = e.amax(dim=(1, 2)).argmax().item()

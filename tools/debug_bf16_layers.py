@@ -28,19 +28,19 @@ l6 = act("l6_act2", act("l6_act1", conv(6, torch.cat([l1, l5], 1))))
 refs = [t0, l1, l2, l3, l4, l5, l6]
 Hw, Ww = H // 2, W // 2
 S = (Ww + 125) // 126
-PW = 126 * (S - 1) + 128
+PW = 126 * S + 4
 for i, ref in enumerate(refs):
     C = ref.shape[1]
     NP = (C + 7) // 8 if i else 2
-    nbytes = NP * (Hw + 2) * PW * 16
+    nbytes = NP * (Hw + 4) * PW * 16
     buf = np.zeros(nbytes, dtype=np.uint8)
     n = lib.fsuae_debug_read_bf16_buffer(eng._h, i, buf.ctypes.data, nbytes)
     a = torch.from_numpy(buf.view(np.int16).astype(np.int32) << 16).view(torch.float32) if False else None
     u16 = torch.from_numpy(buf.view(np.uint16).astype(np.int32))
-    f32 = (u16 << 16).view(torch.int32).view(torch.float32).view(NP, Hw + 2, PW, 8)
-    mine = f32[:, 1:Hw + 1, 1:Ww + 1, :].permute(0, 3, 1, 2).reshape(NP * 8, Hw, Ww)[:C]
+    f32 = (u16 << 16).view(torch.int32).view(torch.float32).view(NP, Hw + 4, PW, 8)
+    mine = f32[:, 2:Hw + 2, 2:Ww + 2, :].permute(0, 3, 1, 2).reshape(NP * 8, Hw, Ww)[:C]
     e = (mine - ref[0]).abs().amax(dim=0)
     bad = (e > 0.02 * max(1.0, ref.abs().max().item())).nonzero()
-    border_ok = (f32[:, 0].abs().max().item() == 0 and f32[:, Hw + 1].abs().max().item() == 0 and f32[:, :, 0].abs().max().item() == 0)
+    border_ok = (f32[:, 0].abs().max().item() == 0 and f32[:, Hw + 3].abs().max().item() == 0 and f32[:, :, 0].abs().max().item() == 0)
     print(f"buffer {i}: C={C} max err {e.max().item():.4f} (ref max {ref.abs().max().item():.2f}) bad px {bad.shape[0]} border_zero={border_ok}",
           ("rows %d-%d cols %d-%d" % (bad[:, 0].min(), bad[:, 0].max(), bad[:, 1].min(), bad[:, 1].max())) if bad.numel() else "")

@@ -9,7 +9,7 @@ sd = O.make_pix_shuffle_state_dict(spec, 31)
 H, W, n = 576, 752, 4
 x = torch.rand(n, 3, H, W, generator=torch.Generator().manual_seed(2)).to(dev)
 Hw, Ww = H // 2, W // 2
-S = (Ww + 125) // 126; PW = 126 * (S - 1) + 128
+S = (Ww + 125) // 126; PW = 126 * S + 4
 planes = [2, 5, 5, 9, 9, 5, 5]
 
 def read_all(m):
@@ -18,10 +18,10 @@ def read_all(m):
     lib.fsuae_debug_read_bf16_buffer.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong]
     out = []
     for i, NP in enumerate(planes):
-        nb = NP * (Hw + 2) * PW * 16 * n
+        nb = NP * (Hw + 4) * PW * 16 * n
         buf = np.zeros(nb, dtype=np.uint8)
         lib.fsuae_debug_read_bf16_buffer(eng._h, i, buf.ctypes.data, nb)
-        out.append(torch.from_numpy(buf.view(np.int16).copy()).view(n, NP, Hw + 2, PW, 8))
+        out.append(torch.from_numpy(buf.view(np.int16).copy()).view(n, NP, Hw + 4, PW, 8))
     return out
 
 os.environ["FSUAE_NO_PAIRS"] = "1"

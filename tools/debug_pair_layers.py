@@ -26,15 +26,15 @@ l5 = conv(5, l4)
 l6 = act("l6_act2", act("l6_act1", conv(6, torch.cat([l1, l5], 1))))
 refs = [t0, l1, l2, l3, l4, l5, l6]
 Hw, Ww = H // 2, W // 2
-S = (Ww + 125) // 126; PW = 126 * (S - 1) + 128
+S = (Ww + 125) // 126; PW = 126 * S + 4
 for i, ref in enumerate(refs):
     C = ref.shape[1]; NP = (C + 7) // 8 if i else 2
-    fbytes = NP * (Hw + 2) * PW * 16
+    fbytes = NP * (Hw + 4) * PW * 16
     buf = np.zeros(fbytes * n, dtype=np.uint8)
     lib.fsuae_debug_read_bf16_buffer(eng._h, i, buf.ctypes.data, fbytes * n)
     u16 = torch.from_numpy(buf.view(np.uint16).astype(np.int32))
-    f32 = (u16 << 16).view(torch.int32).view(torch.float32).view(n, NP, Hw + 2, PW, 8)
-    mine = f32[:, :, 1:Hw + 1, 1:Ww + 1, :].permute(0, 1, 4, 2, 3).reshape(n, NP * 8, Hw, Ww)[:, :C]
+    f32 = (u16 << 16).view(torch.int32).view(torch.float32).view(n, NP, Hw + 4, PW, 8)
+    mine = f32[:, :, 2:Hw + 2, 2:Ww + 2, :].permute(0, 1, 4, 2, 3).reshape(n, NP * 8, Hw, Ww)[:, :C]
     e = (mine - ref).abs().amax(dim=1)
     thr = 0.03 * max(1.0, ref.abs().max().item())
     bad = (e > thr).nonzero()
