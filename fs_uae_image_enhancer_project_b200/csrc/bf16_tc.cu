@@ -18,8 +18,8 @@
 //
 // Warp roles (576 threads, one persistent CTA per SM): warp 0 = TMA producer, warp 1 = MMA issuer
 // (one elected lane), warps 2-17 = four epilogue warpgroups (thread = pixel, TMEM lane = pixel);
-// warpgroup g drains accumulator stage g, i.e. every fourth strip row, so the activation math of
-// four rows overlaps the MMAs of the following ones.
+// warpgroup g drains every fourth strip row; there are up to 8 accumulator stages in TMEM, so the
+// MMAs run several rows ahead of the activation math.
 //
 // Reference semantics: model/model_pix_shuffle.py:227-298 (and activations.py for the slots).
 #include <algorithm>
@@ -81,7 +81,7 @@ struct Cfg {
   static constexpr int ROWBYTES = PT * PLANE_ROW;
   static constexpr int RING_FIT = (SMEM_LIMIT - WBYTES - 64 - 512) / ROWBYTES;
   static constexpr int RING = RING_FIT > 10 ? 10 : RING_FIT;
-  static constexpr int STAGES = EPI_WG;
+  static constexpr int STAGES = (512 / NPAD) > 8 ? 8 : (512 / NPAD);   // accumulator stages: more than warpgroups, so the MMAs run ahead of the (MUFU-bound) epilogues
   static constexpr int BAR_OFF = WBYTES + RING * ROWBYTES + 64;
   static constexpr int SMEM = BAR_OFF + 512;
   static_assert(RING >= 4, "layer does not fit: weights + 4 ring rows exceed shared memory");
@@ -385,9 +385,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
     // ======================= epilogue (warps 2..17) =======================
     const int q = warp & 3;                    // TMEM lane quadrant this warp may access
     const int m = q * 32 + lane;               // pixel index inside the strip row
-    const uint32_t stage = (uint32_t)(warp - 2) >> 2;   // this warpgroup's accumulator stage
+    const uint32_t group = (uint32_t)(warp - 2) >> 2;   // warpgroup g drains blocks g, g+4, g+8, ...
     asm volatile("griddepcontrol.wait;" ::: "memory");   // epilogues read the frame / write buffers earlier layers still read
-    uint32_t spar = 0, blk = 0, qrow = 0;      // qrow: ring-row counter at the start of the item
+    // Block n lives in accumulator stage n % STAGES (use number n / STAGES).  A group's previous block is n-4 and
+    // the MMAs commit in order, so when it waits for block n the stage's previous use (block n-STAGES) has long
+    // been committed: the parity wait can never be a whole phase ahead.
+    uint32_t blk = 0, qrow = 0;                // qrow: ring-row counter at the start of the item
     SegIter it(P, CTAS, (int)rank);
     Seg sg;
     while (it.next(P, sg)) {
@@ -395,7 +398,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
       const int x = s * STRIP + m;
       const bool valid = m < STRIP && x < P.Ww;
       for (int b = 0; b < rows; ++b, ++blk) {
-        if ((blk & (EPI_WG - 1)) != stage) continue;
+        if ((blk & (EPI_WG - 1)) != group) continue;
+        const uint32_t stage = blk % C::STAGES, spar = (blk / C::STAGES) & 1u;
         const int y = y0 + b;
         const size_t pix = (size_t)(y + BORDER) * row_pitch + (size_t)(x + BORDER) * 16;
         // tail: issue the loads of the input pixels (global residual) now, consume them only after the accumulator
@@ -593,7 +597,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
         if (lane == 0) {
           if constexpr (CTAS == 2) mbar_arrive_cluster(&tempty[stage], 0); else mbar_arrive(&tempty[stage]);
         }
-        spar ^= 1;
       }
       qrow += (uint32_t)rows + 2;
     }
@@ -604,6 +607,335 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
   if (warp == 1) {
     if constexpr (CTAS == 2) tmem_dealloc_2cta(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused pair of layers A -> B in one kernel (CTA pairs only)
+//
+// Layer A's output never goes to global memory: its epilogue writes bf16 rows straight into the
+// shared-memory ring layer B's MMAs read.  A computes 128 valid columns per strip row (x0-1 .. x0+126,
+// from a 130-slot input row) and rows y0-1 .. y0+rows of a segment, zeroing everything outside the
+// frame (B's conv must see zero padding, not A applied to padding).  Used for conv3 -> conv4 of the
+// flagship: conv3 alone is bound by its 9-plane HBM write, conv4 by its activation epilogue; fused,
+// the write disappears and A's MMAs run underneath B's epilogue.
+//
+// Block schedule of a segment with R rows:  A(0) A(1) A(2) B(0) A(3) B(1) ... A(R+1) B(R-1);
+// every block takes the next TMEM stage / epilogue warpgroup in turn.
+// ------------------------------------------------------------------------------------------------
+template <int PA, int NA, int CA, int NBP, int CB>
+struct FusedCfg {
+  static constexpr int PB = (CA + 7) / 8;                   // B's input planes = A's output planes
+  static constexpr int PLANE_ROW_A = (MROWS + 2) * 16;      // 130 slots per plane row of A's input
+  static constexpr int STEPS_ROW_A = (3 * PA + 1) / 2, STEPS_A = 3 * STEPS_ROW_A;
+  static constexpr int STEPS_ROW_B = (3 * PB + 1) / 2, STEPS_B = 3 * STEPS_ROW_B;
+  static constexpr int NBA = NA / 2, NBB = NBP / 2;         // weight rows per CTA of the pair
+  static constexpr int WBYTES_A = STEPS_A * NBA * 32, WBYTES_B = STEPS_B * NBB * 32;
+  static constexpr int ROWBYTES_A = PA * PLANE_ROW_A, ROWBYTES_B = PB * PLANE_ROW;
+  static constexpr int RA = 4, RB = 5;                      // ring depths
+  static constexpr int LAG = 3;                             // B(j) is issued after A(j+LAG): A's epilogue for row j+2 has a whole block of slack
+  static_assert(RB >= LAG + 2, "ringB must hold the rows B reads plus the rows A runs ahead");
+  static constexpr int OFF_WB = WBYTES_A, OFF_RA = OFF_WB + WBYTES_B, OFF_RB = OFF_RA + RA * ROWBYTES_A;
+  static constexpr int BAR_OFF = OFF_RB + RB * ROWBYTES_B + 64;
+  static constexpr int SMEM = BAR_OFF + 1024;
+  static constexpr int NSTAGE = NA > NBP ? NA : NBP;        // TMEM columns per accumulator stage
+  static constexpr int STAGES = (512 / NSTAGE) > 8 ? 8 : (512 / NSTAGE);
+  static_assert(SMEM <= SMEM_LIMIT + 1024, "fused pair does not fit in shared memory");
+  static_assert(STAGES >= 6, "the warpgroup rotation below needs at least 6 accumulator stages");
+  static_assert(OFF_RA % 16 == 0 && OFF_RB % 16 == 0 && NBA % 8 == 0 && NBB % 8 == 0, "operand alignment");
+};
+
+// one strip row = 3 input rows x STEPS_ROW instructions; see conv3x3_tc_kernel for the unit/LBO pattern
+template <int PT, int PR16, int NBROWS>
+__device__ __forceinline__ void issue_block_2cta(uint32_t d_tmem, uint32_t ring_lo, uint32_t row16, uint32_t rs, uint32_t ring_n,
+                                                 uint32_t w_lo, uint32_t idesc) {
+  constexpr uint32_t HI = (uint32_t)((128u >> 4)) | (1u << 14);
+  constexpr uint32_t BSTEP = (NBROWS * 32) >> 4;
+  constexpr uint32_t L16 = 1u << 16, L2K = (uint32_t)(PR16 - 2) << 16;
+  constexpr int STEPS_ROW = (3 * PT + 1) / 2, G3 = STEPS_ROW / 3, REM = STEPS_ROW % 3;
+  static_assert(REM == 0 || REM == 2, "unexpected instruction count per row");
+  uint32_t acc = 0, b_lo = w_lo;
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    uint32_t a_lo = ring_lo + rs * row16;
+#pragma unroll 1
+    for (int g3 = 0; g3 < G3; ++g3) {
+      umma_bf16_2cta(d_tmem, ((uint64_t)HI << 32) | (a_lo | L16), ((uint64_t)HI << 32) | b_lo, idesc, acc);
+      umma_bf16_2cta(d_tmem, ((uint64_t)HI << 32) | ((a_lo + 2) | L2K), ((uint64_t)HI << 32) | (b_lo + BSTEP), idesc, 1);
+      umma_bf16_2cta(d_tmem, ((uint64_t)HI << 32) | ((a_lo + PR16 + 1) | L16), ((uint64_t)HI << 32) | (b_lo + 2 * BSTEP), idesc, 1);
+      acc = 1;
+      a_lo += 2 * PR16;
+      b_lo += 3 * BSTEP;
+    }
+    if constexpr (REM == 2) {
+      umma_bf16_2cta(d_tmem, ((uint64_t)HI << 32) | (a_lo | L16), ((uint64_t)HI << 32) | b_lo, idesc, acc);
+      acc = 1;
+      umma_bf16_2cta(d_tmem, ((uint64_t)HI << 32) | ((a_lo + 1) | L16), ((uint64_t)HI << 32) | (b_lo + BSTEP), idesc, 1);
+      b_lo += 2 * BSTEP;
+    }
+    if (++rs == ring_n) rs = 0;
+  }
+}
+
+template <int PA, int NA, int CA, class EPIA, int NBP, int CB, class EPIB>
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv3x3_tc_fused_pair_kernel(const __grid_constant__ LayerK A, const __grid_constant__ LayerK P) {
+  using C = FusedCfg<PA, NA, CA, NBP, CB>;
+  constexpr int OUT_PLANES_B = (CB + 7) / 8;
+  const uint32_t rank = cluster_ctarank();
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* s_wa = smem;
+  uint8_t* s_wb = smem + C::OFF_WB;
+  uint8_t* s_ra = smem + C::OFF_RA;
+  uint8_t* s_rb = smem + C::OFF_RB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
+  uint64_t* fullA = bars;                      // [RA] TMA -> MMA
+  uint64_t* emptyA = fullA + C::RA;            // [RA] MMA -> TMA
+  uint64_t* pfullA = emptyA + C::RA;           // [RA] leader: peer's row landed
+  uint64_t* fullB = pfullA + C::RA;            // [RB] A-epilogue (4 warps) -> MMA / residual readers
+  uint64_t* emptyB = fullB + C::RB;            // [RB] MMA commit (+ 4 residual readers) -> A-epilogue
+  uint64_t* pfullB = emptyB + C::RB;           // [RB] leader: peer's row written
+  uint64_t* tfull = pfullB + C::RB;            // [STAGES]
+  uint64_t* tempty = tfull + C::STAGES;        // [STAGES]
+  uint64_t* wbar = tempty + C::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C::RA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); mbar_init(&pfullA[i], 1); }
+    for (int i = 0; i < C::RB; ++i) { mbar_init(&fullB[i], 4); mbar_init(&emptyB[i], EPIB::kSkip ? 5 : 1); mbar_init(&pfullB[i], 1); }
+    for (int i = 0; i < C::STAGES; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    mbar_init(wbar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2cta(tmem_slot, 512);
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + 16) reinterpret_cast<uint32_t*>(s_rb + C::RB * C::ROWBYTES_B)[threadIdx.x - 64] = 0u;
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  const size_t row_pitch = (size_t)P.PW * 16;
+  const size_t plane_pitch = (size_t)(P.Hw + 2 * BORDER) * row_pitch;
+
+  if (warp == 0) {
+    // ======================= TMA producer: A's input rows y0-2 .. y0+rows+1, columns x0-2 .. x0+127 =======================
+    if (elect_one()) {
+      mbar_arrive_expect_tx(wbar, C::WBYTES_A + C::WBYTES_B);
+      tma_load_1d(s_wa, A.wpack + (size_t)rank * C::WBYTES_A, C::WBYTES_A, wbar);
+      tma_load_1d(s_wb, P.wpack + (size_t)rank * C::WBYTES_B, C::WBYTES_B, wbar);
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      uint32_t slot = 0, par = 1;
+      SegIter it(P, 2, (int)rank);
+      Seg sg;
+      while (it.next(P, sg)) {
+        const unsigned char* g0 = A.src0 + (size_t)sg.f * A.fs0 + (size_t)(sg.y0 - 2 + BORDER) * row_pitch +
+                                  (size_t)(sg.s * STRIP - 2 + BORDER) * 16;
+        for (int k = 0; k < sg.rows + 4; ++k) {
+          mbar_wait(&emptyA[slot], par);
+          mbar_arrive_expect_tx(&fullA[slot], C::ROWBYTES_A);
+          uint8_t* d = s_ra + slot * C::ROWBYTES_A;
+          for (int j = 0; j < PA; ++j)
+            tma_load_1d(d + j * C::PLANE_ROW_A, g0 + (size_t)j * plane_pitch + (size_t)k * row_pitch, C::PLANE_ROW_A, &fullA[slot]);
+          if (++slot == C::RA) { slot = 0; par ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && rank != 0) {
+    // ======================= peer: relay landed / written rows to the leader, in the leader's wait order =======================
+    if (elect_one()) {
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+      mbar_wait(wbar, 0);
+      SegIter it(P, 2, (int)rank);
+      Seg sg;
+      auto relayA = [&]() { mbar_wait(&fullA[sa], pa); mbar_arrive_cluster(&pfullA[sa], 0); if (++sa == C::RA) { sa = 0; pa ^= 1; } };
+      auto relayB = [&]() { mbar_wait(&fullB[sb], pb); mbar_arrive_cluster(&pfullB[sb], 0); if (++sb == C::RB) { sb = 0; pb ^= 1; } };
+      while (it.next(P, sg)) {
+        for (int i = 0; i < sg.rows + C::LAG; ++i) {
+          if (i < sg.rows + 2) {
+            if (i == 0) { relayA(); relayA(); }
+            relayA();
+          }
+          if (i >= C::LAG) {
+            if (i == C::LAG) { relayB(); relayB(); }
+            relayB();
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= leader: MMA issue for both layers =======================
+    if (elect_one()) {
+      constexpr uint32_t IDA = umma_idesc_bf16(2 * MROWS, NA), IDB = umma_idesc_bf16(2 * MROWS, NBP);
+      const uint32_t ra_lo = (smem_u32(s_ra) & 0x3FFFFu) >> 4, rb_lo = (smem_u32(s_rb) & 0x3FFFFu) >> 4;
+      const uint32_t wa_lo = ((smem_u32(s_wa) & 0x3FFFFu) >> 4) | ((uint32_t)((C::NBA * 16) >> 4) << 16);
+      const uint32_t wb_lo = ((smem_u32(s_wb) & 0x3FFFFu) >> 4) | ((uint32_t)((C::NBB * 16) >> 4) << 16);
+      mbar_wait(wbar, 0);
+      uint32_t wa = 0, wpa = 0;           // next ringA slot to wait for
+      uint32_t wb = 0, wpb = 0;           // next ringB slot to wait for
+      uint32_t nblk = 0, stage = 0, spar = 1;      // block counter; stage = n % STAGES, use number n / STAGES
+      auto waitA = [&]() { mbar_wait(&fullA[wa], wpa); mbar_wait(&pfullA[wa], wpa); if (++wa == C::RA) { wa = 0; wpa ^= 1; } };
+      auto waitB = [&]() { mbar_wait(&fullB[wb], wpb); mbar_wait(&pfullB[wb], wpb); if (++wb == C::RB) { wb = 0; wpb ^= 1; } };
+      auto next_stage = [&]() { ++nblk; stage = nblk % C::STAGES; spar = ((nblk / C::STAGES) & 1u) ^ 1u; };
+      SegIter it(P, 2, (int)rank);
+      Seg sg;
+      while (it.next(P, sg)) {
+        const int rows = sg.rows;
+        uint32_t a0 = wa, b0 = wb;        // slots of the first input row of the next A / B block
+        for (int i = 0; i < rows + C::LAG; ++i) {
+          // ---- A(i): image row y0-1+i from ringA rows i, i+1, i+2 ----
+          if (i < rows + 2) {
+          if (i == 0) { waitA(); waitA(); }
+          waitA();
+          mbar_wait(&tempty[stage], spar);
+          tc_fence_after();
+          issue_block_2cta<PA, C::PLANE_ROW_A / 16, C::NBA>(tmem_base + stage * C::NSTAGE, ra_lo, C::ROWBYTES_A >> 4, a0, C::RA, wa_lo, IDA);
+          umma_commit_2cta(&tfull[stage]);
+          umma_commit_2cta(&emptyA[a0]);
+          if (i == rows + 1) {
+            uint32_t s1 = a0 + 1 == C::RA ? 0 : a0 + 1, s2 = s1 + 1 == C::RA ? 0 : s1 + 1;
+            umma_commit_2cta(&emptyA[s1]);
+            umma_commit_2cta(&emptyA[s2]);
+          }
+          if (++a0 == C::RA) a0 = 0;
+          next_stage();
+          }
+          // ---- B(i-LAG): image row y0+i-LAG from ringB rows i-LAG .. i-LAG+2 ----
+          if (i >= C::LAG) {
+            if (i == C::LAG) { waitB(); waitB(); }
+            waitB();
+            mbar_wait(&tempty[stage], spar);
+            tc_fence_after();
+            issue_block_2cta<C::PB, PLANE_ROW / 16, C::NBB>(tmem_base + stage * C::NSTAGE, rb_lo, C::ROWBYTES_B >> 4, b0, C::RB, wb_lo, IDB);
+            umma_commit_2cta(&tfull[stage]);
+            umma_commit_2cta(&emptyB[b0]);
+            if (i == rows + C::LAG - 1) {
+              uint32_t s1 = b0 + 1 == C::RB ? 0 : b0 + 1, s2 = s1 + 1 == C::RB ? 0 : s1 + 1;
+              umma_commit_2cta(&emptyB[s1]);
+              umma_commit_2cta(&emptyB[s2]);
+            }
+            if (++b0 == C::RB) b0 = 0;
+            next_stage();
+          }
+        }
+      }
+    }
+  } else {
+    // ======================= epilogue warpgroups =======================
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const uint32_t group = (uint32_t)(warp - 2) >> 2;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // Block n lives in accumulator stage n % STAGES (use number n / STAGES) and is drained by warpgroup
+    // (n + n/2) & 3.  That rotation gives every group both A blocks (light) and B blocks (heavy epilogue) -- with
+    // n & 3 the strict A B A B order would leave all of B's activation math to two groups -- and consecutive
+    // blocks of one group are at most 5 apart (< STAGES), so when a group waits for block n the stage's previous
+    // use (block n-STAGES) was committed before the group's own previous block: no parity wait can run a phase ahead.
+    uint32_t blk = 0, qB = 0;                  // qB: ringB row counter at the start of the segment
+    auto mine = [&](uint32_t n) { return ((n + (n >> 1)) & 3u) == group; };
+    SegIter it(P, 2, (int)rank);
+    Seg sg;
+    while (it.next(P, sg)) {
+      const int f = sg.f, s = sg.s, y0 = sg.y0, rows = sg.rows;
+      for (int i = 0; i < rows + C::LAG; ++i) {
+        // ---------------- A(i): write image row ya of A's output into ringB ----------------
+        if (i < rows + 2)
+        if (const uint32_t n = blk++; mine(n)) {
+          const uint32_t stage = n % C::STAGES, spar = (n / C::STAGES) & 1u;
+          const int ya = y0 - 1 + i, xa = s * STRIP - 1 + m;
+          const bool inframe = ya >= 0 && ya < P.Hw && xa >= 0 && xa < P.Ww;
+          const uint32_t kb = qB + (uint32_t)i, slot = kb % C::RB;
+          mbar_wait(&tfull[stage], spar);
+          tc_fence_after();
+          mbar_wait(&emptyB[slot], ((kb / C::RB) & 1) ^ 1);      // the row that lived here has been consumed
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + stage * C::NSTAGE;
+          uint8_t* dp = s_rb + slot * C::ROWBYTES_B + m * 16;
+#pragma unroll
+          for (int c = 0; c < C::PB; ++c) {
+            uint32_t v[8];
+            tmem_ld_x8(taddr + c * 8, v);
+            tmem_ld_wait();
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int ch = c * 8 + e;
+              if (ch >= CA) { o[e] = 0.f; continue; }
+              float t = EPIA::post(A, ch, EPIA::pre(A, ch, __uint_as_float(v[e]) + A.bias[ch]));
+              o[e] = inframe ? t : 0.f;         // B's conv sees zero padding outside the frame
+            }
+            *reinterpret_cast<uint4*>(dp + c * PLANE_ROW) =
+                make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+          }
+          fence_proxy_async_smem();             // generic-proxy stores -> visible to the tensor core's reads
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) { mbar_arrive(&fullB[slot]); mbar_arrive_cluster(&tempty[stage], 0); }
+        }
+        // ---------------- B(i-LAG): image row y of B's output to global memory ----------------
+        if (i >= C::LAG) {
+          if (const uint32_t n = blk++; mine(n)) {
+            const uint32_t stage = n % C::STAGES, spar = (n / C::STAGES) & 1u;
+            const int b = i - C::LAG, y = y0 + b, x = s * STRIP + m;
+            const bool valid = m < STRIP && x < P.Ww;
+            const size_t pix = (size_t)(y + BORDER) * row_pitch + (size_t)(x + BORDER) * 16;
+            mbar_wait(&tfull[stage], spar);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + stage * C::NSTAGE;
+            const uint32_t kc = qB + (uint32_t)b + 1, cslot = kc % C::RB;     // centre row of the block
+            uint4 sk[EPIB::kSkip ? OUT_PLANES_B : 1];
+            if constexpr (EPIB::kSkip) {
+              mbar_wait(&fullB[cslot], (kc / C::RB) & 1);         // acquire the other warps' row stores
+              const uint8_t* sp = s_rb + cslot * C::ROWBYTES_B + (m + 1) * 16;
+#pragma unroll
+              for (int c = 0; c < OUT_PLANES_B; ++c)
+                sk[c] = valid ? *reinterpret_cast<const uint4*>(sp + c * PLANE_ROW) : make_uint4(0, 0, 0, 0);
+            }
+            unsigned char* dp = P.dst + (size_t)f * P.fs_dst + pix;
+#pragma unroll
+            for (int c = 0; c < OUT_PLANES_B; ++c) {
+              uint32_t v[8];
+              tmem_ld_x8(taddr + c * 8, v);
+              tmem_ld_wait();
+              float o[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int ch = c * 8 + e;
+                if (ch >= CB) { o[e] = 0.f; continue; }
+                float t = EPIB::pre(P, ch, __uint_as_float(v[e]) + P.bias[ch]);
+                if constexpr (EPIB::kSkip) {
+                  const uint32_t w = (&sk[c].x)[e >> 1];
+                  t += (e & 1) ? bf16_hi(w) : bf16_lo(w);
+                }
+                o[e] = EPIB::post(P, ch, t);
+              }
+              if (valid)
+                *reinterpret_cast<uint4*>(dp + (size_t)c * plane_pitch) =
+                    make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (EPIB::kSkip) {       // residual values consumed: release the ring rows (see conv3x3_tc_kernel)
+                mbar_arrive(&emptyB[cslot]);
+                if (b == 0) mbar_arrive(&emptyB[(kc - 1) % C::RB]);
+                if (b == rows - 1) mbar_arrive(&emptyB[(kc + 1) % C::RB]);
+              }
+              mbar_arrive_cluster(&tempty[stage], 0);
+            }
+          }
+        }
+      }
+      qB += (uint32_t)rows + 2;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2cta(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -827,6 +1159,10 @@ struct Bf16Plan {
   std::vector<int> planes;
   std::vector<size_t> buf_bytes;
   int zero_Hw = -1, zero_Ww = -1;      // geometry the borders are currently valid for
+  // fused layer pair (0-based index of layer A, -1: none): A's output never leaves the SM
+  int fused_at = -1;
+  void (*fused_fn)(const LayerK, const LayerK) = nullptr;
+  int fused_smem = 0;
 };
 
 static int planes_of(int c) { return (c + 7) / 8; }
@@ -936,6 +1272,36 @@ int bf16_create(fsuae_engine* e) {
     }
     FSUAE_CUDA_CHECK(e, cudaFuncSetAttribute((const void*)var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, var->smem));
   }
+  // conv3 -> conv4 of the flagship preset can run as one fused kernel on CTA pairs
+  if (!getenv("FSUAE_NO_FUSION")) {
+    using FusedEpiA = Epi<0, 0, 0, 0, false>;
+    using FusedEpiB = Epi<FSUAE_ACT_MISH, FSUAE_ACT_BIASED_PRELU, FSUAE_ACT_TANH, FSUAE_ACT_RELU, true>;
+    for (int i = 0; i + 1 < d.n_layers - 1; ++i) {
+      const fsuae_layer_desc& LA = d.layers[i];
+      const fsuae_layer_desc& LB = d.layers[i + 1];
+      const LayerPlan& pa = plan->layers[i];
+      const LayerPlan& pb = plan->layers[i + 1];
+      if (pa.launches.size() != 1 || pb.launches.size() != 1 || !pa.launches[0].var2 || !pb.launches[0].var2) continue;
+      const Variant* va = pa.launches[0].var;
+      const Variant* vb = pb.launches[0].var;
+      const bool a_ok = va->PT == 5 && va->NPAD == 80 && va->COUT == 72 && va->skip == 0 && va->pre0 == 0 && va->pre1 == 0 &&
+                        va->post0 == 0 && va->post1 == 0 && LA.cin1 == 0;
+      const bool b_ok = vb->PT == 9 && vb->NPAD == 80 && vb->COUT == 72 && vb->skip == 1 && vb->pre0 == FSUAE_ACT_MISH &&
+                        vb->pre1 == FSUAE_ACT_BIASED_PRELU && vb->post0 == FSUAE_ACT_TANH && vb->post1 == FSUAE_ACT_RELU &&
+                        LB.src0 == i + 1 && LB.cin1 == 0 && LB.skip_src == i + 1;
+      bool a_private = true;     // nobody else reads A's output
+      for (int j = 0; j < d.n_layers; ++j)
+        if (j != i + 1 && (d.layers[j].src0 == i + 1 || (d.layers[j].cin1 > 0 && d.layers[j].src1 == i + 1) || d.layers[j].skip_src == i + 1))
+          a_private = false;
+      if (a_ok && b_ok && a_private) {
+        plan->fused_at = i;
+        plan->fused_fn = conv3x3_tc_fused_pair_kernel<5, 80, 72, FusedEpiA, 80, 72, FusedEpiB>;
+        plan->fused_smem = FusedCfg<5, 80, 72, 80, 72>::SMEM;
+        FSUAE_CUDA_CHECK(e, cudaFuncSetAttribute((const void*)plan->fused_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->fused_smem));
+        break;
+      }
+    }
+  }
   // activation buffers at the largest geometry (no crop)
   const int Hw = unshuffle ? e->H / 2 : e->H, Ww = unshuffle ? e->W / 2 : e->W;
   const int S = (Ww + STRIP - 1) / STRIP, PW = plane_width(S);
@@ -986,41 +1352,57 @@ int bf16_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in
                                                             fstride(0), gin);
   e->launches++;
 
-  for (int i = 0; i < d.n_layers; ++i) {
+  auto fill = [&](int i, const Launch& ln, bool pair) {
     const fsuae_layer_desc& L = d.layers[i];
+    LayerK k = ln.k;
+    k.Hw = g.Hw; k.Ww = g.Ww; k.PW = PW; k.S = S; k.n_frames = n;
+    if (pair) k.wpack = ln.d_w2;
+    k.n_blocks = (pair ? (n + 1) / 2 : n) * S * g.Hw;
+    k.src0 = plan->buf[L.src0]; k.fs0 = fstride(L.src0);
+    if (L.cin1 > 0) { k.src1 = plan->buf[L.src1]; k.fs1 = fstride(L.src1); }
+    if (L.skip_src >= 0) { k.skip = plan->buf[L.skip_src]; k.fs_skip = fstride(L.skip_src); }
+    if (i < d.n_layers - 1) { k.dst = plan->buf[i + 1]; k.fs_dst = fstride(i + 1); }
+    k.frame_in = in; k.frame_out = out; k.in_fmt = in_fmt; k.out_fmt = out_fmt;
+    k.H = g.H; k.W = g.W; k.xoff = g.xoff;
+    k.gamma_in = gin;
+    k.gamma_out = (flags & FSUAE_FLAG_GAMMA_OUT) ? 1 : 0;
+    return k;
+  };
+  auto launch_cfg = [&](cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int n_blocks, int ctas, int smem) {
+    int grid = std::min(n_blocks * ctas, e->sm_count / ctas * ctas);
+    if (const char* g_env = getenv("FSUAE_DEBUG_GRID")) grid = std::max(ctas, std::min(n_blocks * ctas, atoi(g_env) / ctas * ctas));   // debugging aid: force the CTA count
+    cfg = cudaLaunchConfig_t{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 1;
+    if (ctas == 2) {
+      attr[1].id = cudaLaunchAttributeClusterDimension;
+      attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+      cfg.numAttrs = 2;
+    }
+    cfg.attrs = attr;
+  };
+  for (int i = 0; i < d.n_layers; ++i) {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[2];
+    if (i == plan->fused_at && n >= 2) {          // layers i and i+1 as one kernel
+      const LayerK ka = fill(i, plan->layers[i].launches[0], true);
+      const LayerK kb = fill(i + 1, plan->layers[i + 1].launches[0], true);
+      launch_cfg(cfg, attr, kb.n_blocks, 2, plan->fused_smem);
+      FSUAE_CUDA_CHECK(e, cudaLaunchKernelEx(&cfg, plan->fused_fn, ka, kb));
+      e->launches++;
+      ++i;
+      continue;
+    }
     for (Launch& ln : plan->layers[i].launches) {
-      LayerK k = ln.k;
-      k.Hw = g.Hw; k.Ww = g.Ww; k.PW = PW; k.S = S; k.n_frames = n;
       const bool pair = ln.var2 != nullptr && n >= 2;      // CTA pairs process two frames in lockstep
       const Variant* var = pair ? ln.var2 : ln.var;
-      if (pair) k.wpack = ln.d_w2;
-      k.n_blocks = (pair ? (n + 1) / 2 : n) * S * g.Hw;
-      k.src0 = plan->buf[L.src0]; k.fs0 = fstride(L.src0);
-      if (L.cin1 > 0) { k.src1 = plan->buf[L.src1]; k.fs1 = fstride(L.src1); }
-      if (L.skip_src >= 0) { k.skip = plan->buf[L.skip_src]; k.fs_skip = fstride(L.skip_src); }
-      if (i < d.n_layers - 1) { k.dst = plan->buf[i + 1]; k.fs_dst = fstride(i + 1); }
-      k.frame_in = in; k.frame_out = out; k.in_fmt = in_fmt; k.out_fmt = out_fmt;
-      k.H = g.H; k.W = g.W; k.xoff = g.xoff;
-      k.gamma_in = gin;
-      k.gamma_out = (flags & FSUAE_FLAG_GAMMA_OUT) ? 1 : 0;
-      const int ctas = pair ? 2 : 1;
-      int grid = std::min(k.n_blocks * ctas, e->sm_count / ctas * ctas);
-      if (const char* g_env = getenv("FSUAE_DEBUG_GRID")) grid = std::max(ctas, std::min(k.n_blocks * ctas, atoi(g_env) / ctas * ctas));   // debugging aid: force the CTA count
-      cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(grid);
-      cfg.blockDim = dim3(NTHREADS);
-      cfg.dynamicSmemBytes = var->smem;
-      cfg.stream = st;
-      cudaLaunchAttribute attr[2];
-      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[0].val.programmaticStreamSerializationAllowed = 1;
-      cfg.numAttrs = 1;
-      if (pair) {
-        attr[1].id = cudaLaunchAttributeClusterDimension;
-        attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
-        cfg.numAttrs = 2;
-      }
-      cfg.attrs = attr;
+      const LayerK k = fill(i, ln, pair);
+      launch_cfg(cfg, attr, k.n_blocks, pair ? 2 : 1, var->smem);
       FSUAE_CUDA_CHECK(e, cudaLaunchKernelEx(&cfg, var->fn, k));
       e->launches++;
     }
