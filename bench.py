@@ -209,6 +209,17 @@ def main():
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
 
+    # per-kernel device times (CUDA events around every launch, on the launching stream), outside the timed region
+    eng.set_profiling(True)
+    per_kernel = {}
+    for i in range(3):
+        step(i)
+        torch.cuda.synchronize(dev)
+        for label, t_ms in eng.kernel_times():
+            per_kernel.setdefault(label, []).append(t_ms)
+    eng.set_profiling(False)
+    per_kernel = {k: sum(v) / len(v) for k, v in per_kernel.items()}
+
     if args.quick:
         if rank == 0:
             print(json.dumps({"chunk": args.chunk, "fps": BATCH * world * args.steps / (ms / 1000.0),
@@ -250,6 +261,20 @@ def main():
         tf_peak, hbm_peak, how = measured_peaks()
         per_gpu_step_s = ms / 1000.0 / args.steps
         achieved_tf = GFLOP_PER_FRAME * BATCH / per_gpu_step_s / 1000.0
+        # dominant kernel: algorithmic FLOPs of the layers it runs / its own event-timed duration
+        mac = {"conv1": 3888, "conv2": 11664, "conv3": 23328, "conv4": 46656, "conv5": 23328, "conv6": 23328, "conv7": 3888}
+        dom = max(per_kernel, key=per_kernel.get) if per_kernel else None
+        dom_line = None
+        if dom:
+            layers = [l for l in mac if l in dom.replace("+", " ").replace("_", " ").split()]
+            gflop = sum(2 * mac[l] * (FRAME_H // 2) * (FRAME_W // 2) for l in layers) * BATCH / 1e9
+            dom_tf = gflop / per_kernel[dom]                    # GFLOP / ms = TFLOP/s
+            dom_line = {"kernel": dom, "ms": per_kernel[dom], "share_of_step": per_kernel[dom] / sum(per_kernel.values()),
+                        "achieved": dom_tf, "frac": dom_tf / tf_peak,
+                        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, ncu --set full, per launch of 64 frames
+                        # (profiles/r01_layers_ncu_full_summary.csv); algorithmic bytes of the fused kernel: 5 planes in +
+                        # 9 planes out of bf16 = 64 x 14 x 1.77 MB = 1.59 GB
+                        "traffic": 1.566e9 if "conv3+conv4" in dom else None}
         line = {
             "metric": "752x576 frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -263,10 +288,18 @@ def main():
                     "h2d_bytes_per_step": BATCH * FRAME_H * FRAME_W * 4, "d2h_bytes_per_step": BATCH * FRAME_H * FRAME_W * 4,
                     "steps": e2e_steps},
             "gpu_launches": int(launches_per_step * args.steps),
-            "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": tf_peak, "unit": "TFLOP/s",
-                         "frac": achieved_tf / tf_peak, "traffic": None,
-                         "note": f"algorithmic 29.472 GFLOP/frame x {BATCH} frames / step device time (all kernels of the "
-                                 f"pass); peak = {how} sustained bf16; HBM floor: {BYTES_PER_FRAME_U8 * BATCH / 1e9 / (hbm_peak) * 1e3:.3f} ms/step"},
+            "roofline": {"bound": "tensor", "achieved": dom_line["achieved"] if dom_line else achieved_tf, "peak": tf_peak,
+                         "unit": "TFLOP/s", "frac": (dom_line["achieved"] if dom_line else achieved_tf) / tf_peak,
+                         "traffic": dom_line["traffic"] if dom_line else None,
+                         "kernel": dom_line["kernel"] if dom_line else None,
+                         "kernel_ms": dom_line["ms"] if dom_line else None,
+                         "share_of_step": dom_line["share_of_step"] if dom_line else None,
+                         "note": f"dominant kernel, CUDA events on its stream; peak = {how} sustained bf16 (kernel timed inside a long step)"},
+            "roofline_whole_pass": {"bound": "tensor", "achieved": achieved_tf, "peak": tf_peak, "unit": "TFLOP/s",
+                                    "frac": achieved_tf / tf_peak,
+                                    "note": f"algorithmic 29.472 GFLOP/frame x {BATCH} frames / step device time (all kernels of the "
+                                            f"pass); HBM floor: {BYTES_PER_FRAME_U8 * BATCH / 1e9 / (hbm_peak) * 1e3:.3f} ms/step"},
+            "kernel_ms": per_kernel,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -63,6 +63,8 @@ EXPORTS = {
     "fsuae_engine_device_bytes": (C.c_size_t, [C.c_void_p]),
     "fsuae_engine_last_launch_count": (C.c_int64, [C.c_void_p]),
     "fsuae_engine_variant": (C.c_char_p, [C.c_void_p]),
+    "fsuae_engine_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "fsuae_engine_kernel_time": (C.c_float, [C.c_void_p, C.c_int, C.c_char_p, C.c_int]),
     "fsuae_last_error": (C.c_char_p, [C.c_void_p]),
 }
 

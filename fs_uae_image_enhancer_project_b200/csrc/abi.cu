@@ -220,6 +220,7 @@ int fsuae_engine_destroy(fsuae_engine* e) {
   cudaDeviceSynchronize();
   fp32_destroy(e);
   bf16_destroy(e);
+  for (cudaEvent_t ev : e->prof_ev) cudaEventDestroy(ev);
   for (int i = 0; i < 2; ++i) {
     if (e->d_stage_in[i]) cudaFree(e->d_stage_in[i]);
     if (e->d_stage_out[i]) cudaFree(e->d_stage_out[i]);
@@ -258,6 +259,7 @@ int fsuae_engine_enqueue(fsuae_engine* e, const void* in_dev, void* out_dev, int
   int rc = check_formats(e, in_fmt, out_fmt, flags);
   if (rc != FSUAE_OK) return rc;
   e->launches = 0;
+  e->prof_n = 0;
   if (n_frames == 0) return FSUAE_OK;
   int prev = 0;
   cudaGetDevice(&prev);
@@ -326,6 +328,24 @@ int fsuae_engine_run_host(fsuae_engine* e, const void* in_host, void* out_host, 
     rc = set_error(e, FSUAE_ERR_CUDA, cudaGetErrorString(ce != cudaSuccess ? ce : (ce2 != cudaSuccess ? ce2 : ce3)));
   if (prev != e->device) cudaSetDevice(prev);
   return rc;
+}
+
+int fsuae_engine_set_profiling(fsuae_engine* e, int enabled) {
+  if (!e) return FSUAE_ERR_INVALID;
+  e->profiling = enabled != 0;
+  e->prof_n = 0;
+  return FSUAE_OK;
+}
+
+float fsuae_engine_kernel_time(fsuae_engine* e, int index, char* label, int label_bytes) {
+  if (!e || index < 0 || index >= e->prof_n) return -1.f;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, e->prof_ev[2 * index], e->prof_ev[2 * index + 1]) != cudaSuccess) return -1.f;
+  if (label && label_bytes > 0) {
+    strncpy(label, e->prof_label[index].c_str(), label_bytes - 1);
+    label[label_bytes - 1] = 0;
+  }
+  return ms;
 }
 
 size_t fsuae_engine_device_bytes(const fsuae_engine* e) { return e ? e->device_bytes : 0; }

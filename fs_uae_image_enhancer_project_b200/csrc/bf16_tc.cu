@@ -1344,12 +1344,14 @@ int bf16_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in
   auto fstride = [&](int id) { return (unsigned long long)plan->planes[id] * (g.Hw + 2 * BORDER) * PW * 16; };
 
   const int gin = (flags & FSUAE_FLAG_GAMMA_IN) ? 1 : 0;
+  { ProfScope ps(e, st, "head");
   if (d.head == FSUAE_HEAD_UNSHUFFLE2)
     head_unshuffle_bf16_kernel<<<e->sm_count * 8, 256, 0, st>>>(in, plan->buf[0], n, in_fmt, g.H, g.W, g.xoff, g.Hw, g.Ww, PW,
                                                                 fstride(0), gin);
   else
     head_plain_bf16_kernel<<<e->sm_count * 8, 256, 0, st>>>(in, plan->buf[0], n, in_fmt, g.H, g.W, g.xoff, g.Hw, g.Ww, PW,
                                                             fstride(0), gin);
+  }
   e->launches++;
 
   auto fill = [&](int i, const Launch& ln, bool pair) {
@@ -1393,7 +1395,8 @@ int bf16_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in
       const LayerK ka = fill(i, plan->layers[i].launches[0], true);
       const LayerK kb = fill(i + 1, plan->layers[i + 1].launches[0], true);
       launch_cfg(cfg, attr, kb.n_blocks, 2, plan->fused_smem);
-      FSUAE_CUDA_CHECK(e, cudaLaunchKernelEx(&cfg, plan->fused_fn, ka, kb));
+      { ProfScope ps(e, st, ("conv" + std::to_string(i + 1) + "+conv" + std::to_string(i + 2) + "_fused_pair").c_str());
+        FSUAE_CUDA_CHECK(e, cudaLaunchKernelEx(&cfg, plan->fused_fn, ka, kb)); }
       e->launches++;
       ++i;
       continue;
@@ -1403,7 +1406,8 @@ int bf16_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in
       const Variant* var = pair ? ln.var2 : ln.var;
       const LayerK k = fill(i, ln, pair);
       launch_cfg(cfg, attr, k.n_blocks, pair ? 2 : 1, var->smem);
-      FSUAE_CUDA_CHECK(e, cudaLaunchKernelEx(&cfg, var->fn, k));
+      { ProfScope ps(e, st, ("conv" + std::to_string(i + 1) + (pair ? "_pair" : "")).c_str());
+        FSUAE_CUDA_CHECK(e, cudaLaunchKernelEx(&cfg, var->fn, k)); }
       e->launches++;
     }
   }

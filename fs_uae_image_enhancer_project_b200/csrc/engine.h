@@ -40,6 +40,12 @@ struct fsuae_engine {
   // bf16 build
   fsuae::Bf16Plan* bf16 = nullptr;
 
+  // optional per-launch timing (fsuae_engine_set_profiling)
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_ev;        // 2 events per launch slot
+  std::vector<std::string> prof_label;
+  int prof_n = 0;
+
   // run_host staging
   void* d_stage_in[2] = {nullptr, nullptr};
   void* d_stage_out[2] = {nullptr, nullptr};
@@ -96,6 +102,20 @@ int bf16_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in
                        uint32_t flags, cudaStream_t st);
 
 int set_error(fsuae_engine* e, int code, const std::string& msg);
+
+// bracket one kernel launch with events when profiling is on
+struct ProfScope {
+  fsuae_engine* e; cudaStream_t st; int slot;
+  ProfScope(fsuae_engine* e_, cudaStream_t st_, const char* label) : e(e_), st(st_), slot(-1) {
+    if (!e->profiling) return;
+    slot = e->prof_n++;
+    while ((int)e->prof_ev.size() < 2 * (slot + 1)) { cudaEvent_t ev; cudaEventCreate(&ev); e->prof_ev.push_back(ev); }
+    if ((int)e->prof_label.size() <= slot) e->prof_label.resize(slot + 1);
+    e->prof_label[slot] = label;
+    cudaEventRecord(e->prof_ev[2 * slot], st);
+  }
+  ~ProfScope() { if (slot >= 0) cudaEventRecord(e->prof_ev[2 * slot + 1], st); }
+};
 
 #define FSUAE_CUDA_CHECK(e, call)                                                              \
   do {                                                                                         \

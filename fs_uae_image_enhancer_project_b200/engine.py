@@ -55,6 +55,21 @@ class Engine:
     def last_launch_count(self) -> int:
         return int(self._lib.fsuae_engine_last_launch_count(self._h))
 
+    def set_profiling(self, enabled: bool):
+        """Bracket every kernel launch with CUDA events (measurement aid; adds a little launch overhead)."""
+        self._check(self._lib.fsuae_engine_set_profiling(self._h, int(enabled)))
+
+    def kernel_times(self):
+        """[(label, ms), ...] of the last enqueue; synchronise the stream first."""
+        out, buf = [], C.create_string_buffer(96)
+        i = 0
+        while True:
+            ms = self._lib.fsuae_engine_kernel_time(self._h, i, buf, 96)
+            if ms < 0:
+                return out
+            out.append((buf.value.decode(), float(ms)))
+            i += 1
+
     def enqueue(self, x: torch.Tensor, out: torch.Tensor, n_frames: int, in_fmt: int, out_fmt: int,
                 flags: int = 0, stream: Optional[torch.cuda.Stream] = None):
         """Asynchronous forward of ``n_frames`` frames on ``stream`` (default: torch's current stream)."""

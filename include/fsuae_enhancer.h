@@ -179,6 +179,13 @@ FSUAE_API int64_t fsuae_engine_last_launch_count(const fsuae_engine* e);
 /* Name of the kernel variant the engine selected, e.g. "fp32_fma" / "bf16_tcgen05". */
 FSUAE_API const char* fsuae_engine_variant(const fsuae_engine* e);
 
+/* Optional per-kernel timing (measurement aid for bench.py's roofline line, no reference counterpart): when
+ * enabled, every kernel launch of an enqueue is bracketed by CUDA events on the launching stream.
+ * fsuae_engine_kernel_time returns the device time in ms of launch `index` of the last enqueue (after the caller
+ * synchronised the stream) and copies a short kernel label; returns < 0 past the end. */
+FSUAE_API int fsuae_engine_set_profiling(fsuae_engine* e, int enabled);
+FSUAE_API float fsuae_engine_kernel_time(fsuae_engine* e, int index, char* label, int label_bytes);
+
 /* Text of the last error on this engine (or of the last failed create when e == NULL). */
 FSUAE_API const char* fsuae_last_error(const fsuae_engine* e);
 

@@ -6,7 +6,10 @@ agg = collections.OrderedDict()
 for row in csv.DictReader(lines):
     name = row["Kernel Name"]
     m = re.search(r"conv3x3_tc_kernel<(\d+), (\d+), (\d+), (\d+)", name)
-    key = f"tc<PT={m.group(1)},N={m.group(2)},kind={m.group(4)}>" if m else re.sub(r"\(.*", "", name)[-48:]
+    if "fused_pair" in name:
+        key = "tc_fused_pair<conv3+conv4>"
+    else:
+        key = f"tc<PT={m.group(1)},N={m.group(2)},kind={m.group(4)}>" if m else re.sub(r"\(.*", "", name)[-48:]
     v = float(row["Metric Value"].replace(",", ""))
     unit = row["Metric Unit"]
     v = v / 1000 if unit in ("ns", "nsecond") else v * 1000 if unit in ("ms", "msecond") else v
