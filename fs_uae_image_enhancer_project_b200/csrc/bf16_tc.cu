@@ -59,6 +59,7 @@ struct LayerK {
   const unsigned char* skip;
   unsigned char* dst;
   const unsigned char* wpack;
+  const float* dparams;    // device copy of {bias[MAXC], p0[4][MAXC], p1[4][MAXC]} for the run-time epilogue (dynamic channel index)
   // tail (EPI_TAIL_SHUFFLE)
   const void* frame_in;
   void* frame_out;
@@ -133,6 +134,20 @@ __device__ __forceinline__ float act_rt(int op, float x, float p0, float p1) {
     }
     default: return x;
   }
+}
+
+// run-time op-code applied to the 8 channels of one chunk: ONE (warp-uniform) switch per slot and chunk, the
+// per-element work inside each case stays branch-free
+__device__ __forceinline__ void act_rt8(int op, float (&t)[8], const float (&p0)[8], const float (&p1)[8]) {
+#define FSUAE_CASE(OP) case OP: _Pragma("unroll") for (int i = 0; i < 8; ++i) t[i] = act_rt(OP, t[i], p0[i], p1[i]); break;
+  switch (op) {
+    FSUAE_CASE(FSUAE_ACT_RELU) FSUAE_CASE(FSUAE_ACT_RELU6) FSUAE_CASE(FSUAE_ACT_TANH) FSUAE_CASE(FSUAE_ACT_SIGMOID)
+    FSUAE_CASE(FSUAE_ACT_SILU) FSUAE_CASE(FSUAE_ACT_MISH) FSUAE_CASE(FSUAE_ACT_GELU) FSUAE_CASE(FSUAE_ACT_ELU)
+    FSUAE_CASE(FSUAE_ACT_SOFTPLUS) FSUAE_CASE(FSUAE_ACT_LEAKY_RELU) FSUAE_CASE(FSUAE_ACT_PRELU) FSUAE_CASE(FSUAE_ACT_SCALED_TANH)
+    FSUAE_CASE(FSUAE_ACT_TELU) FSUAE_CASE(FSUAE_ACT_SINLU) FSUAE_CASE(FSUAE_ACT_BIASED_RELU) FSUAE_CASE(FSUAE_ACT_BIASED_PRELU)
+    default: break;   // identity
+  }
+#undef FSUAE_CASE
 }
 
 // OP >= 0: compile-time op (the switch folds away); OP < 0: op-code read from the layer parameters
@@ -488,30 +503,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
           if constexpr (EPI::kSkip) release_rows();
         } else if constexpr (KIND == EPI_STORE) {
           // ---- run-time channel count / op-codes (every other network) ----
+          // Per-channel parameters come from global memory here: indexing the kernel-parameter arrays with a
+          // run-time channel would make the compiler spill the whole 4.7 KB parameter block to local memory.
           unsigned char* dp = P.dst + (size_t)f * P.fs_dst + pix + (size_t)P.dst_plane0 * plane_pitch;
           for (int c = 0; c < P.out_planes; ++c) {
             uint4 skc = make_uint4(0, 0, 0, 0);
             if constexpr (EPI::kSkip) {
               if (valid) skc = *reinterpret_cast<const uint4*>(sp + c * PLANE_ROW);
             }
+            float prm[9][8];     // bias, p0[4], p1[4] of the 8 channels of this chunk (uniform addresses: broadcast loads)
+#pragma unroll
+            for (int a = 0; a < 9; ++a) {
+              const bool used = a == 0 || P.op[(a - 1) & 3] != FSUAE_ACT_IDENTITY;
+              float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+              if (used) {
+                lo = __ldg(reinterpret_cast<const float4*>(P.dparams + a * MAXC + c * 8));
+                hi = __ldg(reinterpret_cast<const float4*>(P.dparams + a * MAXC + c * 8 + 4));
+              }
+              prm[a][0] = lo.x; prm[a][1] = lo.y; prm[a][2] = lo.z; prm[a][3] = lo.w;
+              prm[a][4] = hi.x; prm[a][5] = hi.y; prm[a][6] = hi.z; prm[a][7] = hi.w;
+            }
             uint32_t v[8];
             tmem_ld_x8(taddr + c * 8, v);
             tmem_ld_wait();
             float o[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int ch = c * 8 + i;
-              float t = 0.f;
-              if (ch < P.cout) {
-                t = EPI::pre(P, ch, __uint_as_float(v[i]) + P.bias[ch]);
-                if constexpr (EPI::kSkip) {
-                  const uint32_t w = (&skc.x)[i >> 1];
-                  t += (i & 1) ? bf16_hi(w) : bf16_lo(w);
-                }
-                t = EPI::post(P, ch, t);
+            for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[i]) + prm[0][i];
+            act_rt8(P.op[0], o, prm[1], prm[5]);
+            act_rt8(P.op[1], o, prm[2], prm[6]);
+            if constexpr (EPI::kSkip) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const uint32_t w = (&skc.x)[i >> 1];
+                o[i] += (i & 1) ? bf16_hi(w) : bf16_lo(w);
               }
-              o[i] = t;
             }
+            act_rt8(P.op[2], o, prm[3], prm[7]);
+            act_rt8(P.op[3], o, prm[4], prm[8]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = (c * 8 + i < P.cout) ? o[i] : 0.f;
             if (valid) {
               uint4 pk = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
                                     pack_bf16x2(o[6], o[7]));
@@ -1142,6 +1172,7 @@ const std::vector<Variant>& variants() {
 struct Launch {
   const Variant* var = nullptr;
   unsigned char* d_w = nullptr;
+  float* d_params = nullptr;       // device copy of the per-channel epilogue parameters
   const Variant* var2 = nullptr;   // CTA-pair kernel for the same layer (weights packed per CTA), if instantiated
   unsigned char* d_w2 = nullptr;
   LayerK k{};   // geometry-independent fields prefilled
@@ -1255,6 +1286,16 @@ int bf16_create(fsuae_engine* e) {
           if (a && a->op == FSUAE_ACT_BIASED_PRELU) k.p1[s][c] -= 1.f;   // the kernel evaluates y + (slope - 1) * min(y, 0)
         }
       }
+      {
+        std::vector<float> hp((size_t)9 * MAXC);
+        for (int c = 0; c < MAXC; ++c) {
+          hp[c] = k.bias[c];
+          for (int sl = 0; sl < 4; ++sl) { hp[(1 + sl) * MAXC + c] = k.p0[sl][c]; hp[(5 + sl) * MAXC + c] = k.p1[sl][c]; }
+        }
+        FSUAE_CUDA_CHECK(e, cudaMalloc(&ln.d_params, hp.size() * sizeof(float)));
+        FSUAE_CUDA_CHECK(e, cudaMemcpy(ln.d_params, hp.data(), hp.size() * sizeof(float), cudaMemcpyHostToDevice));
+        k.dparams = ln.d_params;
+      }
       if (var == exact && !getenv("FSUAE_NO_PAIRS")) {
         for (const Variant& v : variants())
           if (v.CTAS == 2 && v.PT == var->PT && v.NPAD == var->NPAD && v.COUT == var->COUT && v.KIND == var->KIND &&
@@ -1323,7 +1364,7 @@ void bf16_destroy(fsuae_engine* e) {
   if (!e->bf16) return;
   for (auto& lp : e->bf16->layers)
     for (auto& ln : lp.launches)
-      { if (ln.d_w) cudaFree(ln.d_w); if (ln.d_w2) cudaFree(ln.d_w2); }
+      { if (ln.d_w) cudaFree(ln.d_w); if (ln.d_w2) cudaFree(ln.d_w2); if (ln.d_params) cudaFree(ln.d_params); }
   for (unsigned char* p : e->bf16->buf)
     if (p) cudaFree(p);
   delete e->bf16;
