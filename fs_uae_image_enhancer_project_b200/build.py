@@ -41,6 +41,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             cmd.insert(1, "-Xptxas=-v")
         if src in FAST_MATH_SOURCES:
             cmd.insert(1, "--use_fast_math")
+        for extra in os.environ.get("FSUAE_EXTRA_NVCC_FLAGS", "").split():   # debugging aids (e.g. -DFSUAE_EPI_TIMING)
+            cmd.insert(1, extra)
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:

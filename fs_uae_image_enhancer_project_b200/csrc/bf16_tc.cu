@@ -49,6 +49,16 @@ constexpr int NTHREADS = 64 + 128 * EPI_WG;
 
 enum { EPI_STORE = 0, EPI_TAIL_SHUFFLE = 1, EPI_TAIL_PLAIN = 2 };
 
+#ifdef FSUAE_EPI_TIMING
+__device__ unsigned long long g_epi_timing[8];
+__device__ __forceinline__ long long clk() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory"); return t; }
+#define EPI_T(var) const long long var = clk()
+#define EPI_ACC(i, v) do { if (blockIdx.x == 0 && warp == 2 && lane == 0) g_epi_timing[i] += (unsigned long long)(v); } while (0)
+#else
+#define EPI_T(var)
+#define EPI_ACC(i, v)
+#endif
+
 struct LayerK {
   int Hw, Ww, PW, S, n_frames, n_blocks;   // n_blocks = n_frames * S * Hw strip rows, ordered (frame, strip, row)
   int P0, P1, cout;        // cout: channels this launch produces (a wide layer may be split over launches)
@@ -163,6 +173,8 @@ __device__ __forceinline__ float act_slot(const LayerK& P, int slot, int ch, flo
 template <int PRE0, int PRE1, int POST0, int POST1, bool SKIP>
 struct Epi {
   static constexpr bool kSkip = SKIP;
+  static constexpr bool kRuntime = PRE0 < 0;      // op-codes come from the layer parameters
+  static constexpr int kOp0 = PRE0, kOp1 = PRE1, kOp2 = POST0, kOp3 = POST1;
   __device__ static __forceinline__ float pre(const LayerK& P, int ch, float v) {
     v = act_slot<PRE0>(P, 0, ch, v);
     return act_slot<PRE1>(P, 1, ch, v);
@@ -184,6 +196,84 @@ __device__ __forceinline__ uint8_t to_u8_fast(float v, int gamma_out) {
   if (gamma_out) v = __powf(fmaxf(v, 0.f), 1.0f / 2.2f);
   v = fminf(fmaxf(v, 0.f), 1.f) * 255.0f;
   return (uint8_t)v;
+}
+
+// Run-time activation chain of one 8-channel chunk: o[] holds accumulator + bias on entry.  The four slots are walked
+// by a ROLLED loop around one switch: unrolled, the compiler duplicates the 16-way switch along every path (a 49 KB
+// loop body whose indirect branches miss the instruction cache: 1400 cycles per chunk measured); rolled it is 2 KB.
+// Each slot fetches only the parameters its op-code needs (uniform addresses: broadcast loads).
+//   ops = op0 | op1 << 8 | op2 << 16 | op3 << 24;  prm = dparams + first channel of the chunk;  stride = floats per row
+constexpr uint32_t ACT_PARAM_MASK = (1u << FSUAE_ACT_ELU) | (1u << FSUAE_ACT_SOFTPLUS) | (1u << FSUAE_ACT_LEAKY_RELU) |
+                                    (1u << FSUAE_ACT_PRELU) | (1u << FSUAE_ACT_SINLU) | (1u << FSUAE_ACT_BIASED_RELU) |
+                                    (1u << FSUAE_ACT_BIASED_PRELU);
+__device__ __forceinline__ void act_chain_rt(uint32_t ops, const float* __restrict__ prm, int stride, bool has_skip,
+                                             const uint4& skc, float (&o)[8]) {
+#pragma unroll 1
+  for (int s = 0; s < 4; ++s) {
+    if (s == 2 && has_skip) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t w = (&skc.x)[i >> 1];
+        o[i] += (i & 1) ? bf16_hi(w) : bf16_lo(w);
+      }
+    }
+    const int op = (int)((ops >> (8 * s)) & 0xFFu);
+    if (op == FSUAE_ACT_IDENTITY) continue;
+    float p0[8], p1[8];
+    if ((ACT_PARAM_MASK >> op) & 1u) {
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(prm + (size_t)(1 + s) * stride));
+      const float4 a1 = __ldg(reinterpret_cast<const float4*>(prm + (size_t)(1 + s) * stride + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(prm + (size_t)(5 + s) * stride));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(prm + (size_t)(5 + s) * stride + 4));
+      p0[0] = a0.x; p0[1] = a0.y; p0[2] = a0.z; p0[3] = a0.w; p0[4] = a1.x; p0[5] = a1.y; p0[6] = a1.z; p0[7] = a1.w;
+      p1[0] = b0.x; p1[1] = b0.y; p1[2] = b0.z; p1[3] = b0.w; p1[4] = b1.x; p1[5] = b1.y; p1[6] = b1.z; p1[7] = b1.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { p0[i] = 0.f; p1[i] = 0.f; }
+    }
+    act_rt8(op, o, p0, p1);
+  }
+}
+
+// compile-time op-code of one slot (run-time channel count): parameters are fetched only if the op has any
+template <int OP>
+__device__ __forceinline__ void act_slot8(int s, const float* __restrict__ prm, int stride, float (&o)[8]) {
+  if constexpr (OP != FSUAE_ACT_IDENTITY) {
+    float p0[8], p1[8];
+    if constexpr (((ACT_PARAM_MASK >> OP) & 1u) != 0) {
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(prm + (size_t)(1 + s) * stride));
+      const float4 a1 = __ldg(reinterpret_cast<const float4*>(prm + (size_t)(1 + s) * stride + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(prm + (size_t)(5 + s) * stride));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(prm + (size_t)(5 + s) * stride + 4));
+      p0[0] = a0.x; p0[1] = a0.y; p0[2] = a0.z; p0[3] = a0.w; p0[4] = a1.x; p0[5] = a1.y; p0[6] = a1.z; p0[7] = a1.w;
+      p1[0] = b0.x; p1[1] = b0.y; p1[2] = b0.z; p1[3] = b0.w; p1[4] = b1.x; p1[5] = b1.y; p1[6] = b1.z; p1[7] = b1.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { p0[i] = 0.f; p1[i] = 0.f; }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = act_rt(OP, o[i], p0[i], p1[i]);
+  }
+}
+// activation chain + residual of one chunk for a run-time channel count: compile-time ops when the variant has them
+template <class EPI>
+__device__ __forceinline__ void epi_chain8(uint32_t ops, const float* __restrict__ prm, int stride, bool has_skip, const uint4& skc,
+                                           float (&o)[8]) {
+  if constexpr (EPI::kRuntime) {
+    act_chain_rt(ops, prm, stride, has_skip, skc, o);
+  } else {
+    act_slot8<EPI::kOp0>(0, prm, stride, o);
+    act_slot8<EPI::kOp1>(1, prm, stride, o);
+    if (has_skip) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t w = (&skc.x)[i >> 1];
+        o[i] += (i & 1) ? bf16_hi(w) : bf16_lo(w);
+      }
+    }
+    act_slot8<EPI::kOp2>(2, prm, stride, o);
+    act_slot8<EPI::kOp3>(3, prm, stride, o);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -444,8 +534,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
             }
           }
         }
+        EPI_T(t_a);
         mbar_wait(&tfull[stage], spar);
         tc_fence_after();
+        EPI_T(t_b);
+        EPI_ACC(0, t_b - t_a); EPI_ACC(1, 1);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + stage * NPAD;
         // residual = this layer's input at the same pixel = centre row of the block, still in the ring.
         // Only touch the ring barriers AFTER tfull: the block's MMAs have consumed rows kc-1..kc+1, so their
@@ -506,49 +599,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
           // Per-channel parameters come from global memory here: indexing the kernel-parameter arrays with a
           // run-time channel would make the compiler spill the whole 4.7 KB parameter block to local memory.
           unsigned char* dp = P.dst + (size_t)f * P.fs_dst + pix + (size_t)P.dst_plane0 * plane_pitch;
+          const uint32_t ops_packed = (uint32_t)P.op[0] | ((uint32_t)P.op[1] << 8) | ((uint32_t)P.op[2] << 16) | ((uint32_t)P.op[3] << 24);
           for (int c = 0; c < P.out_planes; ++c) {
             uint4 skc = make_uint4(0, 0, 0, 0);
             if constexpr (EPI::kSkip) {
               if (valid) skc = *reinterpret_cast<const uint4*>(sp + c * PLANE_ROW);
             }
-            float prm[9][8];     // bias, p0[4], p1[4] of the 8 channels of this chunk (uniform addresses: broadcast loads)
-#pragma unroll
-            for (int a = 0; a < 9; ++a) {
-              const bool used = a == 0 || P.op[(a - 1) & 3] != FSUAE_ACT_IDENTITY;
-              float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
-              if (used) {
-                lo = __ldg(reinterpret_cast<const float4*>(P.dparams + a * MAXC + c * 8));
-                hi = __ldg(reinterpret_cast<const float4*>(P.dparams + a * MAXC + c * 8 + 4));
-              }
-              prm[a][0] = lo.x; prm[a][1] = lo.y; prm[a][2] = lo.z; prm[a][3] = lo.w;
-              prm[a][4] = hi.x; prm[a][5] = hi.y; prm[a][6] = hi.z; prm[a][7] = hi.w;
-            }
+            EPI_T(t_c);
+            const float* prm = P.dparams + c * 8;
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(prm)), b1 = __ldg(reinterpret_cast<const float4*>(prm + 4));
             uint32_t v[8];
+            EPI_T(t_d);
             tmem_ld_x8(taddr + c * 8, v);
             tmem_ld_wait();
+            EPI_T(t_e);
             float o[8];
+            o[0] = __uint_as_float(v[0]) + b0.x; o[1] = __uint_as_float(v[1]) + b0.y; o[2] = __uint_as_float(v[2]) + b0.z;
+            o[3] = __uint_as_float(v[3]) + b0.w; o[4] = __uint_as_float(v[4]) + b1.x; o[5] = __uint_as_float(v[5]) + b1.y;
+            o[6] = __uint_as_float(v[6]) + b1.z; o[7] = __uint_as_float(v[7]) + b1.w;
+            EPI_T(t_f);
+            EPI_ACC(2, t_d - t_c); EPI_ACC(3, t_e - t_d); EPI_ACC(4, t_f - t_e); EPI_ACC(7, 1);
+            epi_chain8<EPI>(ops_packed, prm, MAXC, EPI::kSkip, skc, o);
+            if (c * 8 + 8 > P.cout) {      // padding channels of the last plane stay exactly zero (uniform branch)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[i]) + prm[0][i];
-            act_rt8(P.op[0], o, prm[1], prm[5]);
-            act_rt8(P.op[1], o, prm[2], prm[6]);
-            if constexpr (EPI::kSkip) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const uint32_t w = (&skc.x)[i >> 1];
-                o[i] += (i & 1) ? bf16_hi(w) : bf16_lo(w);
-              }
+              for (int i = 0; i < 8; ++i) o[i] = (c * 8 + i < P.cout) ? o[i] : 0.f;
             }
-            act_rt8(P.op[2], o, prm[3], prm[7]);
-            act_rt8(P.op[3], o, prm[4], prm[8]);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = (c * 8 + i < P.cout) ? o[i] : 0.f;
             if (valid) {
               uint4 pk = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
                                     pack_bf16x2(o[6], o[7]));
               *reinterpret_cast<uint4*>(dp + (size_t)c * plane_pitch) = pk;
             }
+            EPI_T(t_g);
+            EPI_ACC(5, t_g - t_f);
           }
           if constexpr (EPI::kSkip) release_rows();
+          EPI_T(t_h);
+          EPI_ACC(6, t_h - t_a);
         } else if constexpr (KIND == EPI_TAIL_PLAIN) {
           // ---- 3-channel full-resolution tail (conv5: as is; conv3: x255 + alpha) straight to the frame ----
           uint32_t v[8];
@@ -1113,6 +1199,8 @@ std::vector<uint16_t> pack_weights(const float* w, int cout, int cin0, int cin1,
   return out;
 }
 
+#include "bf16_wide.cuh"
+
 typedef void (*KernelFn)(const LayerK);
 
 struct Variant {
@@ -1164,6 +1252,17 @@ const std::vector<Variant>& variants() {
       generic_variant<8, 64, EPI_STORE, true>(), generic_variant<1, 64, EPI_STORE, false>(), generic_variant<8, 128, EPI_STORE, false>(),
       generic_variant<16, 32, EPI_STORE, true>(),
       generic_variant<8, 16, EPI_TAIL_PLAIN, false>(), generic_variant<16, 16, EPI_TAIL_PLAIN, false>(),
+      // the same BatchNorm-folded families with compile-time op-codes (ReLU; residual + ReLU; identity / sigmoid tails):
+      // the run-time chain costs ~4x the instructions per chunk and these layers are issue-bound at full resolution
+      make_variant<1, 32, -1, EPI_STORE, Epi<A(RELU), 0, 0, 0, false>>(A(RELU), 0, 0, 0, 0),
+      make_variant<1, 64, -1, EPI_STORE, Epi<A(RELU), 0, 0, 0, false>>(A(RELU), 0, 0, 0, 0),
+      make_variant<4, 64, -1, EPI_STORE, Epi<A(RELU), 0, 0, 0, false>>(A(RELU), 0, 0, 0, 0),
+      make_variant<8, 128, -1, EPI_STORE, Epi<A(RELU), 0, 0, 0, false>>(A(RELU), 0, 0, 0, 0),
+      make_variant<4, 32, -1, EPI_STORE, Epi<0, 0, A(RELU), 0, true>>(0, 0, A(RELU), 0, 1),
+      make_variant<8, 64, -1, EPI_STORE, Epi<0, 0, A(RELU), 0, true>>(0, 0, A(RELU), 0, 1),
+      make_variant<8, 16, -1, EPI_TAIL_PLAIN, Epi<0, 0, 0, 0, false>>(0, 0, 0, 0, 0),
+      make_variant<8, 16, -1, EPI_TAIL_PLAIN, Epi<A(SIGMOID), 0, 0, 0, false>>(A(SIGMOID), 0, 0, 0, 0),
+      make_variant<16, 16, -1, EPI_TAIL_PLAIN, Epi<A(SIGMOID), 0, 0, 0, false>>(A(SIGMOID), 0, 0, 0, 0),
   };
   return v;
 }
@@ -1176,6 +1275,8 @@ struct Launch {
   const Variant* var2 = nullptr;   // CTA-pair kernel for the same layer (weights packed per CTA), if instantiated
   unsigned char* d_w2 = nullptr;
   LayerK k{};   // geometry-independent fields prefilled
+  const WideVariant* wide = nullptr;   // K-streamed tile kernel instead (layers too wide for resident weights / full-depth rows)
+  WideK wk{};
 };
 
 struct LayerPlan {
@@ -1207,6 +1308,15 @@ extern "C" __attribute__((visibility("default"))) long long fsuae_debug_read_bf1
   if (cudaMemcpy(dst, e->bf16->buf[id], n, cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
   return n;
 }
+
+#ifdef FSUAE_EPI_TIMING
+extern "C" __attribute__((visibility("default"))) int fsuae_debug_epi_timing(unsigned long long* out8, int reset) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out8, g_epi_timing, sizeof(g_epi_timing)) != cudaSuccess) return -1;
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_epi_timing, z, sizeof(z)); }
+  return 0;
+}
+#endif
 
 int bf16_create(fsuae_engine* e) {
   const fsuae_net_desc& d = e->desc;
@@ -1241,16 +1351,75 @@ int bf16_create(fsuae_engine* e) {
     // widest instantiated N for its input plane count is split into output-channel groups
     const int need = (L.cout + 15) / 16 * 16;
     const Variant* exact = nullptr;
-    const Variant* fit = nullptr;    // smallest generic NPAD >= need
-    const Variant* widest = nullptr; // widest generic NPAD
+    const Variant* fit = nullptr;        // smallest run-time-op NPAD >= need
+    const Variant* widest = nullptr;     // widest run-time-op NPAD
+    const Variant* fit_ops = nullptr;    // the same with this layer's op-codes compiled in (run-time channel count)
+    const Variant* widest_ops = nullptr;
     for (const Variant& v : variants()) {
       if (v.CTAS != 1 || v.PT != PT || v.KIND != kind || v.skip != skip) continue;
-      if (v.COUT == L.cout && v.pre0 == ops[0] && v.pre1 == ops[1] && v.post0 == ops[2] && v.post1 == ops[3]) exact = &v;
-      if (v.pre0 != -1) continue;
-      if (v.NPAD >= need && (!fit || v.NPAD < fit->NPAD)) fit = &v;
-      if (!widest || v.NPAD > widest->NPAD) widest = &v;
+      const bool ops_eq = v.pre0 == ops[0] && v.pre1 == ops[1] && v.post0 == ops[2] && v.post1 == ops[3];
+      if (v.COUT == L.cout && ops_eq) exact = &v;
+      if (v.COUT > 0) continue;
+      if (ops_eq) {
+        if (v.NPAD >= need && (!fit_ops || v.NPAD < fit_ops->NPAD)) fit_ops = &v;
+        if (!widest_ops || v.NPAD > widest_ops->NPAD) widest_ops = &v;
+      } else if (v.pre0 == -1) {
+        if (v.NPAD >= need && (!fit || v.NPAD < fit->NPAD)) fit = &v;
+        if (!widest || v.NPAD > widest->NPAD) widest = &v;
+      }
     }
-    const Variant* var = exact ? exact : (fit ? fit : widest);
+    const Variant* var = exact ? exact : fit_ops ? fit_ops : fit ? fit : widest_ops ? widest_ops : widest;
+    // Layers whose weights / full-depth input rows do not fit beside each other in shared memory stream K through the
+    // wide tile kernel (thin-input layers are cheap to split over output-channel groups instead).
+    const bool too_wide = !var || var->NPAD < need;
+    const bool use_wide = !exact && kind != EPI_TAIL_SHUFFLE && !getenv("FSUAE_NO_WIDE") &&
+                          ((too_wide && (PT >= 4 || !var)) || (getenv("FSUAE_FORCE_WIDE") != nullptr));
+    if (use_wide) {
+      const int ngroups = kind == EPI_STORE ? (need + 127) / 128 : 1;
+      const int per = ((need + ngroups - 1) / ngroups + 15) / 16 * 16;
+      const WideVariant* wv = nullptr;
+      for (int pass = 0; pass < 2 && !wv; ++pass)      // first a variant with this layer's op-codes compiled in, then the run-time one
+        for (const WideVariant& v : wide_variants()) {
+          const bool ops_eq = v.pre0 == ops[0] && v.pre1 == ops[1] && v.post0 == ops[2] && v.post1 == ops[3] && v.skip == skip;
+          if (v.KIND != kind || v.NT < per || (pass == 0 ? !ops_eq : v.pre0 != -1)) continue;
+          if (!wv || v.NT < wv->NT) wv = &v;
+        }
+      if (!wv) return set_error(e, FSUAE_ERR_UNSUPPORTED, tag + "no wide tensor-core kernel for " + std::to_string(L.cout) + " output channels");
+      Launch ln;
+      ln.wide = wv;
+      std::vector<uint16_t> wp = pack_weights_wide(e->h_blob.data() + L.w_off, L.cout, L.cin0, L.cin1, P0, P1, wv->NT, ngroups);
+      FSUAE_CUDA_CHECK(e, cudaMalloc(&ln.d_w, wp.size() * 2));
+      FSUAE_CUDA_CHECK(e, cudaMemcpy(ln.d_w, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
+      e->device_bytes += wp.size() * 2;
+      WideK& k = ln.wk;
+      std::memset(&k, 0, sizeof(k));
+      k.P0 = P0; k.pin = PT; k.kchunks = (PT + 1) / 2;
+      k.ngroups = ngroups; k.cout = L.cout; k.cpad = ngroups * wv->NT;
+      k.has_skip = skip;
+      k.wpack = ln.d_w;
+      std::vector<float> hp((size_t)9 * k.cpad, 0.f);
+      for (int c = 0; c < k.cpad; ++c) {
+        const int cc = std::min(c, L.cout - 1);
+        hp[c] = (c < L.cout && L.b_off >= 0) ? e->h_blob[L.b_off + c] : 0.f;
+        for (int s = 0; s < 4; ++s) {
+          const fsuae_act_desc* a = nullptr;
+          if (s < 2 && s < L.n_pre) a = &L.pre[s];
+          if (s >= 2 && s - 2 < L.n_post) a = &L.post[s - 2];
+          float v0 = (a && a->n0 > 0) ? e->h_blob[a->p0_off + (a->n0 == 1 ? 0 : cc)] : 0.f;
+          float v1 = (a && a->n1 > 0) ? e->h_blob[a->p1_off + (a->n1 == 1 ? 0 : cc)] : 0.f;
+          if (a && a->op == FSUAE_ACT_BIASED_PRELU) v1 -= 1.f;
+          hp[(size_t)(1 + s) * k.cpad + c] = v0;
+          hp[(size_t)(5 + s) * k.cpad + c] = v1;
+        }
+      }
+      for (int s = 0; s < 4; ++s) k.op[s] = ops[s];
+      FSUAE_CUDA_CHECK(e, cudaMalloc(&ln.d_params, hp.size() * sizeof(float)));
+      FSUAE_CUDA_CHECK(e, cudaMemcpy(ln.d_params, hp.data(), hp.size() * sizeof(float), cudaMemcpyHostToDevice));
+      k.dparams = ln.d_params;
+      FSUAE_CUDA_CHECK(e, cudaFuncSetAttribute((const void*)wv->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, wv->smem));
+      lp.launches.push_back(ln);
+      continue;
+    }
     if (!var || (kind != EPI_STORE && var->NPAD < need))
       return set_error(e, FSUAE_ERR_UNSUPPORTED,
                        tag + "no tensor-core kernel instantiated for " + std::to_string(PT) + " input planes / " +
@@ -1443,6 +1612,24 @@ int bf16_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in
       continue;
     }
     for (Launch& ln : plan->layers[i].launches) {
+      if (ln.wide) {
+        const fsuae_layer_desc& L = d.layers[i];
+        WideK k = ln.wk;
+        k.Hw = g.Hw; k.Ww = g.Ww; k.PW = PW; k.S = S; k.n_frames = n;
+        k.rowblocks = (g.Hw + 7) / 8;
+        k.n_units = n * S * k.rowblocks * k.ngroups;
+        k.src0 = plan->buf[L.src0]; k.fs0 = fstride(L.src0);
+        if (L.cin1 > 0) { k.src1 = plan->buf[L.src1]; k.fs1 = fstride(L.src1); }
+        if (L.skip_src >= 0) { k.skip = plan->buf[L.skip_src]; k.fs_skip = fstride(L.skip_src); }
+        if (i < d.n_layers - 1) { k.dst = plan->buf[i + 1]; k.fs_dst = fstride(i + 1); }
+        k.frame_out = out; k.out_fmt = out_fmt; k.H = g.H; k.W = g.W; k.xoff = g.xoff;
+        k.gamma_out = (flags & FSUAE_FLAG_GAMMA_OUT) ? 1 : 0;
+        launch_cfg(cfg, attr, k.n_units, 2, ln.wide->smem);
+        { ProfScope ps(e, st, ("conv" + std::to_string(i + 1) + "_wide").c_str());
+          FSUAE_CUDA_CHECK(e, cudaLaunchKernelEx(&cfg, ln.wide->fn, k)); }
+        e->launches++;
+        continue;
+      }
       const bool pair = ln.var2 != nullptr && n >= 2;      // CTA pairs process two frames in lockstep
       const Variant* var = pair ? ln.var2 : ln.var;
       const LayerK k = fill(i, ln, pair);

@@ -254,20 +254,38 @@ def test_bf16_full_size_float_and_batch_properties():
 
 
 def test_bf16_unsupported_network_fails_loudly():
-    """conv3 heavyweight (192/256 channels: 48 KB ring rows) has no tensor-core kernel yet: explicit error, no fallback."""
-    from fs_uae_image_enhancer_project_b200 import _lib, model_conv3
-    m = model_conv3.get_model("heavyweight").to(dev()).set_precision("bf16")
-    with pytest.raises(_lib.EngineError) as ei:
-        m(torch.zeros(1, 4, 16, 16, dtype=torch.uint8, device=dev()))
-    assert ei.value.code == _lib.ERR_UNSUPPORTED
+    """A channel-softmax slot has no tensor-core epilogue: explicit error, no fallback."""
+    from fs_uae_image_enhancer_project_b200 import _lib
     spec = gold_spec("vocab_b")                                   # channel softmax slot
     mb = _bf16_model(spec, O.make_pix_shuffle_state_dict(spec, 1))
-    with pytest.raises(_lib.EngineError):
+    with pytest.raises(_lib.EngineError) as ei:
         mb(torch.rand(1, 3, 16, 16, device=dev()))
+    assert ei.value.code == _lib.ERR_UNSUPPORTED
+
+
+def test_bf16_conv3_heavyweight_wide_kernel():
+    """192 -> 256 -> 3 channels: neither the weights (884 KB) nor full-depth input rows fit in shared memory; the
+    K-streamed tile kernel (CTA pairs, 8-row tiles, 2 output-channel groups) runs conv2 and conv3."""
+    from fs_uae_image_enhancer_project_b200 import model_conv3
+    g = load_gold("conv3_heavyweight")
+    sd = O.make_bn_state_dict(O.conv3_channels("heavyweight"), int(g["seed"]))
+    m = model_conv3.get_model("heavyweight")
+    m.load_state_dict(sd)
+    m = m.to(dev()).set_precision("bf16")
+    y = m(torch.from_numpy(g["x"]).to(dev())).float().cpu()
+    want = torch.from_numpy(g["y"])
+    assert y.shape == want.shape and (y[:, 3] == 255.0).all()
+    assert (y - want).abs().max().item() <= 255 * BF16_TOL and O.psnr(y, want, 255.0) >= 50.0
+    # ragged geometry: 3 frames, 21 rows (tiles hang over the bottom edge), 300 columns (3 strips, last one partial)
+    x = torch.randint(0, 256, (3, 4, 21, 300), dtype=torch.uint8, generator=torch.Generator().manual_seed(9))
+    want = O.conv3_forward(sd, x)
+    got = m(x.to(dev())).float().cpu()
+    assert (got - want).abs().max().item() <= 255 * BF16_TOL and O.psnr(got, want, 255.0) >= 50.0
+    assert torch.equal(got[1:2], m(x[1:2].contiguous().to(dev())).float().cpu())     # tiling is invisible
 
 
 def test_bf16_pix_shuffle_heavyweight_matches_reference_vectors():
-    """108-channel conv4 is split over three output-channel groups (packed weights would not fit otherwise)."""
+    """108-channel conv4/conv5 stream K through the wide tile kernel (packed weights would not fit otherwise)."""
     g = load_gold("pix_shuffle_heavyweight")
     spec = gold_spec("heavyweight")
     sd = O.make_pix_shuffle_state_dict(spec, int(g["seed"]))
@@ -302,7 +320,7 @@ def test_bf16_conv3_lightweight_matches_reference_vectors_and_screenshot():
 
 @pytest.mark.parametrize("preset", ["lightweight", "heavyweight"])
 def test_bf16_conv5_matches_reference_vectors(preset):
-    """conv5 heavyweight's 128->128 layer runs as four 32-channel groups."""
+    """conv5 heavyweight's 128->128 layers (residual add read from global memory) run on the wide tile kernel."""
     from fs_uae_image_enhancer_project_b200 import model_conv5
     g = load_gold(f"conv5_{preset}")
     m = model_conv5.get_model(preset)

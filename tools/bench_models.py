@@ -33,7 +33,7 @@ for fam, mod, batch in (("pix_shuffle", model_pix_shuffle, 32), ("conv3", model_
                 m(xs[i & 1])
             e1.record(); torch.cuda.synchronize()
             us = 1e3 * e0.elapsed_time(e1) / (steps * b)
-            rows.append((fam, preset, prec, us, f"{1e6 / us:9.0f} fps  {GF[(fam, preset)] / us * 1e-3 * 1e3:7.1f} TFLOP/s"))
+            rows.append((fam, preset, prec, us, f"{1e6 / us:9.0f} fps  {GF[(fam, preset)] / us * 1e3:7.0f} TFLOP/s"))
             m.close()
 for r in rows:
     print(f"{r[0]:12s} {r[1]:12s} {r[2]:5s} " + (f"{r[3]:9.1f} us/frame  {r[4]}" if r[3] else f"unsupported: {r[4]}"))
