@@ -60,6 +60,9 @@ EXPORTS = {
                                        C.c_uint32, C.c_void_p]),
     "fsuae_engine_run_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                         C.c_uint32]),
+    "fsuae_engine_submit_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                           C.c_uint32]),
+    "fsuae_engine_wait_host": (C.c_int, [C.c_void_p]),
     "fsuae_engine_device_bytes": (C.c_size_t, [C.c_void_p]),
     "fsuae_engine_last_launch_count": (C.c_int64, [C.c_void_p]),
     "fsuae_engine_variant": (C.c_char_p, [C.c_void_p]),

@@ -171,7 +171,7 @@ int fsuae_engine_create(const fsuae_net_desc* desc, const float* blob, size_t bl
   // host-pipeline staging: sized for the widest formats
   e->host_chunk = std::min(e->chunk, 16);  // largest stage of the host-buffer pipeline (H2D / compute / D2H overlap)
   size_t in_b = (size_t)e->host_chunk * 12 * height * width, out_b = (size_t)e->host_chunk * 16 * height * width;
-  for (int i = 0; i < 2 && ce == cudaSuccess; ++i) {
+  for (int i = 0; i < FSUAE_STAGE_BUFS && ce == cudaSuccess; ++i) {
     ce = cudaMalloc(&e->d_stage_in[i], in_b);
     if (ce == cudaSuccess) ce = cudaMalloc(&e->d_stage_out[i], out_b);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming);
@@ -221,7 +221,7 @@ int fsuae_engine_destroy(fsuae_engine* e) {
   fp32_destroy(e);
   bf16_destroy(e);
   for (cudaEvent_t ev : e->prof_ev) cudaEventDestroy(ev);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < FSUAE_STAGE_BUFS; ++i) {
     if (e->d_stage_in[i]) cudaFree(e->d_stage_in[i]);
     if (e->d_stage_out[i]) cudaFree(e->d_stage_out[i]);
     if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
@@ -269,8 +269,8 @@ int fsuae_engine_enqueue(fsuae_engine* e, const void* in_dev, void* out_dev, int
   return rc;
 }
 
-int fsuae_engine_run_host(fsuae_engine* e, const void* in_host, void* out_host, int n_frames, int in_fmt,
-                          int out_fmt, uint32_t flags) {
+int fsuae_engine_submit_host(fsuae_engine* e, const void* in_host, void* out_host, int n_frames, int in_fmt,
+                             int out_fmt, uint32_t flags) {
   if (!e) return FSUAE_ERR_INVALID;
   if (!in_host || !out_host || n_frames < 0) return set_error(e, FSUAE_ERR_INVALID, "null buffer or negative frame count");
   int rc = check_formats(e, in_fmt, out_fmt, flags);
@@ -281,37 +281,54 @@ int fsuae_engine_run_host(fsuae_engine* e, const void* in_host, void* out_host, 
   cudaGetDevice(&prev);
   if (prev != e->device) cudaSetDevice(e->device);
   size_t in_fb = fmt_frame_bytes(in_fmt, e->H, e->W), out_fb = fmt_frame_bytes(out_fmt, e->H, e->W);
-  int it = 0;
   rc = FSUAE_OK;
-  // Stage sizes ramp up (4, 8, 16, 16, ... 4): compute starts after a short first upload and the last download is
-  // short -- the call is synchronous, so pipeline fill and drain are paid on every call.
+  // Stage sizes (measured on a B200 / PCIe 5 x16 box, 64-frame calls, tools/e2e_stage_sweep.sh): when earlier
+  // submissions are still in flight the stream is full and uniform large stages are best (22.8 k frames/s); when the
+  // pipeline is idle the call is most likely a blocking one that pays fill (first upload) and drain (last download),
+  // so stages ramp up 4, 6, 8, 10, 12 ... and back down ... 10, 8, 6 (19.5 k frames/s against 16.9 k for uniform 16).
   std::vector<int> stages;
-  {
-    int rem = n_frames, step = std::min(4, e->host_chunk);
-    const int tail = n_frames >= 24 ? 4 : 0;
-    rem -= tail;
-    while (rem > 0) {
-      const int take = std::min(step, rem);
-      stages.push_back(take);
-      rem -= take;
-      step = std::min(step * 2, e->host_chunk);
+  if (const char* env = getenv("FSUAE_HOST_STAGES"); env && *env) {      // debugging aid: explicit schedule "2,4,8,..." (repeated to cover n_frames)
+    std::vector<int> pat;
+    for (const char* c = env; *c;) { pat.push_back(std::max(1, std::min(e->host_chunk, atoi(c)))); while (*c && *c != ',') ++c; if (*c) ++c; }
+    for (int rem = n_frames, i = 0; rem > 0 && !pat.empty(); ++i) { int t = std::min(pat[i % pat.size()], rem); stages.push_back(t); rem -= t; }
+  } else if (e->stage_seq > 0 && cudaStreamQuery(e->s_out) == cudaErrorNotReady) {
+    for (int rem = n_frames; rem > 0; rem -= stages.back()) stages.push_back(std::min(e->host_chunk, rem));
+  } else {
+    const int up[4] = {4, 6, 8, 10}, down[3] = {10, 8, 6};
+    std::vector<int> tail;
+    int rem = n_frames;
+    if (n_frames >= 40)
+      for (int d : down) { tail.push_back(std::min(d, e->host_chunk)); rem -= tail.back(); }
+    for (int u : up) {
+      if (rem <= 0) break;
+      stages.push_back(std::min(std::min(u, e->host_chunk), rem));
+      rem -= stages.back();
     }
-    if (tail) stages.push_back(tail);
+    while (rem > 0) { stages.push_back(std::min(std::min(12, e->host_chunk), rem)); rem -= stages.back(); }
+    stages.insert(stages.end(), tail.begin(), tail.end());
   }
-  for (int f0 = 0, n = 0; it < (int)stages.size() && rc == FSUAE_OK; f0 += n, ++it) {
-    n = stages[it];
-    int b = it & 1;
+  int f0 = 0;
+  for (size_t it = 0; it < stages.size() && rc == FSUAE_OK; ++it) {
+    const int n = stages[it];
+    const int b = (int)(e->stage_seq % FSUAE_STAGE_BUFS);
+    const bool reused = e->stage_seq >= FSUAE_STAGE_BUFS;     // staging pair b has been used before (possibly by an earlier submission)
     cudaError_t ce = cudaSuccess;
-    if (it >= 2) ce = cudaStreamWaitEvent(e->s_in, e->ev_out[b], 0);  // staging pair b is free again
+    // Input staging b is free once the pass that read it (two stages ago) has finished; output staging b once its
+    // download has.  Keeping the two dependencies apart lets upload(i), compute(i-1) and download(i-2) overlap with
+    // two buffers each (tied together, the period was upload + download instead of max(upload, compute, download)).
+    if (reused) ce = cudaStreamWaitEvent(e->s_in, e->ev_comp[b], 0);
     if (ce == cudaSuccess)
       ce = cudaMemcpyAsync(e->d_stage_in[b], (const char*)in_host + (size_t)f0 * in_fb, (size_t)n * in_fb,
                            cudaMemcpyHostToDevice, e->s_in);
     if (ce == cudaSuccess) ce = cudaEventRecord(e->ev_in[b], e->s_in);
     if (ce == cudaSuccess) ce = cudaStreamWaitEvent(e->s_comp, e->ev_in[b], 0);
+    if (ce == cudaSuccess && reused) ce = cudaStreamWaitEvent(e->s_comp, e->ev_out[b], 0);
     if (ce != cudaSuccess) { rc = set_error(e, FSUAE_ERR_CUDA, cudaGetErrorString(ce)); break; }
+    const int64_t launches = e->launches;
     rc = e->precision == FSUAE_PREC_FP32
              ? fp32_enqueue_chunk(e, e->d_stage_in[b], e->d_stage_out[b], n, in_fmt, out_fmt, flags, e->s_comp)
              : bf16_enqueue_chunk(e, e->d_stage_in[b], e->d_stage_out[b], n, in_fmt, out_fmt, flags, e->s_comp);
+    (void)launches;
     if (rc != FSUAE_OK) break;
     ce = cudaEventRecord(e->ev_comp[b], e->s_comp);
     if (ce == cudaSuccess) ce = cudaStreamWaitEvent(e->s_out, e->ev_comp[b], 0);
@@ -320,14 +337,33 @@ int fsuae_engine_run_host(fsuae_engine* e, const void* in_host, void* out_host, 
                            cudaMemcpyDeviceToHost, e->s_out);
     if (ce == cudaSuccess) ce = cudaEventRecord(e->ev_out[b], e->s_out);
     if (ce != cudaSuccess) rc = set_error(e, FSUAE_ERR_CUDA, cudaGetErrorString(ce));
+    e->stage_seq++;
+    f0 += n;
   }
+  if (prev != e->device) cudaSetDevice(prev);
+  return rc;
+}
+
+int fsuae_engine_wait_host(fsuae_engine* e) {
+  if (!e) return FSUAE_ERR_INVALID;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  if (prev != e->device) cudaSetDevice(e->device);
   cudaError_t ce = cudaStreamSynchronize(e->s_out);
   cudaError_t ce2 = cudaStreamSynchronize(e->s_comp);
   cudaError_t ce3 = cudaStreamSynchronize(e->s_in);
-  if (rc == FSUAE_OK && (ce != cudaSuccess || ce2 != cudaSuccess || ce3 != cudaSuccess))
-    rc = set_error(e, FSUAE_ERR_CUDA, cudaGetErrorString(ce != cudaSuccess ? ce : (ce2 != cudaSuccess ? ce2 : ce3)));
   if (prev != e->device) cudaSetDevice(prev);
-  return rc;
+  if (ce != cudaSuccess || ce2 != cudaSuccess || ce3 != cudaSuccess)
+    return set_error(e, FSUAE_ERR_CUDA, cudaGetErrorString(ce != cudaSuccess ? ce : (ce2 != cudaSuccess ? ce2 : ce3)));
+  return FSUAE_OK;
+}
+
+int fsuae_engine_run_host(fsuae_engine* e, const void* in_host, void* out_host, int n_frames, int in_fmt,
+                          int out_fmt, uint32_t flags) {
+  int rc = fsuae_engine_submit_host(e, in_host, out_host, n_frames, in_fmt, out_fmt, flags);
+  if (!e) return rc;
+  const int rc2 = fsuae_engine_wait_host(e);      // drain even after a failed submission: nothing stays in flight
+  return rc != FSUAE_OK ? rc : rc2;
 }
 
 int fsuae_engine_set_profiling(fsuae_engine* e, int enabled) {

@@ -15,6 +15,8 @@ struct Bf16Plan;  // bf16_tc.cu
 
 }  // namespace fsuae
 
+#define FSUAE_STAGE_BUFS 3   // staging buffers of the host pipeline (upload / compute / download of three stages in flight)
+
 struct fsuae_engine {
   fsuae_net_desc desc;
   int device = 0;
@@ -47,10 +49,11 @@ struct fsuae_engine {
   int prof_n = 0;
 
   // run_host staging
-  void* d_stage_in[2] = {nullptr, nullptr};
-  void* d_stage_out[2] = {nullptr, nullptr};
+  void* d_stage_in[FSUAE_STAGE_BUFS] = {};
+  void* d_stage_out[FSUAE_STAGE_BUFS] = {};
   cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
-  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  unsigned long long stage_seq = 0;   // stages ever submitted: staging set = stage_seq % FSUAE_STAGE_BUFS, carries across submissions
+  cudaEvent_t ev_in[FSUAE_STAGE_BUFS] = {}, ev_comp[FSUAE_STAGE_BUFS] = {}, ev_out[FSUAE_STAGE_BUFS] = {};
 };
 
 namespace fsuae {

@@ -81,6 +81,19 @@ class Engine:
         self._check(self._lib.fsuae_engine_enqueue(self._h, x.data_ptr(), out.data_ptr(), n_frames, in_fmt,
                                                    out_fmt, flags, st.cuda_stream))
 
+    def submit_host(self, x: torch.Tensor, out: torch.Tensor, n_frames: int, in_fmt: int, out_fmt: int,
+                    flags: int = 0):
+        """Streaming form of :meth:`run_host`: queue upload, forward and download, return at once.  ``x`` and ``out``
+        must stay alive (and be pinned for real asynchrony) until :meth:`wait_host` returns."""
+        if x.is_cuda or out.is_cuda or not x.is_contiguous() or not out.is_contiguous():
+            raise ValueError("engine.submit_host needs contiguous CPU tensors")
+        self._check(self._lib.fsuae_engine_submit_host(self._h, x.data_ptr(), out.data_ptr(), n_frames, in_fmt,
+                                                       out_fmt, flags))
+
+    def wait_host(self):
+        """Block until every frame submitted with :meth:`submit_host` has arrived in its host output buffer."""
+        self._check(self._lib.fsuae_engine_wait_host(self._h))
+
     def run_host(self, x: torch.Tensor, out: torch.Tensor, n_frames: int, in_fmt: int, out_fmt: int,
                  flags: int = 0):
         """Synchronous end-to-end call on HOST tensors (pinned recommended): H2D, forward, D2H."""

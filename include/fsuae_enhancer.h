@@ -21,6 +21,7 @@
  *                            (convertion_tools/torch2onnx.py:184-768), i.e. OrtRun
  *                            (convert_raw_to_png_using_final_model.py:82)
  *   fsuae_engine_run_host    the same call as made from the emulator side with HOST framebuffers
+ *   fsuae_engine_submit_host / fsuae_engine_wait_host   streaming (asynchronous) form of run_host
  *                            (README.md:21-24: upload, upscale, copy back)
  *   fsuae_engine_destroy     Python GC of the module / OrtReleaseSession
  *   fsuae_last_error         Python exception text (ValueError at model_conv3.py:109-110,
@@ -171,6 +172,16 @@ FSUAE_API int fsuae_engine_enqueue(fsuae_engine* e, const void* in_dev, void* ou
  * overlaps H2D copy, compute and D2H copy on internal streams, returns when out_host is complete. */
 FSUAE_API int fsuae_engine_run_host(fsuae_engine* e, const void* in_host, void* out_host, int n_frames,
                           int in_fmt, int out_fmt, uint32_t flags);
+
+/* Streaming form of the same call (no reference counterpart: ONNX Runtime's Run is synchronous; this is what removes
+ * the per-frame copy-back stall README.md:23-24 describes).  submit queues upload, forward and download of n_frames
+ * frames on the engine's internal streams and returns at once; consecutive submissions overlap each other.  The
+ * buffers must stay valid -- and must be pinned for the copies to be asynchronous -- until fsuae_engine_wait_host
+ * returns, which blocks until every submitted frame has arrived in its out_host.
+ * fsuae_engine_run_host == submit + wait. */
+FSUAE_API int fsuae_engine_submit_host(fsuae_engine* e, const void* in_host, void* out_host, int n_frames,
+                             int in_fmt, int out_fmt, uint32_t flags);
+FSUAE_API int fsuae_engine_wait_host(fsuae_engine* e);
 
 /* Device bytes held by the engine (parameters + workspace + staging). */
 FSUAE_API size_t fsuae_engine_device_bytes(const fsuae_engine* e);

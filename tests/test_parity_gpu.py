@@ -399,3 +399,24 @@ def test_bf16_is_reproducible_at_full_size():
     first = m(x).clone()
     for _ in range(11):
         assert torch.equal(m(x), first)
+
+
+def test_streaming_host_submissions_match_the_blocking_call():
+    """fsuae_engine_submit_host x3 + one wait == three fsuae_engine_run_host calls (staging pairs carry across
+    submissions; upload, forward and download of consecutive submissions overlap)."""
+    from fs_uae_image_enhancer_project_b200 import _lib
+    spec = O.pix_shuffle_preset("lightweight")
+    sd = O.make_pix_shuffle_state_dict(spec, 77)
+    m = _bf16_model(spec, sd)
+    m.chunk_frames = 8
+    fbs = [O.synth_framebuffers(n, seed=20 + n, h=64, w=96).pin_memory() for n in (5, 40, 9)]
+    want = [m.run_host(fb) for fb in fbs]
+    eng = m.engine_for(dev(), 64, 96)
+    outs = [torch.zeros_like(fb).pin_memory() for fb in fbs]
+    flags = _lib.FLAG_GAMMA_IN | _lib.FLAG_GAMMA_OUT
+    for fb, out in zip(fbs, outs):
+        eng.submit_host(fb, out, fb.shape[0], _lib.FMT_U8_NHWC4, _lib.FMT_U8_NHWC4, flags)
+    eng.wait_host()
+    for w, o in zip(want, outs):
+        assert torch.equal(w, o)
+    assert (want[0].int() - O.framebuffer_forward(sd, spec, fbs[0]).int()).abs().max().item() <= 6
