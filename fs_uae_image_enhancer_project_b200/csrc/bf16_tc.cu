@@ -76,13 +76,19 @@ struct LayerK {
   int in_fmt, out_fmt, H, W, xoff, gamma_in, gamma_out;
   // epilogue parameters, expanded per channel on the host
   int n_pre, n_post;
+  int dbg;                 // debugging aid (FSUAE_DBG): 1 = epilogue skips its global stores, 2 = producer re-reads the segment's first row
   int op[4];               // pre0, pre1, post0, post1 (identity-padded)
   float bias[MAXC];
   float p0[4][MAXC];
   float p1[4][MAXC];
 };
 
-template <int PT, int NPAD, int CTAS = 1>   // CTAS = 2: CTA pair (cta_group::2), each CTA holds half of the weight rows
+// CTAS = 2: CTA pair (cta_group::2), each CTA holds half of the weight rows.
+// R3: "three output rows per instruction" mode (single CTA): one MMA multiplies an input row by the weights of all
+// three kernel rows at once (N = 3 * NPAD) and accumulates into the three neighbouring output rows, whose
+// accumulators sit side by side in a circular TMEM buffer.  The A operand (4 KB per instruction, the bottleneck of
+// narrow-N UMMA: max(N/2, (4096 + 32 N)/128) cycles) is then read once per input row instead of three times.
+template <int PT, int NPAD, int CTAS = 1, bool R3 = false>
 struct Cfg {
   static constexpr int UNITS_ROW = 3 * PT;                 // (chunk, dx) units of one input row
   static constexpr int STEPS_ROW = (UNITS_ROW + 1) / 2;    // K=16 instructions per input row
@@ -92,12 +98,14 @@ struct Cfg {
   static constexpr int ROWBYTES = PT * PLANE_ROW;
   static constexpr int RING_FIT = (SMEM_LIMIT - WBYTES - 64 - 512) / ROWBYTES;
   static constexpr int RING = RING_FIT > 10 ? 10 : RING_FIT;
-  static constexpr int STAGES = (512 / NPAD) > 8 ? 8 : (512 / NPAD);   // accumulator stages: more than warpgroups, so the MMAs run ahead of the (MUFU-bound) epilogues
+  static constexpr int STAGES_CAP = R3 ? 12 : 8;
+  static constexpr int STAGES = (512 / NPAD) > STAGES_CAP ? STAGES_CAP : (512 / NPAD);   // accumulator stages: more than warpgroups, so the MMAs run ahead of the (MUFU-bound) epilogues
   static constexpr int BAR_OFF = WBYTES + RING * ROWBYTES + 64;
   static constexpr int SMEM = BAR_OFF + 512;
   static_assert(RING >= 4, "layer does not fit: weights + 4 ring rows exceed shared memory");
   static_assert(STAGES * NPAD <= 512, "accumulator stages exceed TMEM");
   static_assert(NB % 8 == 0, "each CTA of a pair needs whole 8-row core matrices of B");
+  static_assert(!R3 || (CTAS == 1 && 3 * NPAD <= 256 && STAGES >= 6), "R3 mode: single CTA, N = 3 NPAD <= 256, >= 6 accumulators");
 };
 
 // ---- fast activation math for the bf16 build (error well below bf16 resolution) ----------------
@@ -310,9 +318,10 @@ struct SegIter {
 // ------------------------------------------------------------------------------------------------
 // the layer kernel
 // ------------------------------------------------------------------------------------------------
-template <int PT, int NPAD, int COUT, int KIND, class EPI, int CTAS = 1>
+template <int PT, int NPAD, int COUT, int KIND, class EPI, int CTAS = 1, bool R3 = false>
 __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_constant__ LayerK P) {
-  using C = Cfg<PT, NPAD, CTAS>;
+  using C = Cfg<PT, NPAD, CTAS, R3>;
+  static_assert(!R3 || !EPI::kSkip, "R3 mode releases a ring row as soon as its MMAs are done: no residual from the ring");
   const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;   // rank 0 of a pair issues the MMAs
   constexpr int OUT_PLANES = COUT > 0 ? (COUT + 7) / 8 : 1;   // COUT <= 0: channel count is a run-time parameter
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -381,12 +390,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
         const unsigned char* g1 = P.P1 ? P.src1 + (size_t)f * P.fs1 + org : nullptr;
         for (int k = 0; k < rows + 2; ++k) {          // padded rows y0 .. y0+rows+1
           mbar_wait(&empty[slot], par);
-          mbar_arrive_expect_tx(&full[slot], C::ROWBYTES);
           uint8_t* d = s_ring + slot * C::ROWBYTES;
+          const int kk = (P.dbg & 2) ? 0 : k;
+          if (P.dbg & 4) {      // timing experiment: one plane only (results are garbage)
+            mbar_arrive_expect_tx(&full[slot], PLANE_ROW);
+            tma_load_1d(d, g0 + (size_t)kk * row_pitch, PLANE_ROW, &full[slot]);
+            if (++slot == C::RING) { slot = 0; par ^= 1; }
+            continue;
+          }
+          mbar_arrive_expect_tx(&full[slot], C::ROWBYTES);
           for (int j = 0; j < P.P0; ++j)
-            tma_load_1d(d + j * PLANE_ROW, g0 + (size_t)j * plane_pitch + (size_t)k * row_pitch, PLANE_ROW, &full[slot]);
+            tma_load_1d(d + j * PLANE_ROW, g0 + (size_t)j * plane_pitch + (size_t)kk * row_pitch, PLANE_ROW, &full[slot]);
           for (int j = 0; j < P.P1; ++j)
-            tma_load_1d(d + (P.P0 + j) * PLANE_ROW, g1 + (size_t)j * plane_pitch + (size_t)k * row_pitch, PLANE_ROW, &full[slot]);
+            tma_load_1d(d + (P.P0 + j) * PLANE_ROW, g1 + (size_t)j * plane_pitch + (size_t)kk * row_pitch, PLANE_ROW, &full[slot]);
           if (++slot == C::RING) { slot = 0; par ^= 1; }
         }
       }
@@ -428,6 +444,73 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
       uint32_t stage = 0, spar = 1;       // accumulator stage / parity for tempty
       SegIter it(P, CTAS, (int)rank);
       Seg sg;
+      if constexpr (R3) {
+        // ---- three output rows per instruction ----
+        // Input row k of a segment (image row y0-1+k) feeds output rows j = k-2 (kernel row 2), k-1 (row 1), k (row 0);
+        // the B operand of a step is [W2 | W1 | W0] (3 NPAD rows), a sub-range of it is just a start-address offset.
+        // Output row j (block number blk0 + j) accumulates in TMEM slot (blk0 + j) % STAGES; the slots of j-2..j are
+        // adjacent except where the circular buffer wraps, there the instruction is split in two.  The newest row's
+        // accumulator must be overwritten, not accumulated into, by its first instruction: that one is issued apart.
+        constexpr uint32_t N3 = 3 * NPAD;
+        constexpr uint32_t BSTEP3 = (N3 * 32) >> 4;
+        const uint32_t w3_lo = ((smem_u32(s_w) & 0x3FFFFu) >> 4) | ((uint32_t)((N3 * 16) >> 4) << 16);
+        uint32_t blk0 = 0;
+        constexpr uint32_t IDESC0 = umma_idesc_bf16(MROWS, 0);             // N field (bits 17..22, N >> 3) added per run
+        constexpr uint32_t IDN = (uint32_t)(NPAD >> 3) << 17;
+        while (it.next(P, sg)) {
+          const int rows = sg.rows;
+          // slot / tempty parity of block blk0 + k, kept incrementally (one thread issues everything: every integer
+          // division here would cost more than an MMA)
+          uint32_t sk = blk0 % C::STAGES, pk = ((blk0 / C::STAGES) & 1u) ^ 1u;
+          for (int k = 0; k < rows + 2; ++k) {
+            wait_row(wslot, wpar);
+            const uint32_t rs = wslot;
+            if (++wslot == C::RING) { wslot = 0; wpar ^= 1; }
+            const int jlo = max(k - 2, 0), jhi = min(k, rows - 1);
+            const bool has_new = k <= rows - 1;
+            if (has_new) mbar_wait(&tempty[sk], pk);
+            tc_fence_after();
+            const int back = k - jlo;                                           // 0..2 older rows in flight
+            const uint32_t slot_lo = sk >= (uint32_t)back ? sk - (uint32_t)back : sk + C::STAGES - (uint32_t)back;
+            const uint32_t boff0 = (uint32_t)((jlo - (k - 2)) * NPAD);     // first B row of the run, in 16-byte units
+            // steps >= 1 (and step 0 of the last two input rows): output rows jlo..jhi, split where the accumulator ring wraps
+            const int cnt = jhi - jlo + 1;
+            const int c0 = min(cnt, (int)(C::STAGES - slot_lo)), c1 = cnt - c0;
+            const uint32_t d0 = tmem_base + slot_lo * NPAD, d1 = tmem_base;
+            const uint32_t id0 = IDESC0 + (uint32_t)c0 * IDN, id1 = IDESC0 + (uint32_t)c1 * IDN;
+            const uint32_t bo1 = boff0 + (uint32_t)(c0 * NPAD);
+            // step 0 of a row that opens a new accumulator: rows jlo..k-1 accumulate, row k is overwritten
+            const int co0 = min(back, (int)(C::STAGES - slot_lo)), co1 = back - co0;
+            const uint32_t ido0 = IDESC0 + (uint32_t)co0 * IDN, ido1 = IDESC0 + (uint32_t)co1 * IDN;
+            const uint32_t boo1 = boff0 + (uint32_t)(co0 * NPAD);
+            const uint32_t dn = tmem_base + sk * NPAD, bon = 2u * NPAD;
+            const uint32_t s_done = sk >= 2u ? sk - 2u : sk + C::STAGES - 2u;   // slot of output row k-2
+            if (++sk == C::STAGES) { sk = 0; pk ^= 1u; }
+            const uint32_t a_row = ring_lo + rs * (C::ROWBYTES >> 4);
+#pragma unroll
+            for (int st = 0; st < C::STEPS_ROW; ++st) {
+              // units 2 st, 2 st + 1 of the row (unit u: plane u / 3, tap u % 3); odd tail: units 3 PT - 2 (zero weights), 3 PT - 1
+              const int u0 = (2 * st + 1 < 3 * PT) ? 2 * st : 3 * PT - 2;
+              const int pl = u0 / 3, dx = u0 - 3 * pl;
+              const uint32_t lbo = dx == 2 ? (uint32_t)((PLANE_ROW >> 4) - 2) : 1u;
+              const uint64_t a_desc = ((uint64_t)HI << 32) | ((a_row + (uint32_t)(pl * (PLANE_ROW >> 4) + dx)) | (lbo << 16));
+              const uint64_t b_hi = (uint64_t)HI << 32;
+              const uint32_t b_st = w3_lo + (uint32_t)st * BSTEP3;
+              if (st == 0 && has_new) {
+                if (co0 > 0) umma_bf16(d0, a_desc, b_hi | (b_st + boff0), ido0, 1u);
+                if (co1 > 0) umma_bf16(d1, a_desc, b_hi | (b_st + boo1), ido1, 1u);
+                umma_bf16(dn, a_desc, b_hi | (b_st + bon), IDESC0 + IDN, 0u);
+              } else {
+                umma_bf16(d0, a_desc, b_hi | (b_st + boff0), id0, 1u);
+                if (c1 > 0) umma_bf16(d1, a_desc, b_hi | (b_st + bo1), id1, 1u);
+              }
+            }
+            commit(&empty[rs]);                                              // this input row is not needed again
+            if (k >= 2) commit(&tfull[s_done]);                               // output row k-2 is complete
+          }
+          blk0 += (uint32_t)rows;
+        }
+      } else
       while (it.next(P, sg)) {
         const int rows = sg.rows;
         uint32_t s0 = wslot;              // slot of the block's first input row
@@ -501,7 +584,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
     while (it.next(P, sg)) {
       const int f = sg.f, s = sg.s, y0 = sg.y0, rows = sg.rows;
       const int x = s * STRIP + m;
-      const bool valid = m < STRIP && x < P.Ww;
+      const bool valid = m < STRIP && x < P.Ww && !(P.dbg & 1);
       for (int b = 0; b < rows; ++b, ++blk) {
         if ((blk & (EPI_WG - 1)) != group) continue;
         const uint32_t stage = blk % C::STAGES, spar = (blk / C::STAGES) & 1u;
@@ -1201,9 +1284,37 @@ std::vector<uint16_t> pack_weights(const float* w, int cout, int cin0, int cin1,
 
 #include "bf16_wide.cuh"
 
+// R3 mode: B operand of step st of an input row = [2 halves][3 NPAD rows][8 k]; row block b holds kernel row dy = 2 - b
+// (the input row is the bottom / middle / top row of output rows k-2 / k-1 / k).
+std::vector<uint16_t> pack_weights_r3(const float* w, int cout, int cin0, int cin1, int P0, int P1, int NPAD) {
+  const int PT = P0 + P1, cin = cin0 + cin1;
+  const int steps_row = (3 * PT + 1) / 2, N3 = 3 * NPAD;
+  std::vector<uint16_t> out((size_t)steps_row * 2 * N3 * 8, 0);
+  for (int st = 0; st < steps_row; ++st)
+    for (int h = 0; h < 2; ++h) {
+      int u = 2 * st + h;
+      if (2 * st + 1 >= 3 * PT) {
+        if (h == 0) continue;
+        u = 3 * PT - 1;
+      }
+      const int j = u / 3, dx = u % 3;
+      for (int b = 0; b < 3; ++b)
+        for (int n = 0; n < cout; ++n)
+          for (int k = 0; k < 8; ++k) {
+            int ci;
+            if (j < P0) { ci = j * 8 + k; if (ci >= cin0) continue; }
+            else { ci = (j - P0) * 8 + k; if (ci >= cin1) continue; ci += cin0; }
+            const float v = w[((size_t)n * cin + ci) * 9 + (2 - b) * 3 + dx];
+            out[(((size_t)st * 2 + h) * N3 + b * NPAD + n) * 8 + k] = f2bf(v);
+          }
+    }
+  return out;
+}
+
 typedef void (*KernelFn)(const LayerK);
 
 struct Variant {
+  int R3;                               // 1: three-output-rows-per-instruction kernel (single CTA), preferred when instantiated
   int CTAS;                             // 2: CTA-pair kernel (cta_group::2), used when a launch has >= 2 frames
   int PT, NPAD, COUT, KIND;             // COUT <= 0: run-time channel count
   int pre0, pre1, post0, post1, skip;   // -1 = run-time op-codes
@@ -1211,9 +1322,10 @@ struct Variant {
   int smem;
 };
 
-template <int PT, int NPAD, int COUT, int KIND, class EPI, int CTAS = 1>
+template <int PT, int NPAD, int COUT, int KIND, class EPI, int CTAS = 1, bool R3 = false>
 Variant make_variant(int a, int b, int c, int d, int skip) {
-  Variant v{CTAS, PT, NPAD, COUT, KIND, a, b, c, d, skip, conv3x3_tc_kernel<PT, NPAD, COUT, KIND, EPI, CTAS>, Cfg<PT, NPAD, CTAS>::SMEM};
+  Variant v{R3 ? 1 : 0, CTAS, PT, NPAD, COUT, KIND, a, b, c, d, skip, conv3x3_tc_kernel<PT, NPAD, COUT, KIND, EPI, CTAS, R3>,
+            Cfg<PT, NPAD, CTAS, R3>::SMEM};
   return v;
 }
 template <int PT, int NPAD, int KIND, bool SKIP>
@@ -1240,6 +1352,11 @@ const std::vector<Variant>& variants() {
       make_variant<9, 48, 36, EPI_STORE, Epi<0, 0, 0, 0, false>, 2>(0, 0, 0, 0, 0),
       make_variant<10, 48, 36, EPI_STORE, Epi<A(MISH), A(RELU6), 0, 0, false>, 2>(A(MISH), A(RELU6), 0, 0, 0),
       make_variant<5, 16, 12, EPI_TAIL_SHUFFLE, Epi<A(BIASED_PRELU), 0, 0, 0, false>, 2>(A(BIASED_PRELU), 0, 0, 0, 0),
+      // ---- the layers without a residual as three-output-rows-per-instruction kernels (A operand read once per input row) ----
+      make_variant<2, 48, 36, EPI_STORE, Epi<A(SINLU), A(RELU6), 0, 0, false>, 1, true>(A(SINLU), A(RELU6), 0, 0, 0),
+      make_variant<9, 48, 36, EPI_STORE, Epi<0, 0, 0, 0, false>, 1, true>(0, 0, 0, 0, 0),
+      make_variant<10, 48, 36, EPI_STORE, Epi<A(MISH), A(RELU6), 0, 0, false>, 1, true>(A(MISH), A(RELU6), 0, 0, 0),
+      make_variant<5, 16, 12, EPI_TAIL_SHUFFLE, Epi<A(BIASED_PRELU), 0, 0, 0, false>, 1, true>(A(BIASED_PRELU), 0, 0, 0, 0),
       // ---- run-time epilogues: any activation chain of the registry (except channel softmax), any Cout <= NPAD ----
       // pix_shuffle channel plans (36/72 and the heavyweight 108)
       generic_variant<2, 48, EPI_STORE, false>(), generic_variant<5, 48, EPI_STORE, false>(), generic_variant<5, 48, EPI_STORE, true>(),
@@ -1274,6 +1391,8 @@ struct Launch {
   float* d_params = nullptr;       // device copy of the per-channel epilogue parameters
   const Variant* var2 = nullptr;   // CTA-pair kernel for the same layer (weights packed per CTA), if instantiated
   unsigned char* d_w2 = nullptr;
+  const Variant* var3 = nullptr;   // three-output-rows-per-instruction kernel for the same layer, if instantiated
+  unsigned char* d_w3 = nullptr;
   LayerK k{};   // geometry-independent fields prefilled
   const WideVariant* wide = nullptr;   // K-streamed tile kernel instead (layers too wide for resident weights / full-depth rows)
   WideK wk{};
@@ -1356,7 +1475,7 @@ int bf16_create(fsuae_engine* e) {
     const Variant* fit_ops = nullptr;    // the same with this layer's op-codes compiled in (run-time channel count)
     const Variant* widest_ops = nullptr;
     for (const Variant& v : variants()) {
-      if (v.CTAS != 1 || v.PT != PT || v.KIND != kind || v.skip != skip) continue;
+      if (v.CTAS != 1 || v.R3 || v.PT != PT || v.KIND != kind || v.skip != skip) continue;
       const bool ops_eq = v.pre0 == ops[0] && v.pre1 == ops[1] && v.post0 == ops[2] && v.post1 == ops[3];
       if (v.COUT == L.cout && ops_eq) exact = &v;
       if (v.COUT > 0) continue;
@@ -1465,9 +1584,26 @@ int bf16_create(fsuae_engine* e) {
         FSUAE_CUDA_CHECK(e, cudaMemcpy(ln.d_params, hp.data(), hp.size() * sizeof(float), cudaMemcpyHostToDevice));
         k.dparams = ln.d_params;
       }
+      // Opt-in (FSUAE_R3=1): measured on B200 it only ties the CTA-pair kernels (conv5 6.4 vs 6.0 us/frame, conv7 3.6 vs
+      // 3.6) -- the N = 144 instruction costs 85 cycles against 3 x 43 for the pair kernel's three N = 48 ones, but the
+      // accumulator-ring wrap splits, the separate first instruction of every new row and the longer per-row scalar
+      // prologue of the single issuing thread eat the difference.
+      if (var == exact && getenv("FSUAE_R3") && atoi(getenv("FSUAE_R3")) != 0) {
+        for (const Variant& v : variants())
+          if (v.R3 && v.PT == var->PT && v.NPAD == var->NPAD && v.COUT == var->COUT && v.KIND == var->KIND && v.skip == var->skip &&
+              v.pre0 == var->pre0 && v.pre1 == var->pre1 && v.post0 == var->post0 && v.post1 == var->post1)
+            ln.var3 = &v;
+        if (ln.var3) {
+          std::vector<uint16_t> wp3 = pack_weights_r3(e->h_blob.data() + L.w_off, cg, L.cin0, L.cin1, P0, P1, var->NPAD);
+          FSUAE_CUDA_CHECK(e, cudaMalloc(&ln.d_w3, wp3.size() * 2));
+          FSUAE_CUDA_CHECK(e, cudaMemcpy(ln.d_w3, wp3.data(), wp3.size() * 2, cudaMemcpyHostToDevice));
+          e->device_bytes += wp3.size() * 2;
+          FSUAE_CUDA_CHECK(e, cudaFuncSetAttribute((const void*)ln.var3->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ln.var3->smem));
+        }
+      }
       if (var == exact && !getenv("FSUAE_NO_PAIRS")) {
         for (const Variant& v : variants())
-          if (v.CTAS == 2 && v.PT == var->PT && v.NPAD == var->NPAD && v.COUT == var->COUT && v.KIND == var->KIND &&
+          if (v.CTAS == 2 && !v.R3 && v.PT == var->PT && v.NPAD == var->NPAD && v.COUT == var->COUT && v.KIND == var->KIND &&
               v.skip == var->skip && v.pre0 == var->pre0 && v.pre1 == var->pre1 && v.post0 == var->post0 && v.post1 == var->post1)
             ln.var2 = &v;
         if (ln.var2) {
@@ -1533,7 +1669,7 @@ void bf16_destroy(fsuae_engine* e) {
   if (!e->bf16) return;
   for (auto& lp : e->bf16->layers)
     for (auto& ln : lp.launches)
-      { if (ln.d_w) cudaFree(ln.d_w); if (ln.d_w2) cudaFree(ln.d_w2); if (ln.d_params) cudaFree(ln.d_params); }
+      { if (ln.d_w) cudaFree(ln.d_w); if (ln.d_w2) cudaFree(ln.d_w2); if (ln.d_w3) cudaFree(ln.d_w3); if (ln.d_params) cudaFree(ln.d_params); }
   for (unsigned char* p : e->bf16->buf)
     if (p) cudaFree(p);
   delete e->bf16;
@@ -1578,6 +1714,7 @@ int bf16_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in
     k.H = g.H; k.W = g.W; k.xoff = g.xoff;
     k.gamma_in = gin;
     k.gamma_out = (flags & FSUAE_FLAG_GAMMA_OUT) ? 1 : 0;
+    if (const char* dbg = getenv("FSUAE_DBG")) k.dbg = atoi(dbg);
     return k;
   };
   auto launch_cfg = [&](cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int n_blocks, int ctas, int smem) {
@@ -1630,11 +1767,13 @@ int bf16_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in
         e->launches++;
         continue;
       }
-      const bool pair = ln.var2 != nullptr && n >= 2;      // CTA pairs process two frames in lockstep
-      const Variant* var = pair ? ln.var2 : ln.var;
-      const LayerK k = fill(i, ln, pair);
+      const bool r3 = ln.var3 != nullptr;
+      const bool pair = !r3 && ln.var2 != nullptr && n >= 2;      // CTA pairs process two frames in lockstep
+      const Variant* var = r3 ? ln.var3 : (pair ? ln.var2 : ln.var);
+      LayerK k = fill(i, ln, pair);
+      if (r3) k.wpack = ln.d_w3;
       launch_cfg(cfg, attr, k.n_blocks, pair ? 2 : 1, var->smem);
-      { ProfScope ps(e, st, ("conv" + std::to_string(i + 1) + (pair ? "_pair" : "")).c_str());
+      { ProfScope ps(e, st, ("conv" + std::to_string(i + 1) + (r3 ? "_r3" : (pair ? "_pair" : ""))).c_str());
         FSUAE_CUDA_CHECK(e, cudaLaunchKernelEx(&cfg, var->fn, k)); }
       e->launches++;
     }

@@ -420,3 +420,19 @@ def test_streaming_host_submissions_match_the_blocking_call():
     for w, o in zip(want, outs):
         assert torch.equal(w, o)
     assert (want[0].int() - O.framebuffer_forward(sd, spec, fbs[0]).int()).abs().max().item() <= 6
+
+
+def test_bf16_three_rows_per_instruction_kernels(monkeypatch):
+    """Opt-in R3 kernels (one MMA feeds three output rows, N = 3 x NPAD, circular TMEM accumulators): same results as
+    the default CTA-pair kernels within bf16 tolerance, for ragged segment partitions too."""
+    spec = O.pix_shuffle_preset("lightweight")
+    sd = O.make_pix_shuffle_state_dict(spec, 91)
+    x = torch.rand(3, 3, 50, 600, generator=torch.Generator().manual_seed(6))
+    want = O.pix_shuffle_forward(sd, spec, x)
+    monkeypatch.setenv("FSUAE_R3", "1")
+    m = _bf16_model(spec, sd)
+    got = m(x.to(dev())).cpu()
+    assert (got - want).abs().max().item() <= BF16_TOL and O.psnr(got, want, 1.0) >= BF16_PSNR
+    for grid in (1, 3, 7):
+        monkeypatch.setenv("FSUAE_DEBUG_GRID", str(grid))
+        assert torch.equal(m(x.to(dev())).cpu(), got)

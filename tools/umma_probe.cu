@@ -52,7 +52,7 @@ __global__ void probe_correct(const __nv_bfloat16* A, const __nv_bfloat16* B, fl
 
 // ---------------- test 2: issue rate ----------------
 // one CTA per SM; thread 0 issues `iters` x 64 MMAs; descriptors advance by adds only (lean issue loop)
-__global__ void probe_rate(int N, int iters, uint32_t a_step16, uint32_t b_step16, long long* cycles) {
+__global__ void probe_rate(int N, int iters, uint32_t a_step16, uint32_t b_step16, long long* cycles, uint32_t d_off = 0, uint32_t d_alt = 256) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base;
@@ -77,7 +77,7 @@ __global__ void probe_rate(int N, int iters, uint32_t a_step16, uint32_t b_step1
       uint32_t a_lo = a_lo0, b_lo = b_lo0;
 #pragma unroll
       for (int j = 0; j < 64; ++j) {
-        umma_bf16(tb + (it & 1) * 256, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc, 1);
+        umma_bf16(tb + d_off + (it & 1) * d_alt, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc, 1);
         a_lo += a_step16;   // 64 x step must stay inside the 96 KB A window
         b_lo += b_step16;
       }
@@ -163,6 +163,19 @@ int main() {
         printf("rate grid=%3d N=%3d mode=%d: %.1f cycles/MMA (ideal N/2 = %d; A-read bound 32)\n", grid, N, mode,
                (double)mx / (iters * 64), N / 2);
       }
+    }
+  }
+  // wide N (three output rows per instruction) and accumulators that do not start at column 0
+  for (int N : {96, 144, 192, 240}) {
+    for (uint32_t d_off : {0u, 16u, 48u}) {
+      const uint32_t d_alt = (N + d_off <= 256) ? 256u : 0u;
+      probe_rate<<<sms, 128, smem>>>(N, 50, 65, 0, dcy, d_off, d_alt);
+      CK(cudaDeviceSynchronize());
+      std::vector<long long> h(sms);
+      CK(cudaMemcpy(h.data(), dcy, sms * 8, cudaMemcpyDeviceToHost));
+      long long mx = 0; for (auto v : h) mx = v > mx ? v : mx;
+      printf("wide rate N=%3d d_col=%2u: %.1f cycles/MMA (N/2 = %d, (4096+32N)/128 = %d)\n", N, d_off, (double)mx / (50 * 64), N / 2,
+             (4096 + 32 * N) / 128);
     }
   }
   return ok ? 0 : 1;
