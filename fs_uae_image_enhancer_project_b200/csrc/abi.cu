@@ -57,7 +57,7 @@ static int validate(const fsuae_net_desc* d, size_t blob_floats, int H, int W, s
     if (L.src0 < 0 || L.src0 > i || ch[L.src0] != L.cin0) return bad(tag + "src0 mismatch");
     if (L.cin1 > 0 && (L.src1 < 0 || L.src1 > i || ch[L.src1] != L.cin1)) return bad(tag + "src1 mismatch");
     if (L.skip_src >= 0 && (L.skip_src > i || ch[L.skip_src] != L.cout))
-      return bad(tag + "skip source channel mismatch (1x1 skip projections are not supported)");
+      return bad(tag + "skip source channel mismatch (a 1x1 skip projection is described as a layer of its own)");
     size_t wn = (size_t)L.cout * (L.cin0 + L.cin1) * 9;
     if (L.w_off < 0 || (size_t)L.w_off + wn > blob_floats) return bad(tag + "weights outside blob");
     if (L.b_off >= 0 && (size_t)L.b_off + L.cout > blob_floats) return bad(tag + "bias outside blob");

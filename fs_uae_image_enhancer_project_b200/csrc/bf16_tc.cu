@@ -687,6 +687,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
             uint4 skc = make_uint4(0, 0, 0, 0);
             if constexpr (EPI::kSkip) {
               if (valid) skc = *reinterpret_cast<const uint4*>(sp + c * PLANE_ROW);
+            } else if (P.skip != nullptr) {      // residual from another buffer (1x1 skip projection): read from global memory
+              if (valid) skc = __ldg(reinterpret_cast<const uint4*>(P.skip + (size_t)f * P.fs_skip + pix + (size_t)(P.skip_plane0 + c) * plane_pitch));
             }
             EPI_T(t_c);
             const float* prm = P.dparams + c * 8;
@@ -702,7 +704,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
             o[6] = __uint_as_float(v[6]) + b1.z; o[7] = __uint_as_float(v[7]) + b1.w;
             EPI_T(t_f);
             EPI_ACC(2, t_d - t_c); EPI_ACC(3, t_e - t_d); EPI_ACC(4, t_f - t_e); EPI_ACC(7, 1);
-            epi_chain8<EPI>(ops_packed, prm, MAXC, EPI::kSkip, skc, o);
+            epi_chain8<EPI>(ops_packed, prm, MAXC, EPI::kSkip || P.skip != nullptr, skc, o);
             if (c * 8 + 8 > P.cout) {      // padding channels of the last plane stay exactly zero (uniform branch)
 #pragma unroll
               for (int i = 0; i < 8; ++i) o[i] = (c * 8 + i < P.cout) ? o[i] : 0.f;
@@ -1462,9 +1464,12 @@ int bf16_create(fsuae_engine* e) {
     for (int k = 0; k < L.n_pre; ++k) ops[k] = L.pre[k].op;
     for (int k = 0; k < L.n_post; ++k) ops[2 + k] = L.post[k].op;
     const int kind = !last ? EPI_STORE : (d.tail == FSUAE_TAIL_SHUFFLE2_RESIDUAL_RELU ? EPI_TAIL_SHUFFLE : EPI_TAIL_PLAIN);
-    const int skip = L.skip_src >= 0 ? 1 : 0;
-    if (skip && (L.skip_src != L.src0 || L.cin1 > 0))
-      return set_error(e, FSUAE_ERR_UNSUPPORTED, tag + "the residual must be the layer's own input (true for every reference model)");
+    // The residual is normally the layer's own input and is then read from the centre row of the shared-memory ring;
+    // a residual from another buffer (the 1x1 skip projections of model_pix_shuffle.py:126-128, 143-145) is read from
+    // global memory by the run-time epilogues.
+    const int any_skip = L.skip_src >= 0 ? 1 : 0;
+    const bool global_skip = any_skip && (L.skip_src != L.src0 || L.cin1 > 0);
+    const int skip = any_skip && !global_skip ? 1 : 0;
 
     // pick the kernel: exact compile-time epilogue if there is one, else the run-time one; a layer wider than the
     // widest instantiated N for its input plane count is split into output-channel groups
@@ -1487,11 +1492,12 @@ int bf16_create(fsuae_engine* e) {
         if (!widest || v.NPAD > widest->NPAD) widest = &v;
       }
     }
+    if (global_skip) exact = fit_ops = widest_ops = nullptr;      // only the run-time epilogue knows about a residual in global memory
     const Variant* var = exact ? exact : fit_ops ? fit_ops : fit ? fit : widest_ops ? widest_ops : widest;
     // Layers whose weights / full-depth input rows do not fit beside each other in shared memory stream K through the
     // wide tile kernel (thin-input layers are cheap to split over output-channel groups instead).
     const bool too_wide = !var || var->NPAD < need;
-    const bool use_wide = !exact && kind != EPI_TAIL_SHUFFLE && !getenv("FSUAE_NO_WIDE") &&
+    const bool use_wide = !exact && !getenv("FSUAE_NO_WIDE") &&
                           ((too_wide && (PT >= 4 || !var)) || (getenv("FSUAE_FORCE_WIDE") != nullptr));
     if (use_wide) {
       const int ngroups = kind == EPI_STORE ? (need + 127) / 128 : 1;
@@ -1499,7 +1505,7 @@ int bf16_create(fsuae_engine* e) {
       const WideVariant* wv = nullptr;
       for (int pass = 0; pass < 2 && !wv; ++pass)      // first a variant with this layer's op-codes compiled in, then the run-time one
         for (const WideVariant& v : wide_variants()) {
-          const bool ops_eq = v.pre0 == ops[0] && v.pre1 == ops[1] && v.post0 == ops[2] && v.post1 == ops[3] && v.skip == skip;
+          const bool ops_eq = v.pre0 == ops[0] && v.pre1 == ops[1] && v.post0 == ops[2] && v.post1 == ops[3] && v.skip == any_skip;
           if (v.KIND != kind || v.NT < per || (pass == 0 ? !ops_eq : v.pre0 != -1)) continue;
           if (!wv || v.NT < wv->NT) wv = &v;
         }
@@ -1514,7 +1520,7 @@ int bf16_create(fsuae_engine* e) {
       std::memset(&k, 0, sizeof(k));
       k.P0 = P0; k.pin = PT; k.kchunks = (PT + 1) / 2;
       k.ngroups = ngroups; k.cout = L.cout; k.cpad = ngroups * wv->NT;
-      k.has_skip = skip;
+      k.has_skip = any_skip;
       k.wpack = ln.d_w;
       std::vector<float> hp((size_t)9 * k.cpad, 0.f);
       for (int c = 0; c < k.cpad; ++c) {
@@ -1759,7 +1765,8 @@ int bf16_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in
         if (L.cin1 > 0) { k.src1 = plan->buf[L.src1]; k.fs1 = fstride(L.src1); }
         if (L.skip_src >= 0) { k.skip = plan->buf[L.skip_src]; k.fs_skip = fstride(L.skip_src); }
         if (i < d.n_layers - 1) { k.dst = plan->buf[i + 1]; k.fs_dst = fstride(i + 1); }
-        k.frame_out = out; k.out_fmt = out_fmt; k.H = g.H; k.W = g.W; k.xoff = g.xoff;
+        k.frame_in = in; k.frame_out = out; k.in_fmt = in_fmt; k.out_fmt = out_fmt; k.H = g.H; k.W = g.W; k.xoff = g.xoff;
+        k.gamma_in = gin;
         k.gamma_out = (flags & FSUAE_FLAG_GAMMA_OUT) ? 1 : 0;
         launch_cfg(cfg, attr, k.n_units, 2, ln.wide->smem);
         { ProfScope ps(e, st, ("conv" + std::to_string(i + 1) + "_wide").c_str());

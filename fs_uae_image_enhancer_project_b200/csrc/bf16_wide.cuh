@@ -31,8 +31,9 @@ struct WideK {
   const unsigned char* wpack;    // [group][slice][rank][tap][half][NT/2][8] bf16
   const float* dparams;          // {bias, p0[4], p1[4]} x cpad
   int op[4];
+  const void* frame_in;          // EPI_TAIL_SHUFFLE: the network input is added back behind PixelShuffle(2)
   void* frame_out;
-  int out_fmt, H, W, xoff, gamma_out;
+  int in_fmt, out_fmt, H, W, xoff, gamma_in, gamma_out;
 };
 
 template <int NT>
@@ -82,6 +83,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_wide_kernel(const __gr
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_2cta(tmem_slot, 512);
+  __shared__ float s_lut[KIND == EPI_TAIL_SHUFFLE ? 256 : 1];
+  if constexpr (KIND == EPI_TAIL_SHUFFLE) {
+    for (int i = threadIdx.x; i < 256; i += NTHREADS) {
+      const float t = (float)i * (1.0f / 255.0f);
+      s_lut[i] = P.gamma_in ? powf(t, 2.2f) : t;
+    }
+  }
   if (threadIdx.x >= 64 && threadIdx.x < 64 + 16)      // pad behind the last stage (the dx = 2 tap of the last row reads 32 B past it)
     reinterpret_cast<uint32_t*>(smem + C::NSTAGE * C::STAGE)[threadIdx.x - 64] = 0u;
   fence_proxy_async_smem();
@@ -221,6 +229,65 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_wide_kernel(const __gr
             *reinterpret_cast<uint4*>(dp + (size_t)c * plane_pitch) =
                 make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
         }
+      } else if constexpr (KIND == EPI_TAIL_SHUFFLE) {
+        // ---- 12 channels -> PixelShuffle(2) + network input + ReLU straight to the frame (model_pix_shuffle.py:293-296) ----
+        uint32_t v[16];
+        tmem_ld_x16(taddr, v);
+        tmem_ld_wait();
+        float o[12];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {          // channels 0..7 and 8..11 through the chunk-wise chain (4 padding channels ride along)
+          float t8[8];
+          const float* prm = P.dparams + h * 8;
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(prm)), b1 = __ldg(reinterpret_cast<const float4*>(prm + 4));
+          t8[0] = __uint_as_float(v[h * 8 + 0]) + b0.x; t8[1] = __uint_as_float(v[h * 8 + 1]) + b0.y;
+          t8[2] = __uint_as_float(v[h * 8 + 2]) + b0.z; t8[3] = __uint_as_float(v[h * 8 + 3]) + b0.w;
+          t8[4] = __uint_as_float(v[h * 8 + 4]) + b1.x; t8[5] = __uint_as_float(v[h * 8 + 5]) + b1.y;
+          t8[6] = __uint_as_float(v[h * 8 + 6]) + b1.z; t8[7] = __uint_as_float(v[h * 8 + 7]) + b1.w;
+          const uint32_t ops_packed = (uint32_t)P.op[0] | ((uint32_t)P.op[1] << 8) | ((uint32_t)P.op[2] << 16) | ((uint32_t)P.op[3] << 24);
+          epi_chain8<EPI>(ops_packed, prm, P.cpad, false, make_uint4(0, 0, 0, 0), t8);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (h * 8 + i < 12) o[h * 8 + i] = t8[i];
+        }
+        if (valid) {
+          const size_t fpl = (size_t)P.H * P.W;
+#pragma unroll
+          for (int dy = 0; dy < 2; ++dy) {
+            const size_t p0 = (size_t)(2 * y + dy) * P.W + 2 * x + P.xoff;
+            float idv[3][2];
+            if (P.in_fmt == FSUAE_FMT_F32_NCHW3) {
+              const float* ip = (const float*)P.frame_in + (size_t)w.f * 3 * fpl + p0;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(ip + c * fpl)); idv[c][0] = t2.x; idv[c][1] = t2.y; }
+            } else if (P.in_fmt == FSUAE_FMT_U8_NHWC4) {
+              const uint2 t2 = __ldg(reinterpret_cast<const uint2*>((const unsigned char*)P.frame_in + ((size_t)w.f * fpl + p0) * 4));
+#pragma unroll
+              for (int c = 0; c < 3; ++c) { idv[c][0] = s_lut[(t2.x >> (8 * c)) & 0xFF]; idv[c][1] = s_lut[(t2.y >> (8 * c)) & 0xFF]; }
+            } else {
+              const unsigned char* ip = (const unsigned char*)P.frame_in + (size_t)w.f * 4 * fpl + p0;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) { idv[c][0] = s_lut[__ldg(ip + c * fpl)]; idv[c][1] = s_lut[__ldg(ip + c * fpl + 1)]; }
+            }
+            float res[3][2];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+              for (int dx = 0; dx < 2; ++dx) res[c][dx] = fmaxf(o[c * 4 + dy * 2 + dx] + idv[c][dx], 0.f);
+            if (P.out_fmt == FSUAE_FMT_F32_NCHW3) {
+              float* op = (float*)P.frame_out + (size_t)w.f * 3 * fpl + p0;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) *reinterpret_cast<float2*>(op + c * fpl) = make_float2(res[c][0], res[c][1]);
+            } else {
+              uint32_t px[2];
+#pragma unroll
+              for (int dx = 0; dx < 2; ++dx)
+                px[dx] = (uint32_t)to_u8_fast(res[0][dx], P.gamma_out) | ((uint32_t)to_u8_fast(res[1][dx], P.gamma_out) << 8) |
+                         ((uint32_t)to_u8_fast(res[2][dx], P.gamma_out) << 16) | 0xFF000000u;
+              *reinterpret_cast<uint2*>((unsigned char*)P.frame_out + ((size_t)w.f * fpl + p0) * 4) = make_uint2(px[0], px[1]);
+            }
+          }
+        }
       } else {
         // ---- 3-channel full-resolution tail straight to the frame (model_conv3.py:145-153, model_conv5.py:149) ----
         float prm[9][4];
@@ -304,7 +371,7 @@ const std::vector<WideVariant>& wide_variants() {
   using RT = Epi<-1, -1, -1, -1, false>;
   static const std::vector<WideVariant> v = {
       make_wide<64, EPI_STORE, RT>(), make_wide<96, EPI_STORE, RT>(), make_wide<112, EPI_STORE, RT>(), make_wide<128, EPI_STORE, RT>(),
-      make_wide<16, EPI_TAIL_PLAIN, RT>(),
+      make_wide<16, EPI_TAIL_PLAIN, RT>(), make_wide<16, EPI_TAIL_SHUFFLE, RT>(),
       // BatchNorm-folded families (model_conv3.py:127-145, model_conv5.py:123-149): ReLU, residual + ReLU, identity / sigmoid tails
       make_wide<128, EPI_STORE, Epi<FSUAE_ACT_RELU, 0, 0, 0, false>>(), make_wide<128, EPI_STORE, Epi<0, 0, FSUAE_ACT_RELU, 0, true>>(),
       make_wide<16, EPI_TAIL_PLAIN, Epi<0, 0, 0, 0, false>>(), make_wide<16, EPI_TAIL_PLAIN, Epi<FSUAE_ACT_SIGMOID, 0, 0, 0, false>>(),

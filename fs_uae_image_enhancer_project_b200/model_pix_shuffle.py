@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import _lib as L
 from . import activations
@@ -43,9 +44,6 @@ class Model(FusedEnhancer):
                 raise ValueError("kernel_size must be odd for symmetric padding")
         if any(k != 3 for k in ks):
             raise ValueError("the fused engine implements 3x3 convolutions only (both reference presets use 3)")
-        if ch[0] != ch[1] or ch[2] != ch[3]:
-            raise ValueError("1x1 skip projections (layer1 != layer2 or layer3 != layer4 channels) are not "
-                             "implemented by the fused engine; neither reference preset uses them")
         self.channels = tuple(ch)
         cin = [12, ch[0], ch[1], ch[2], ch[3], ch[0] + ch[4], ch[5]]
         cout = ch + [12]
@@ -56,8 +54,9 @@ class Model(FusedEnhancer):
             name = kwargs.pop(f"layer{layer}_act{idx}", default)
             params = kwargs.pop(f"layer{layer}_act{idx}_params", None)
             setattr(self, f"l{layer}_act{idx}", activations.get_activation(name, params=params))
-        self.skip1_proj_conv = None
-        self.skip2_proj_conv = None
+        # 1x1 projections of the short skips when the channel counts differ (reference :126-128, :143-145; same keys)
+        self.skip1_proj_conv = nn.Conv2d(ch[0], ch[1], 1, stride=1, padding=0, bias=False) if ch[0] != ch[1] else None
+        self.skip2_proj_conv = nn.Conv2d(ch[2], ch[3], 1, stride=1, padding=0, bias=False) if ch[2] != ch[3] else None
         self.pixel_shuffle = nn.PixelShuffle(2)
         if kwargs:
             raise TypeError(f"unexpected arguments: {sorted(kwargs)}")
@@ -71,18 +70,31 @@ class Model(FusedEnhancer):
         c = lambda i: getattr(self, f"conv{i}")
         a = lambda l, k: getattr(self, f"l{l}_act{k}")
         ch = self.channels
-        # buffer ids: 0 = unshuffled input, i = output of conv i
-        return [
-            LayerSpec(c(1).weight, c(1).bias, src0=0, cin0=12, pre=[a(1, 1), a(1, 2)]),
-            LayerSpec(c(2).weight, c(2).bias, src0=1, cin0=ch[0], skip_src=1,
-                      pre=[a(2, 1), a(2, 2)], post=[a(2, 3), a(2, 4)]),
-            LayerSpec(c(3).weight, c(3).bias, src0=2, cin0=ch[1], pre=[a(3, 1), a(3, 2)]),
-            LayerSpec(c(4).weight, c(4).bias, src0=3, cin0=ch[2], skip_src=3,
-                      pre=[a(4, 1), a(4, 2)], post=[a(4, 3), a(4, 4)]),
-            LayerSpec(c(5).weight, c(5).bias, src0=4, cin0=ch[3], pre=[a(5, 1), a(5, 2)]),
-            LayerSpec(c(6).weight, c(6).bias, src0=1, cin0=ch[0], src1=5, cin1=ch[4], pre=[a(6, 1), a(6, 2)]),
-            LayerSpec(c(7).weight, c(7).bias, src0=6, cin0=ch[5], pre=[a(7, 1), a(7, 2)]),
-        ]
+        specs = []
+
+        def add(spec):       # -> buffer id of the layer's output (0 = unshuffled input, i = output of specs[i-1])
+            specs.append(spec)
+            return len(specs)
+
+        def projected(proj, src, cin):
+            """A 1x1 skip projection runs as a layer of its own: centre tap of a 3x3 kernel, no bias, no activation."""
+            if proj is None:
+                return src
+            w = F.pad(proj.weight, (1, 1, 1, 1))
+            return add(LayerSpec(w, None, src0=src, cin0=cin))
+
+        b1 = add(LayerSpec(c(1).weight, c(1).bias, src0=0, cin0=12, pre=[a(1, 1), a(1, 2)]))
+        s1 = projected(self.skip1_proj_conv, b1, ch[0])
+        b2 = add(LayerSpec(c(2).weight, c(2).bias, src0=b1, cin0=ch[0], skip_src=s1,
+                           pre=[a(2, 1), a(2, 2)], post=[a(2, 3), a(2, 4)]))
+        b3 = add(LayerSpec(c(3).weight, c(3).bias, src0=b2, cin0=ch[1], pre=[a(3, 1), a(3, 2)]))
+        s2 = projected(self.skip2_proj_conv, b3, ch[2])
+        b4 = add(LayerSpec(c(4).weight, c(4).bias, src0=b3, cin0=ch[2], skip_src=s2,
+                           pre=[a(4, 1), a(4, 2)], post=[a(4, 3), a(4, 4)]))
+        b5 = add(LayerSpec(c(5).weight, c(5).bias, src0=b4, cin0=ch[3], pre=[a(5, 1), a(5, 2)]))
+        b6 = add(LayerSpec(c(6).weight, c(6).bias, src0=b1, cin0=ch[0], src1=b5, cin1=ch[4], pre=[a(6, 1), a(6, 2)]))
+        add(LayerSpec(c(7).weight, c(7).bias, src0=b6, cin0=ch[5], pre=[a(7, 1), a(7, 2)]))
+        return specs
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """x: ``[B,3,H,W]`` float (fp32; fp16/bf16 are converted), H and W even."""

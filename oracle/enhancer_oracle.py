@@ -177,9 +177,11 @@ def pix_shuffle_forward(sd: Dict[str, torch.Tensor], spec: PixShuffleSpec, x: to
                         dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """model_pix_shuffle.py:227-298, un-fused eval forward.  x: [B,3,H,W] linear RGB."""
     c1, c2, c3, c4, _, _ = spec.channels
-    if c1 != c2 or c3 != c4:
-        raise NotImplementedError("1x1 skip projections (:126-128, :143-145) are not in any preset")
     w = lambda k: sd[k].to(dtype)
+
+    def proj(key, t, cin, cout):
+        """1x1 projection of a short skip when the channel counts differ (:126-128, :143-145, :250-251, :269-270)."""
+        return F.conv2d(t, w(key)) if cin != cout else t
 
     def act(slot, t):
         name, params = spec.acts[slot]
@@ -195,12 +197,12 @@ def pix_shuffle_forward(sd: Dict[str, torch.Tensor], spec: PixShuffleSpec, x: to
     long_skip = x                                            # :241
     short = x                                                # :244
     x = act("l2_act2", act("l2_act1", conv(2, x)))           # :245-247
-    x = short + x                                            # :252
+    x = proj("skip1_proj_conv.weight", short, c1, c2) + x    # :250-252
     x = act("l2_act4", act("l2_act3", x))                    # :254-255
     x = act("l3_act2", act("l3_act1", conv(3, x)))           # :258-260
     short = x                                                # :263
     x = act("l4_act2", act("l4_act1", conv(4, x)))           # :264-266
-    x = short + x                                            # :271
+    x = proj("skip2_proj_conv.weight", short, c3, c4) + x    # :269-271
     x = act("l4_act4", act("l4_act3", x))                    # :273-274
     x = act("l5_act2", act("l5_act1", conv(5, x)))           # :277-279
     x = torch.cat([long_skip, x], dim=1)                     # :282
@@ -321,6 +323,11 @@ def make_pix_shuffle_state_dict(spec: PixShuffleSpec, seed: int) -> Dict[str, to
                 sd[slot + suffix] = _u(rs, shape, -0.1, 0.1)
             else:
                 sd[slot + suffix] = _u(rs, shape, 0.05, 0.45)
+    c1, c2, c3, c4, _, _ = spec.channels          # drawn last: the streams of the projection-free specs stay as they were
+    if c1 != c2:
+        sd["skip1_proj_conv.weight"] = _u(rs, (c2, c1, 1, 1), -1.0 / math.sqrt(c1), 1.0 / math.sqrt(c1))
+    if c3 != c4:
+        sd["skip2_proj_conv.weight"] = _u(rs, (c4, c3, 1, 1), -1.0 / math.sqrt(c3), 1.0 / math.sqrt(c3))
     return sd
 
 

@@ -76,8 +76,38 @@ VOCAB_SPECS = {
 }
 
 
+# channel plans whose short skips need the 1x1 projections (model_pix_shuffle.py:126-128, 143-145); arbitrary widths
+PROJ_SPECS = {
+    "proj_a": O.PixShuffleSpec((24, 40, 40, 56, 20, 28)).with_acts(
+        l1_act1="sinlu", l1_act2="relu6",
+        l2_act1="telu", l2_act2="identity", l2_act3="sinlu", l2_act4=("biased_prelu", {"num_parameters": 40}),
+        l4_act1="mish", l4_act2=("biased_prelu", {"num_parameters": 56}), l4_act3="tanh", l4_act4="relu",
+        l6_act1="mish", l6_act2="relu6",
+        l7_act1="identity", l7_act2=("biased_prelu", {"num_parameters": 1})),
+}
+
+
+def gen_projection_cases(mps):
+    """Added after the first fixture set: own generator, so the files above keep their bytes."""
+    g = torch.Generator().manual_seed(4321)
+    for seed, (name, spec) in enumerate(PROJ_SPECS.items(), start=51):
+        sd = O.make_pix_shuffle_state_dict(spec, seed)
+        model = ref_pix_shuffle(mps, spec)
+        model.load_state_dict(sd, strict=True)
+        x = torch.rand((2, 3, 44, 60), generator=g) * 1.1
+        with torch.no_grad():
+            y = model(x)
+        np.savez_compressed(os.path.join(GOLD, f"pix_shuffle_{name}.npz"), seed=seed, x=x.numpy(), y=y.numpy())
+        os.chmod(os.path.join(GOLD, f"pix_shuffle_{name}.npz"), 0o644)
+        yo = O.pix_shuffle_forward(sd, spec, x)
+        print(f"pix_shuffle {name}: oracle-vs-reference max|d| = {(y - yo).abs().max().item():.3e}")
+
+
 def main():
     mps, mc3, mc5, gamma = import_reference()
+    if "--only-projections" in sys.argv:
+        gen_projection_cases(mps)
+        return
     if os.path.isdir(GOLD):
         shutil.rmtree(GOLD)
     os.makedirs(GOLD)
@@ -147,6 +177,7 @@ def main():
                     os.path.join(GOLD, "predicted_pix_shuffle"))
         shutil.copy(os.path.join(REF, f"model/model_conv3/predicted/sample{i}.png"),
                     os.path.join(GOLD, "predicted_conv3"))
+    gen_projection_cases(mps)
     for root, _, files in os.walk(GOLD):
         for f in files:
             os.chmod(os.path.join(root, f), 0o644)

@@ -145,8 +145,15 @@ def test_model_constructor_errors():
         model_pix_shuffle.Model(layer3_kernel_size=4)
     with pytest.raises(ValueError, match="odd"):
         model_conv3.Model(kernel_size=2)
-    with pytest.raises(ValueError):
-        model_pix_shuffle.Model(layer1_out_channels=24, layer2_out_channels=36)   # skip projection
+    with pytest.raises(ValueError, match="3x3"):
+        model_pix_shuffle.Model(layer2_kernel_size=5)
+    # channel plans with 1x1 skip projections: same parameter names as the reference (:126-128, :143-145), and the
+    # projection becomes a layer of its own in the engine descriptor
+    m = model_pix_shuffle.Model(layer1_out_channels=24, layer2_out_channels=36, layer3_out_channels=40, layer4_out_channels=40)
+    assert tuple(m.state_dict()["skip1_proj_conv.weight"].shape) == (36, 24, 1, 1) and m.skip2_proj_conv is None
+    specs = m._layer_specs()
+    assert len(specs) == 8 and specs[1].bias is None and specs[2].skip_src == 2 and specs[2].src0 == 1
+    assert float(specs[1].weight[:, :, 0, 0].abs().sum()) == 0.0 and specs[1].weight.shape == (36, 24, 3, 3)
     with pytest.raises(ValueError, match="Unsupported activation"):
         model_pix_shuffle.Model(layer1_act1="nonsense")
 

@@ -10,7 +10,7 @@ from oracle import enhancer_oracle as O
 from tests.util import GOLD, gold_spec, load_gold, load_png_rgb, load_png_rgba, trained_conv3_sd, trained_pix_shuffle_sd
 
 
-@pytest.mark.parametrize("name", ["lightweight", "heavyweight", "vocab_a", "vocab_b"])
+@pytest.mark.parametrize("name", ["lightweight", "heavyweight", "vocab_a", "vocab_b", "proj_a"])
 def test_pix_shuffle_matches_reference_vectors(name):
     g = load_gold(f"pix_shuffle_{name}")
     spec = gold_spec(name)

@@ -35,7 +35,7 @@ def test_native_library_is_what_runs():
     assert any("libfsuae_enhancer.so" in l for l in open("/proc/self/maps"))
 
 
-@pytest.mark.parametrize("name", ["lightweight", "heavyweight", "vocab_a", "vocab_b"])
+@pytest.mark.parametrize("name", ["lightweight", "heavyweight", "vocab_a", "vocab_b", "proj_a"])
 def test_fp32_pix_shuffle_matches_reference_vectors(name):
     g = load_gold(f"pix_shuffle_{name}")
     spec = gold_spec(name)
@@ -436,3 +436,19 @@ def test_bf16_three_rows_per_instruction_kernels(monkeypatch):
     for grid in (1, 3, 7):
         monkeypatch.setenv("FSUAE_DEBUG_GRID", str(grid))
         assert torch.equal(m(x.to(dev())).cpu(), got)
+
+
+def test_bf16_arbitrary_channel_plan_with_skip_projections():
+    """Channel plan (24, 40, 40, 56, 20, 28): both short skips go through 1x1 projections (run as centre-tap layers, the
+    residual then comes from global memory), no layer has an instantiated resident-weight kernel, so everything --
+    including the concat layer and the PixelShuffle tail -- runs on the K-streamed wide kernel."""
+    g = load_gold("pix_shuffle_proj_a")
+    spec = gold_spec("proj_a")
+    sd = O.make_pix_shuffle_state_dict(spec, int(g["seed"]))
+    m = _bf16_model(spec, sd)
+    got = m(torch.from_numpy(g["x"]).to(dev())).cpu()
+    want = torch.from_numpy(g["y"])
+    assert (got - want).abs().max().item() <= BF16_TOL and O.psnr(got, want, 1.0) >= BF16_PSNR
+    fb = O.synth_framebuffers(3, seed=12, h=70, w=300)
+    d = (m.forward_framebuffer(fb.to(dev())).cpu().int() - O.framebuffer_forward(sd, spec, fb).int()).abs()
+    assert d.max().item() <= 6 and (d == 0).float().mean().item() >= 0.85

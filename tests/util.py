@@ -17,8 +17,8 @@ def load_gold(name):
 def gold_spec(name):
     if name in ("lightweight", "heavyweight"):
         return O.pix_shuffle_preset(name)
-    from oracle.gen_golden import VOCAB_SPECS
-    return VOCAB_SPECS[name]
+    from oracle.gen_golden import PROJ_SPECS, VOCAB_SPECS
+    return VOCAB_SPECS[name] if name in VOCAB_SPECS else PROJ_SPECS[name]
 
 
 def trained_pix_shuffle_sd():
