@@ -749,10 +749,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
           tmem_ld_x16(taddr, v);
           tmem_ld_wait();
           float o[12];
+          if constexpr (EPI::kRuntime) {
+            // run-time op-codes: the chunk-wise chain (one switch per slot and 8 channels), not one switch per element
+            const uint32_t ops_packed = (uint32_t)P.op[0] | ((uint32_t)P.op[1] << 8) | ((uint32_t)P.op[2] << 16) | ((uint32_t)P.op[3] << 24);
 #pragma unroll
-          for (int ch = 0; ch < 12; ++ch) {
-            float t = EPI::pre(P, ch, __uint_as_float(v[ch]) + P.bias[ch]);
-            o[ch] = EPI::post(P, ch, t);
+            for (int h = 0; h < 2; ++h) {
+              float t8[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) t8[i] = __uint_as_float(v[h * 8 + i]) + P.bias[h * 8 + i];
+              epi_chain8<EPI>(ops_packed, P.dparams + h * 8, MAXC, false, make_uint4(0, 0, 0, 0), t8);
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (h * 8 + i < 12) o[h * 8 + i] = t8[i];
+            }
+          } else {
+#pragma unroll
+            for (int ch = 0; ch < 12; ++ch) {
+              float t = EPI::pre(P, ch, __uint_as_float(v[ch]) + P.bias[ch]);
+              o[ch] = EPI::post(P, ch, t);
+            }
           }
           if (valid) {
             const size_t fpl = (size_t)P.H * P.W;
