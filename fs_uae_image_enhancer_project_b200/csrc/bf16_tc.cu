@@ -1369,6 +1369,20 @@ const std::vector<Variant>& variants() {
       make_variant<9, 48, 36, EPI_STORE, Epi<0, 0, 0, 0, false>, 2>(0, 0, 0, 0, 0),
       make_variant<10, 48, 36, EPI_STORE, Epi<A(MISH), A(RELU6), 0, 0, false>, 2>(A(MISH), A(RELU6), 0, 0, 0),
       make_variant<5, 16, 12, EPI_TAIL_SHUFFLE, Epi<A(BIASED_PRELU), 0, 0, 0, false>, 2>(A(BIASED_PRELU), 0, 0, 0, 0),
+      // ---- pix_shuffle heavyweight = the constructor's default activations (model_pix_shuffle.py:20-68, 312-314), 108-channel middle;
+      //      its conv4 (108 -> 108) runs on the wide kernel ----
+      make_variant<2, 48, 36, EPI_STORE, Epi<A(RELU), 0, 0, 0, false>>(A(RELU), 0, 0, 0, 0),
+      make_variant<5, 48, 36, EPI_STORE, Epi<A(MISH), A(BIASED_RELU), A(TANH), A(RELU6), true>>(A(MISH), A(BIASED_RELU), A(TANH), A(RELU6), 1),
+      make_variant<5, 112, 108, EPI_STORE, Epi<0, 0, 0, 0, false>>(0, 0, 0, 0, 0),
+      make_variant<14, 48, 36, EPI_STORE, Epi<0, 0, 0, 0, false>>(0, 0, 0, 0, 0),
+      make_variant<10, 48, 36, EPI_STORE, Epi<A(MISH), A(PRELU), 0, 0, false>>(A(MISH), A(PRELU), 0, 0, 0),
+      make_variant<5, 16, 12, EPI_TAIL_SHUFFLE, Epi<A(SINLU), A(PRELU), 0, 0, false>>(A(SINLU), A(PRELU), 0, 0, 0),
+      make_variant<2, 48, 36, EPI_STORE, Epi<A(RELU), 0, 0, 0, false>, 2>(A(RELU), 0, 0, 0, 0),
+      make_variant<5, 48, 36, EPI_STORE, Epi<A(MISH), A(BIASED_RELU), A(TANH), A(RELU6), true>, 2>(A(MISH), A(BIASED_RELU), A(TANH), A(RELU6), 1),
+      make_variant<5, 112, 108, EPI_STORE, Epi<0, 0, 0, 0, false>, 2>(0, 0, 0, 0, 0),
+      make_variant<14, 48, 36, EPI_STORE, Epi<0, 0, 0, 0, false>, 2>(0, 0, 0, 0, 0),
+      make_variant<10, 48, 36, EPI_STORE, Epi<A(MISH), A(PRELU), 0, 0, false>, 2>(A(MISH), A(PRELU), 0, 0, 0),
+      make_variant<5, 16, 12, EPI_TAIL_SHUFFLE, Epi<A(SINLU), A(PRELU), 0, 0, false>, 2>(A(SINLU), A(PRELU), 0, 0, 0),
       // ---- the layers without a residual as three-output-rows-per-instruction kernels (A operand read once per input row) ----
       make_variant<2, 48, 36, EPI_STORE, Epi<A(SINLU), A(RELU6), 0, 0, false>, 1, true>(A(SINLU), A(RELU6), 0, 0, 0),
       make_variant<9, 48, 36, EPI_STORE, Epi<0, 0, 0, 0, false>, 1, true>(0, 0, 0, 0, 0),

@@ -374,6 +374,7 @@ const std::vector<WideVariant>& wide_variants() {
       make_wide<16, EPI_TAIL_PLAIN, RT>(), make_wide<16, EPI_TAIL_SHUFFLE, RT>(),
       // BatchNorm-folded families (model_conv3.py:127-145, model_conv5.py:123-149): ReLU, residual + ReLU, identity / sigmoid tails
       make_wide<128, EPI_STORE, Epi<FSUAE_ACT_RELU, 0, 0, 0, false>>(), make_wide<128, EPI_STORE, Epi<0, 0, FSUAE_ACT_RELU, 0, true>>(),
+      make_wide<112, EPI_STORE, Epi<FSUAE_ACT_TELU, FSUAE_ACT_LEAKY_RELU, FSUAE_ACT_TANH, 0, true>>(),      // pix_shuffle heavyweight conv4
       make_wide<16, EPI_TAIL_PLAIN, Epi<0, 0, 0, 0, false>>(), make_wide<16, EPI_TAIL_PLAIN, Epi<FSUAE_ACT_SIGMOID, 0, 0, 0, false>>(),
   };
   return v;
