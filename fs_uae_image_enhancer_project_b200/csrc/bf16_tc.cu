@@ -1411,6 +1411,15 @@ const std::vector<Variant>& variants() {
       make_variant<8, 16, -1, EPI_TAIL_PLAIN, Epi<0, 0, 0, 0, false>>(0, 0, 0, 0, 0),
       make_variant<8, 16, -1, EPI_TAIL_PLAIN, Epi<A(SIGMOID), 0, 0, 0, false>>(A(SIGMOID), 0, 0, 0, 0),
       make_variant<16, 16, -1, EPI_TAIL_PLAIN, Epi<A(SIGMOID), 0, 0, 0, false>>(A(SIGMOID), 0, 0, 0, 0),
+      // ... the residual layers as CTA pairs (measured: 8-13 % faster; the plain ReLU layers are bound by their full-resolution
+      //     stores, ~4.4 TB/s of HBM traffic, and lose 5-10 % as pairs, so they stay single-CTA) ...
+      make_variant<4, 32, -1, EPI_STORE, Epi<0, 0, A(RELU), 0, true>, 2>(0, 0, A(RELU), 0, 1),
+      make_variant<8, 64, -1, EPI_STORE, Epi<0, 0, A(RELU), 0, true>, 2>(0, 0, A(RELU), 0, 1),
+      // ... and the 3-channel full-resolution tails with three output rows per instruction: at N = 16 the instruction is
+      // bound by its 4 KB A read, so tripling N (48) is free and the tail needs a third of the instructions
+      make_variant<8, 16, -1, EPI_TAIL_PLAIN, Epi<0, 0, 0, 0, false>, 1, true>(0, 0, 0, 0, 0),
+      make_variant<8, 16, -1, EPI_TAIL_PLAIN, Epi<A(SIGMOID), 0, 0, 0, false>, 1, true>(A(SIGMOID), 0, 0, 0, 0),
+      make_variant<16, 16, -1, EPI_TAIL_PLAIN, Epi<A(SIGMOID), 0, 0, 0, false>, 1, true>(A(SIGMOID), 0, 0, 0, 0),
   };
   return v;
 }
@@ -1623,7 +1632,10 @@ int bf16_create(fsuae_engine* e) {
       // 3.6) -- the N = 144 instruction costs 85 cycles against 3 x 43 for the pair kernel's three N = 48 ones, but the
       // accumulator-ring wrap splits, the separate first instruction of every new row and the longer per-row scalar
       // prologue of the single issuing thread eat the difference.
-      if (var == exact && getenv("FSUAE_R3") && atoi(getenv("FSUAE_R3")) != 0) {
+      const bool matched = var == exact || var == fit_ops;      // op-codes compiled in: sibling kernels exist for the same signature
+      const bool r3_default = var->KIND == EPI_TAIL_PLAIN;      // N = 16 tails: clear win (conv3 lightweight tail 21.7 -> see profiles)
+      const char* r3_env = getenv("FSUAE_R3");
+      if (matched && (r3_env ? atoi(r3_env) != 0 : r3_default)) {
         for (const Variant& v : variants())
           if (v.R3 && v.PT == var->PT && v.NPAD == var->NPAD && v.COUT == var->COUT && v.KIND == var->KIND && v.skip == var->skip &&
               v.pre0 == var->pre0 && v.pre1 == var->pre1 && v.post0 == var->post0 && v.post1 == var->post1)
@@ -1636,7 +1648,7 @@ int bf16_create(fsuae_engine* e) {
           FSUAE_CUDA_CHECK(e, cudaFuncSetAttribute((const void*)ln.var3->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ln.var3->smem));
         }
       }
-      if (var == exact && !getenv("FSUAE_NO_PAIRS")) {
+      if (matched && !getenv("FSUAE_NO_PAIRS")) {
         for (const Variant& v : variants())
           if (v.CTAS == 2 && !v.R3 && v.PT == var->PT && v.NPAD == var->NPAD && v.COUT == var->COUT && v.KIND == var->KIND &&
               v.skip == var->skip && v.pre0 == var->pre0 && v.pre1 == var->pre1 && v.post0 == var->post0 && v.post1 == var->post1)
