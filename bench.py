@@ -84,15 +84,25 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.sm)}
 
 
-def cpu_forward_fps(n_frames: int, batch: int, repeats: int = 1):
+def seeded_model():
+    """Config 1 of SURVEY 8d: torch.manual_seed(S) before constructing get_model('lightweight') (product module, CPU)."""
+    import torch
+    from fs_uae_image_enhancer_project_b200 import model_pix_shuffle
+    torch.manual_seed(7)
+    return model_pix_shuffle.get_model("lightweight")
+
+
+def cpu_forward_fps(n_frames: int, batch: int, sd=None, frames=None, repeats: int = 1):
     """The reference's CPU eval forward (oracle port: same torch ops as model_pix_shuffle.py:227-298 +
-    the float glue of train.py:57-73) on the host cores, on a bounded sample of the workload."""
+    the float glue of train.py:57-73) on the host cores, on a bounded sample of the workload: the same weights and
+    the same synthetic frames as the GPU arm.  The only place bench.py touches oracle/."""
     import torch
     from oracle import enhancer_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     spec = O.pix_shuffle_preset("lightweight")
-    sd = O.make_pix_shuffle_state_dict(spec, 7)
-    fb = O.synth_framebuffers(n_frames, seed=100)
+    if sd is None:
+        sd = {k: v.detach().clone() for k, v in seeded_model().state_dict().items()}
+    fb = frames if frames is not None else torch.from_numpy(O.synth_rgb444_frames(n_frames, FRAME_H, FRAME_W, seed=1000))
     with torch.no_grad():
         O.framebuffer_forward(sd, spec, fb[:1])                       # warm-up
         times = []
@@ -147,8 +157,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from fs_uae_image_enhancer_project_b200 import _lib, model_pix_shuffle
-    from oracle import enhancer_oracle as O     # synthetic frames, seeded weights, cpu_baseline leg only
+    from fs_uae_image_enhancer_project_b200 import _lib, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -158,11 +167,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    spec = O.pix_shuffle_preset("lightweight")
-    sd = O.make_pix_shuffle_state_dict(spec, 7)
-    model = model_pix_shuffle.get_model("lightweight")
-    model.load_state_dict(sd)
-    model = model.to(dev)
+    model = seeded_model().to(dev)                       # random-init weights of the named architecture, seeded
     model.chunk_frames = args.chunk
     precision = args.precision
     if precision in ("auto", "bf16"):
@@ -179,8 +184,10 @@ def main():
     eng = model.engine_for(dev, FRAME_H, FRAME_W)
 
     # two rotating batches: 2 x 64 frames x (1.73 MB in + 1.73 MB out) = 443 MB > 126 MB L2
-    host = [O.synth_framebuffers(BATCH, seed=1000 + 10 * rank + i).pin_memory() for i in range(2)]
-    d_in = [h.to(dev) for h in host]
+    # synthetic RGB444 framebuffers are generated on the device (fsuae_synth_rgb444_frames: frame g uses pixel mode g & 3,
+    # i.e. 16 frames of each mode per batch); pinned host copies feed the end-to-end measurement
+    d_in = [synth.synth_rgb444_frames(BATCH, FRAME_H, FRAME_W, seed=1000 + rank, first_frame=i * BATCH, device=dev) for i in range(2)]
+    host = [t.cpu().pin_memory() for t in d_in]
     d_out = [torch.empty_like(t) for t in d_in]
     flags = _lib.FLAG_GAMMA_IN | _lib.FLAG_GAMMA_OUT
 
@@ -315,7 +322,7 @@ def main():
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            cfps, threads = cpu_forward_fps(16, 4)
+            cfps, threads = cpu_forward_fps(16, 4, sd={k: v.detach().cpu() for k, v in model.state_dict().items()}, frames=host[0][:16])
             line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": threads, "kind": "port",
                                     "sample": "16 of the 64 frames, batch 4, oracle port of the PyTorch fp32 eval forward"}
         print(json.dumps(line), flush=True)

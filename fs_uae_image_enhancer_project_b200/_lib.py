@@ -63,6 +63,9 @@ EXPORTS = {
     "fsuae_engine_submit_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                            C.c_uint32]),
     "fsuae_engine_wait_host": (C.c_int, [C.c_void_p]),
+    "fsuae_quantize_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_void_p]),
+    "fsuae_synth_rgb444_frames": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_int, C.c_void_p]),
     "fsuae_engine_device_bytes": (C.c_size_t, [C.c_void_p]),
     "fsuae_engine_last_launch_count": (C.c_int64, [C.c_void_p]),
     "fsuae_engine_variant": (C.c_char_p, [C.c_void_p]),

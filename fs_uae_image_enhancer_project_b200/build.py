@@ -12,7 +12,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libfsuae_enhancer.so")
-SOURCES = ["abi.cu", "fp32_path.cu", "bf16_tc.cu"]
+SOURCES = ["abi.cu", "fp32_path.cu", "bf16_tc.cu", "synth.cu"]
 FAST_MATH_SOURCES = {"bf16_tc.cu"}   # approximate transcendentals + flush-to-zero: bf16 build only, never the fp32 build
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -24,6 +24,10 @@
  *   fsuae_engine_submit_host / fsuae_engine_wait_host   streaming (asynchronous) form of run_host
  *                            (README.md:21-24: upload, upscale, copy back)
  *   fsuae_engine_destroy     Python GC of the module / OrtReleaseSession
+ *   fsuae_quantize_frames    dataset_generator/quantize.py:464-473, 512-521 (grid quantisation, no dithering) +
+ *                            dataset_generator/util.py:318-350 (pixel-mode replication)
+ *   fsuae_synth_rgb444_frames  the synthetic benchmark stream of SURVEY 8d (README.md:7-10 pixel modes,
+ *                            rgb444_flat_image_generator.py:28-30 expansion), generated on the device
  *   fsuae_last_error         Python exception text (ValueError at model_conv3.py:109-110,
  *                            model_pix_shuffle.py:81-83, activations.py:123-127)
  *
@@ -182,6 +186,28 @@ FSUAE_API int fsuae_engine_run_host(fsuae_engine* e, const void* in_host, void* 
 FSUAE_API int fsuae_engine_submit_host(fsuae_engine* e, const void* in_host, void* out_host, int n_frames,
                              int in_fmt, int out_fmt, uint32_t flags);
 FSUAE_API int fsuae_engine_wait_host(fsuae_engine* e);
+
+/* ---- input side: what turns an image into the framebuffer the enhancer sees (byte work, bit-exact) ---------------
+ * Colour depths of dataset_generator/quantize.py:464-473, 512-521 (dithering_method='none': floor onto the grid). */
+enum {
+  FSUAE_CS_RGB888 = 0,
+  FSUAE_CS_RGB444 = 1,
+  FSUAE_CS_RGB555 = 2,
+  FSUAE_CS_RGB565 = 3,
+  FSUAE_CS_RGB666 = 4
+};
+/* out[f][y][x] = quantise(in[f][y / sy][x / sx]), alpha = 255: grid quantisation followed by the pixel-mode
+ * replication of dataset_generator/util.py:318-350 (post_apply_resolution_style: lores sy=sx=2, lores_laced sy=1 sx=2,
+ * hires sy=2 sx=1, hires_laced 1x1; PIL NEAREST by an integer factor).  in: uint8 [n][h][w][in_channels] (3 or 4),
+ * out: uint8 RGBA [n][h*sy][w*sx][4], both on the current device.  expand17: RGB444 values become (v >> 4) * 17, the
+ * 4 -> 8 bit expansion a real framebuffer holds (rgb444_flat_image_generator.py:28-30), instead of floor(v/16)*16. */
+FSUAE_API int fsuae_quantize_frames(const void* in_dev, void* out_dev_rgba, int n_frames, int in_height, int in_width,
+                          int in_channels, int color_space, int sy, int sx, int expand17, void* cuda_stream);
+/* Synthetic RGB444 framebuffers generated on the device (SURVEY 8d workload): frame g = first_frame + i uses pixel mode
+ * g & 3 (lores, lores_laced, hires, hires_laced); every sy x sx cell holds one counter-hashed 12-bit colour
+ * (splitmix64 of seed, g, cell), stored as q * 17 (expand17) or q * 16; alpha = 255.  Deterministic in (seed, g). */
+FSUAE_API int fsuae_synth_rgb444_frames(void* out_dev_rgba, int n_frames, int height, int width, uint64_t seed,
+                              int64_t first_frame, int expand17, void* cuda_stream);
 
 /* Device bytes held by the engine (parameters + workspace + staging). */
 FSUAE_API size_t fsuae_engine_device_bytes(const fsuae_engine* e);

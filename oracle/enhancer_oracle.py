@@ -385,3 +385,73 @@ def synth_framebuffers(n: int, seed: int, h: int = FRAME_H, w: int = FRAME_W,
 def psnr(a: torch.Tensor, b: torch.Tensor, peak: float) -> float:
     mse = torch.mean((a.double() - b.double()) ** 2).item()
     return float("inf") if mse == 0 else 10.0 * math.log10(peak * peak / mse)
+
+
+# --------------------------------------------------------------------------------------
+# input side: colour-depth grid quantisation, pixel-mode replication, counter-hashed synthetic frames
+# (dataset_generator/quantize.py:464-473, 512-521; dataset_generator/util.py:318-350)
+# --------------------------------------------------------------------------------------
+
+def quantize_grid(img: np.ndarray, color_space: str) -> np.ndarray:
+    """quantize.py:512-521 with dithering_method='none', target_palette_size=None: floor onto the colour grid.
+    img: uint8 [..., 3]."""
+    t = img.astype(np.float64)
+    if color_space == "RGB444":
+        t = np.floor(t / 16) * 16
+    elif color_space == "RGB666":
+        t = np.floor(t / 4) * 4
+    elif color_space == "RGB565":
+        t = t.copy()
+        t[..., 0] = np.floor(t[..., 0] / 8) * 8
+        t[..., 1] = np.floor(t[..., 1] / 4) * 4
+        t[..., 2] = np.floor(t[..., 2] / 8) * 8
+    elif color_space == "RGB555":
+        t = np.floor(t / 8) * 8
+    elif color_space != "RGB888":
+        raise ValueError(f"Invalid color_space '{color_space}'")
+    return np.clip(t, 0, 255).astype(np.uint8)
+
+
+def post_resolution_style(img: np.ndarray, style: str) -> np.ndarray:
+    """util.py:318-350: nearest-neighbour replication back to display resolution.  img: [h, w, c]."""
+    sy, sx = PIXEL_MODES[style]
+    return np.repeat(np.repeat(img, sy, axis=0), sx, axis=1)
+
+
+def quantize_frames(img: np.ndarray, color_space: str, style: str, expand17: bool = False) -> np.ndarray:
+    """[B,h,w,3|4] uint8 -> RGBA [B,h*sy,w*sx,4]: what fsuae_quantize_frames computes."""
+    q = quantize_grid(img[..., :3], color_space)
+    if expand17 and color_space == "RGB444":
+        q = (q >> 4) * 17                                   # rgb444_flat_image_generator.py:28-30
+    out = np.stack([post_resolution_style(f, style) for f in q]) if len(q) else \
+        np.zeros((0, img.shape[1] * PIXEL_MODES[style][0], img.shape[2] * PIXEL_MODES[style][1], 3), np.uint8)
+    alpha = np.full(out.shape[:3] + (1,), 255, np.uint8)
+    return np.concatenate([out.astype(np.uint8), alpha], axis=3)
+
+
+def _mix64(z: np.ndarray) -> np.ndarray:
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+SYNTH_STYLE_OF_FRAME = ("lores", "lores_laced", "hires", "hires_laced")
+
+
+def synth_rgb444_frames(n: int, h: int, w: int, seed: int, first_frame: int = 0, expand17: bool = True) -> np.ndarray:
+    """The device-side synthetic stream (fsuae_synth_rgb444_frames): frame g = first_frame + i uses pixel mode g & 3,
+    every sy x sx cell one counter-hashed 12-bit colour."""
+    out = np.empty((n, h, w, 4), np.uint8)
+    out[..., 3] = 255
+    with np.errstate(over="ignore"):
+        for i in range(n):
+            g = np.uint64(first_frame + i)
+            sy, sx = PIXEL_MODES[SYNTH_STYLE_OF_FRAME[int(g) & 3]]
+            cy, cx = np.meshgrid(np.arange(h, dtype=np.uint64) // np.uint64(sy), np.arange(w, dtype=np.uint64) // np.uint64(sx),
+                                 indexing="ij")
+            key = _mix64(np.array(np.uint64(seed & (2 ** 64 - 1)) + np.uint64(0x9E3779B97F4A7C15) * (g + np.uint64(1))))
+            r = _mix64(key ^ (cy * np.uint64(65536) + cx))
+            for c in range(3):
+                q = ((r >> np.uint64(20 * c + 4)) & np.uint64(15)).astype(np.uint8)
+                out[i, :, :, c] = q * (17 if expand17 else 16)
+    return out

@@ -103,7 +103,34 @@ def gen_projection_cases(mps):
         print(f"pix_shuffle {name}: oracle-vs-reference max|d| = {(y - yo).abs().max().item():.3e}")
 
 
+def gen_quantize_cases():
+    """dataset_generator/quantize.py reduce_color_depth_and_dither(dithering_method='none') for every colour depth and
+    util.py post_apply_resolution_style for every style, on one seeded image (own generator: earlier fixtures keep their bytes)."""
+    from PIL import Image
+    sys.path.insert(0, os.path.join(REF, "dataset_generator"))
+    import quantize as ref_q   # noqa: E402  (numba / sklearn / PIL are present in this container)
+    import util as ref_u       # noqa: E402
+    rs = np.random.RandomState(77)
+    img = rs.randint(0, 256, (22, 36, 3)).astype(np.uint8)
+    img[0, :6] = [[0, 15, 16], [17, 31, 32], [239, 240, 255], [7, 8, 9], [3, 4, 5], [251, 252, 253]]   # grid boundaries
+    out = {"img": img}
+    for cs in ("RGB888", "RGB444", "RGB555", "RGB565", "RGB666"):
+        q = ref_q.reduce_color_depth_and_dither(img, cs, dithering_method="none", verbose=0)
+        out[f"q_{cs}"] = q
+        print(f"quantize {cs}: oracle-vs-reference equal = {np.array_equal(q, O.quantize_grid(img, cs))}")
+    q444 = out["q_RGB444"]
+    for style in ref_u.SUPPORTED_RESOLUTION_STYLES:
+        up = np.asarray(ref_u.post_apply_resolution_style(Image.fromarray(q444), style))
+        out[f"post_{style}"] = up
+        print(f"post style {style}: {up.shape}, oracle-vs-reference equal = {np.array_equal(up, O.post_resolution_style(q444, style))}")
+    np.savez_compressed(os.path.join(GOLD, "quantize.npz"), **out)
+    os.chmod(os.path.join(GOLD, "quantize.npz"), 0o644)
+
+
 def main():
+    if "--only-quantize" in sys.argv:
+        gen_quantize_cases()
+        return
     mps, mc3, mc5, gamma = import_reference()
     if "--only-projections" in sys.argv:
         gen_projection_cases(mps)
@@ -178,6 +205,7 @@ def main():
         shutil.copy(os.path.join(REF, f"model/model_conv3/predicted/sample{i}.png"),
                     os.path.join(GOLD, "predicted_conv3"))
     gen_projection_cases(mps)
+    gen_quantize_cases()
     for root, _, files in os.walk(GOLD):
         for f in files:
             os.chmod(os.path.join(root, f), 0o644)

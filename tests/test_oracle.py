@@ -93,3 +93,27 @@ def test_synth_framebuffers_are_rgb444_with_pixel_modes():
     assert (lores_laced[:, 0::2] == lores_laced[:, 1::2]).all() and not (lores_laced[0::2] == lores_laced[1::2]).all()
     assert (hires[0::2] == hires[1::2]).all() and not (hires[:, 0::2] == hires[:, 1::2]).all()
     assert not (hires_laced[0::2] == hires_laced[1::2]).all()
+
+
+def test_quantize_and_resolution_style_match_reference_vectors():
+    """oracle quantize_grid / post_resolution_style == dataset_generator/quantize.py:512-521 (dithering 'none') and
+    util.py:318-350, on the vectors gen_golden.py produced by calling the reference's own functions."""
+    g = load_gold("quantize")
+    for cs in ("RGB888", "RGB444", "RGB555", "RGB565", "RGB666"):
+        assert np.array_equal(O.quantize_grid(g["img"], cs), g[f"q_{cs}"])
+    for style in ("lores", "lores_laced", "hires", "hires_laced"):
+        assert np.array_equal(O.post_resolution_style(g["q_RGB444"], style), g[f"post_{style}"])
+    with pytest.raises(ValueError):
+        O.quantize_grid(g["img"], "RGB333")
+
+
+def test_synthetic_stream_is_rgb444_in_the_four_pixel_modes():
+    fr = O.synth_rgb444_frames(8, 16, 24, seed=5)
+    assert fr.shape == (8, 16, 24, 4) and (fr[..., 3] == 255).all() and (fr[..., :3] % 17 == 0).all()
+    for i, style in enumerate(O.SYNTH_STYLE_OF_FRAME * 2):
+        sy, sx = O.PIXEL_MODES[style]
+        cells = fr[i, ::sy, ::sx]
+        assert np.array_equal(np.repeat(np.repeat(cells, sy, 0), sx, 1), fr[i])        # sy x sx blocks
+    assert np.array_equal(O.synth_rgb444_frames(3, 16, 24, seed=5, first_frame=4), fr[4:7])   # a stream can be cut anywhere
+    assert not np.array_equal(fr[0], fr[4]) and len(np.unique(fr[3, :, :, 0])) == 16
+    assert (O.synth_rgb444_frames(1, 8, 8, seed=5, expand17=False)[..., :3] % 16 == 0).all()

@@ -452,3 +452,40 @@ def test_bf16_arbitrary_channel_plan_with_skip_projections():
     fb = O.synth_framebuffers(3, seed=12, h=70, w=300)
     d = (m.forward_framebuffer(fb.to(dev())).cpu().int() - O.framebuffer_forward(sd, spec, fb).int()).abs()
     assert d.max().item() <= 6 and (d == 0).float().mean().item() >= 0.85
+
+
+def test_quantize_and_synth_kernels_are_bit_exact():
+    """Input-side byte kernels: colour-depth grid + pixel-mode replication against the reference's own outputs
+    (tests/golden/quantize.npz) and the oracle; the device-side synthetic stream against its numpy restatement."""
+    from fs_uae_image_enhancer_project_b200 import synth
+    g = load_gold("quantize")
+    img = torch.from_numpy(g["img"])[None].to(dev())
+    for cs in ("RGB888", "RGB444", "RGB555", "RGB565", "RGB666"):
+        got = synth.quantize_frames(img, cs).cpu().numpy()
+        assert np.array_equal(got[0, :, :, :3], g[f"q_{cs}"]) and (got[..., 3] == 255).all()
+    for style in ("lores", "lores_laced", "hires", "hires_laced"):
+        got = synth.quantize_frames(img, "RGB444", style).cpu().numpy()
+        assert np.array_equal(got[0, :, :, :3], g[f"post_{style}"])
+    rs = np.random.RandomState(3)
+    batch = rs.randint(0, 256, (5, 37, 53, 4)).astype(np.uint8)                    # RGBA input, odd sizes
+    for cs, style, e17 in (("RGB444", "lores", True), ("RGB565", "hires", False), ("RGB666", "lores_laced", False)):
+        got = synth.quantize_frames(torch.from_numpy(batch).to(dev()), cs, style, expand17=e17).cpu().numpy()
+        assert np.array_equal(got, O.quantize_frames(batch, cs, style, expand17=e17))
+    assert synth.quantize_frames(torch.zeros((0, 4, 4, 3), dtype=torch.uint8, device=dev())).shape == (0, 4, 4, 4)
+    with pytest.raises(ValueError):
+        synth.quantize_frames(img, "RGB333")
+    for n, h, w, seed, first, e17 in ((9, 576, 752, 1234, 0, True), (5, 33, 47, 2 ** 63 + 11, 6, False)):
+        got = synth.synth_rgb444_frames(n, h, w, seed=seed, first_frame=first, expand17=e17, device=dev()).cpu().numpy()
+        assert np.array_equal(got, O.synth_rgb444_frames(n, h, w, seed, first, e17))
+
+
+def test_device_generated_stream_through_the_engine():
+    """Frames born on the GPU go straight into the fused forward: same bytes as the oracle gets from the same frames."""
+    from fs_uae_image_enhancer_project_b200 import synth
+    spec = O.pix_shuffle_preset("lightweight")
+    sd = O.make_pix_shuffle_state_dict(spec, 13)
+    m = build_pkg_pix_shuffle(spec, sd).to(dev())                                  # fp32 build: <= 1 LSB
+    fb = synth.synth_rgb444_frames(4, 64, 96, seed=9, device=dev())
+    want = O.framebuffer_forward(sd, spec, torch.from_numpy(O.synth_rgb444_frames(4, 64, 96, 9)))
+    got = m.forward_framebuffer(fb).cpu()
+    assert (got.int() - want.int()).abs().max().item() <= 1
