@@ -11,7 +11,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "libfsuae_enhancer.so")
+LIB_PATH = os.environ.get("FSUAE_LIB_PATH") or os.path.join(PKG_DIR, "libfsuae_enhancer.so")   # override: A/B builds side by side
 SOURCES = ["abi.cu", "fp32_path.cu", "bf16_tc.cu", "synth.cu"]
 FAST_MATH_SOURCES = {"bf16_tc.cu"}   # approximate transcendentals + flush-to-zero: bf16 build only, never the fp32 build
 NVCC_FLAGS = [

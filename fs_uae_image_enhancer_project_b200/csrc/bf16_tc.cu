@@ -49,6 +49,10 @@ constexpr int NTHREADS = 64 + 128 * EPI_WG;
 
 enum { EPI_STORE = 0, EPI_TAIL_SHUFFLE = 1, EPI_TAIL_PLAIN = 2 };
 
+#ifndef FSUAE_ROW_MAJOR
+#define FSUAE_ROW_MAJOR 1      // 1: input-row-major MMA order with A-collector reuse; 0: the older block-major order (A/B builds)
+#endif
+
 #ifdef FSUAE_EPI_TIMING
 __device__ unsigned long long g_epi_timing[8];
 __device__ __forceinline__ long long clk() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory"); return t; }
@@ -76,7 +80,7 @@ struct LayerK {
   int in_fmt, out_fmt, H, W, xoff, gamma_in, gamma_out;
   // epilogue parameters, expanded per channel on the host
   int n_pre, n_post;
-  int dbg;                 // debugging aid (FSUAE_DBG): 1 = epilogue skips its global stores, 2 = producer re-reads the segment's first row
+  int dbg;                 // debugging aid (FSUAE_DBG): 1 = epilogue skips its global stores, 2 = producer re-reads the segment's first row, 4 = one TMA per row, 8 = no MMAs
   int op[4];               // pre0, pre1, post0, post1 (identity-padded)
   float bias[MAXC];
   float p0[4][MAXC];
@@ -507,6 +511,62 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
             }
             commit(&empty[rs]);                                              // this input row is not needed again
             if (k >= 2) commit(&tfull[s_done]);                               // output row k-2 is complete
+          }
+          blk0 += (uint32_t)rows;
+        }
+      } else if constexpr (FSUAE_ROW_MAJOR != 0 && PT > 0) {      // (PT > 0 keeps the condition value-dependent: the front end mis-parses a non-dependent one here)
+        // ---- input-row-major issue order with A-collector reuse ----
+        // Input row k of a segment feeds output rows j = k-2 (kernel row 2), k-1 (row 1), k (row 0).  For every step the
+        // three MMAs share the A tile (fill / use / lastuse), so it is read from shared memory once instead of three
+        // times -- the A read is what bounds narrow-N UMMA.  Each output row keeps its own accumulator stage
+        // (block n = blk0 + j in stage n % STAGES): no contiguity constraint, accumulate flags per instruction.
+        constexpr uint32_t BSTEP = (C::NB * 32) >> 4;
+        uint32_t blk0 = 0;
+        while (it.next(P, sg)) {
+          const int rows = sg.rows;
+          uint32_t sk = blk0 % C::STAGES, pk = ((blk0 / C::STAGES) & 1u) ^ 1u;   // stage / tempty parity of block blk0 + k
+          for (int k = 0; k < rows + 2; ++k) {
+            wait_row(wslot, wpar);
+            const uint32_t rs = wslot;
+            if (++wslot == C::RING) { wslot = 0; wpar ^= 1; }
+            const bool v0 = k <= rows - 1, v1 = k >= 1 && k <= rows, v2 = k >= 2;
+            if (v0) mbar_wait(&tempty[sk], pk);
+            tc_fence_after();
+            const uint32_t s1 = sk >= 1u ? sk - 1u : sk + C::STAGES - 1u, s2 = sk >= 2u ? sk - 2u : sk + C::STAGES - 2u;
+            const uint32_t d0 = tmem_base + sk * NPAD, d1 = tmem_base + s1 * NPAD, d2 = tmem_base + s2 * NPAD;
+            const uint32_t a_row = ring_lo + rs * (C::ROWBYTES >> 4);
+            const uint64_t hi = (uint64_t)HI << 32;
+            if (P.dbg & 8) {
+              // timing experiment: no MMAs at all (garbage results): what the barrier / commit chain alone costs
+            } else if (v0 && v1 && v2) {
+#pragma unroll
+              for (int st = 0; st < C::STEPS_ROW; ++st) {
+                const int u0 = (2 * st + 1 < 3 * PT) ? 2 * st : 3 * PT - 2;      // odd tail: units 3 PT - 2 (zero weights), 3 PT - 1
+                const int pl = u0 / 3, dx = u0 - 3 * pl;
+                const uint32_t lbo = dx == 2 ? (uint32_t)((PLANE_ROW >> 4) - 2) : 1u;
+                const uint64_t a_desc = hi | ((a_row + (uint32_t)(pl * (PLANE_ROW >> 4) + dx)) | (lbo << 16));
+                const uint32_t b_st = w_lo + (uint32_t)st * BSTEP;
+                umma_bf16_coll<CTAS, 1>(d2, a_desc, hi | (b_st + 2u * C::STEPS_ROW * BSTEP), IDESC, 1u);
+                umma_bf16_coll<CTAS, 2>(d1, a_desc, hi | (b_st + 1u * C::STEPS_ROW * BSTEP), IDESC, 1u);
+                umma_bf16_coll<CTAS, 3>(d0, a_desc, hi | b_st, IDESC, st == 0 ? 0u : 1u);
+              }
+            } else {
+              // the first and last two input rows of a segment feed fewer than three output rows
+#pragma unroll
+              for (int st = 0; st < C::STEPS_ROW; ++st) {
+                const int u0 = (2 * st + 1 < 3 * PT) ? 2 * st : 3 * PT - 2;
+                const int pl = u0 / 3, dx = u0 - 3 * pl;
+                const uint32_t lbo = dx == 2 ? (uint32_t)((PLANE_ROW >> 4) - 2) : 1u;
+                const uint64_t a_desc = hi | ((a_row + (uint32_t)(pl * (PLANE_ROW >> 4) + dx)) | (lbo << 16));
+                const uint32_t b_st = w_lo + (uint32_t)st * BSTEP;
+                if (v2) mma(d2, a_desc, hi | (b_st + 2u * C::STEPS_ROW * BSTEP), IDESC, 1u);
+                if (v1) mma(d1, a_desc, hi | (b_st + 1u * C::STEPS_ROW * BSTEP), IDESC, 1u);
+                if (v0) mma(d0, a_desc, hi | b_st, IDESC, st == 0 ? 0u : 1u);
+              }
+            }
+            commit(&empty[rs]);                    // the MMAs are done with this input row
+            if (v2) commit(&tfull[s2]);            // output row k-2 is complete
+            if (++sk == C::STAGES) { sk = 0; pk ^= 1u; }
           }
           blk0 += (uint32_t)rows;
         }

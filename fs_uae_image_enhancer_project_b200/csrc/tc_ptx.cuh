@@ -96,6 +96,28 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The same with an A-operand collector hint: consecutive MMAs that share one A tile (the three kernel rows of a 3x3
+// convolution: one input row, three accumulators, three weight blocks) read it from shared memory once.
+//   COLL: 1 = fill (read A, keep it), 2 = use (re-use, keep), 3 = lastuse (re-use, release).  SASS: UTCHMMA .A_KEEP / .A_REUSE.
+// tools/umma_probe.cu: N = 16 / 48 / 80 cost 32 / 46 / 62 cycles per instruction in such triples against 51 / 59 / 72 plain.
+template <int CTAS, int COLL>
+__device__ __forceinline__ void umma_bf16_coll(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+#define FSUAE_MMA_ASM(GROUP, HINT)                                                                                  \
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                                                  \
+               "tcgen05.mma.cta_group::" GROUP ".kind::f16.collector::a::" HINT " [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), \
+               "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)                                                \
+               : "memory")
+  if constexpr (CTAS == 2) {
+    if constexpr (COLL == 1) FSUAE_MMA_ASM("2", "fill");
+    else if constexpr (COLL == 2) FSUAE_MMA_ASM("2", "use");
+    else FSUAE_MMA_ASM("2", "lastuse");
+  } else {
+    if constexpr (COLL == 1) FSUAE_MMA_ASM("1", "fill");
+    else if constexpr (COLL == 2) FSUAE_MMA_ASM("1", "use");
+    else FSUAE_MMA_ASM("1", "lastuse");
+  }
+#undef FSUAE_MMA_ASM
+}
 // all previously issued MMAs of this thread arrive on `bar` when they complete
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -116,6 +138,42 @@ __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&v)[8]) {
                : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- wide TMEM loads: NCOL consecutive columns issued back to back, ONE wait afterwards (a tcgen05.ld + wait round trip is
+// ~230 cycles: chunk-by-chunk read-back serialises that latency once per 8 columns) ----
+template <int NV>
+__device__ __forceinline__ void tmem_ld_n8(uint32_t taddr, uint32_t (&v)[NV], int o) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7])
+               : "r"(taddr));
+}
+template <int NV>
+__device__ __forceinline__ void tmem_ld_n16(uint32_t taddr, uint32_t (&v)[NV], int o) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7]), "=r"(v[o + 8]), "=r"(v[o + 9]), "=r"(v[o + 10]), "=r"(v[o + 11]), "=r"(v[o + 12]), "=r"(v[o + 13]), "=r"(v[o + 14]), "=r"(v[o + 15])
+               : "r"(taddr));
+}
+template <int NV>
+__device__ __forceinline__ void tmem_ld_n32(uint32_t taddr, uint32_t (&v)[NV], int o) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+               : "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7]), "=r"(v[o + 8]), "=r"(v[o + 9]), "=r"(v[o + 10]), "=r"(v[o + 11]), "=r"(v[o + 12]), "=r"(v[o + 13]), "=r"(v[o + 14]), "=r"(v[o + 15]), "=r"(v[o + 16]), "=r"(v[o + 17]), "=r"(v[o + 18]), "=r"(v[o + 19]), "=r"(v[o + 20]), "=r"(v[o + 21]), "=r"(v[o + 22]), "=r"(v[o + 23]), "=r"(v[o + 24]), "=r"(v[o + 25]), "=r"(v[o + 26]), "=r"(v[o + 27]), "=r"(v[o + 28]), "=r"(v[o + 29]), "=r"(v[o + 30]), "=r"(v[o + 31])
+               : "r"(taddr));
+}
+template <int NV>
+__device__ __forceinline__ void tmem_ld_n64(uint32_t taddr, uint32_t (&v)[NV], int o) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+               : "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7]), "=r"(v[o + 8]), "=r"(v[o + 9]), "=r"(v[o + 10]), "=r"(v[o + 11]), "=r"(v[o + 12]), "=r"(v[o + 13]), "=r"(v[o + 14]), "=r"(v[o + 15]), "=r"(v[o + 16]), "=r"(v[o + 17]), "=r"(v[o + 18]), "=r"(v[o + 19]), "=r"(v[o + 20]), "=r"(v[o + 21]), "=r"(v[o + 22]), "=r"(v[o + 23]), "=r"(v[o + 24]), "=r"(v[o + 25]), "=r"(v[o + 26]), "=r"(v[o + 27]), "=r"(v[o + 28]), "=r"(v[o + 29]), "=r"(v[o + 30]), "=r"(v[o + 31]), "=r"(v[o + 32]), "=r"(v[o + 33]), "=r"(v[o + 34]), "=r"(v[o + 35]), "=r"(v[o + 36]), "=r"(v[o + 37]), "=r"(v[o + 38]), "=r"(v[o + 39]), "=r"(v[o + 40]), "=r"(v[o + 41]), "=r"(v[o + 42]), "=r"(v[o + 43]), "=r"(v[o + 44]), "=r"(v[o + 45]), "=r"(v[o + 46]), "=r"(v[o + 47]), "=r"(v[o + 48]), "=r"(v[o + 49]), "=r"(v[o + 50]), "=r"(v[o + 51]), "=r"(v[o + 52]), "=r"(v[o + 53]), "=r"(v[o + 54]), "=r"(v[o + 55]), "=r"(v[o + 56]), "=r"(v[o + 57]), "=r"(v[o + 58]), "=r"(v[o + 59]), "=r"(v[o + 60]), "=r"(v[o + 61]), "=r"(v[o + 62]), "=r"(v[o + 63])
+               : "r"(taddr));
+}
+template <int NCOL>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[NCOL]) {     // no wait inside
+  static_assert(NCOL % 8 == 0 && NCOL <= 128, "column count");
+  int o = 0;
+  if constexpr (NCOL >= 64) { tmem_ld_n64(taddr, v, 0); o = 64; }
+  if constexpr ((NCOL % 64) >= 32) { tmem_ld_n32(taddr + o, v, o); o += 32; }
+  if constexpr ((NCOL % 32) >= 16) { tmem_ld_n16(taddr + o, v, o); o += 16; }
+  if constexpr ((NCOL % 16) >= 8) { tmem_ld_n8(taddr + o, v, o); }
+}
 
 // ---- CTA pairs (cta_group::2): one MMA spans two SMs, each provides its own A rows and half of B ----------
 __device__ __forceinline__ uint32_t cluster_ctarank() {

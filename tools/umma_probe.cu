@@ -93,6 +93,78 @@ __global__ void probe_rate(int N, int iters, uint32_t a_step16, uint32_t b_step1
   if (threadIdx.x < 32) tmem_dealloc(tb, 512);
 }
 
+// ---------------- test 3: A-operand collector reuse ----------------
+// Triples of MMAs share one A tile (the three kernel rows of a 3x3 convolution: same input row, three accumulators, three
+// weight blocks): .collector::a::fill / ::use / ::lastuse keep A in the collector buffer, so only the first reads it from smem.
+__device__ __forceinline__ void umma_bf16_coll(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, int which, uint32_t acc) {
+  if (which == 0)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+  else if (which == 1)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16.collector::a::use [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__global__ void probe_reuse(int N, int iters, int reuse, long long* cycles, float* dout) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) ((uint32_t*)smem)[i] = 0x3c003c00u + (uint32_t)((i * 2654435761u) >> 28) * 0x00100010u;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (threadIdx.x < 32) tmem_alloc(&tmem_base, 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tb = tmem_base;
+  const int warp_idx = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  if (warp_idx == 0 && elect_one()) {
+    const uint32_t idesc = umma_idesc_bf16(128, N);
+    const uint64_t ad0 = umma_desc(smem_u32(smem), 16 * 1024, 128);
+    const uint64_t bd0 = umma_desc(smem_u32(smem) + 128 * 1024, N * 16, 128);
+    const uint32_t a_hi = (uint32_t)(ad0 >> 32), b_hi = (uint32_t)(bd0 >> 32);
+    const uint32_t a_lo0 = (uint32_t)ad0, b_lo0 = (uint32_t)bd0;
+    const uint32_t bstep = (uint32_t)(N * 32) >> 4;
+    long long t0 = clock64();
+    uint32_t phase = 0;
+    for (int it = 0; it < iters; ++it) {
+      uint32_t a_lo = a_lo0;
+#pragma unroll
+      for (int j = 0; j < 21; ++j) {          // 21 triples = 63 MMAs
+        const uint64_t a = ((uint64_t)a_hi << 32) | a_lo;
+        const uint32_t acc = j > 0 ? 1u : 0u;     // every iteration starts its three accumulators afresh
+        if (reuse) {
+          umma_bf16_coll(tb + 0 * 128, a, ((uint64_t)b_hi << 32) | (b_lo0 + 0 * bstep), idesc, 0, acc);
+          umma_bf16_coll(tb + 1 * 128, a, ((uint64_t)b_hi << 32) | (b_lo0 + 1 * bstep), idesc, 1, acc);
+          umma_bf16_coll(tb + 2 * 128, a, ((uint64_t)b_hi << 32) | (b_lo0 + 2 * bstep), idesc, 2, acc);
+        } else {
+          umma_bf16(tb + 0 * 128, a, ((uint64_t)b_hi << 32) | (b_lo0 + 0 * bstep), idesc, acc);
+          umma_bf16(tb + 1 * 128, a, ((uint64_t)b_hi << 32) | (b_lo0 + 1 * bstep), idesc, acc);
+          umma_bf16(tb + 2 * 128, a, ((uint64_t)b_hi << 32) | (b_lo0 + 2 * bstep), idesc, acc);
+        }
+        a_lo += 65;
+      }
+      umma_commit(&bar);
+      mbar_wait(&bar, phase);
+      phase ^= 1;
+    }
+    long long t1 = clock64();
+    cycles[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  // read one accumulator back so both variants can be compared for equality (lane = row, first 8 columns of accumulator 1)
+  if (threadIdx.x < 128 && dout) {
+    uint32_t v[8];
+    tc_fence_after();
+    tmem_ld_x8(tb + ((uint32_t)(threadIdx.x & ~31u) << 16) + 128, v);
+    tmem_ld_wait();
+    for (int i = 0; i < 8; ++i) dout[(blockIdx.x * 128 + threadIdx.x) * 8 + i] = __uint_as_float(v[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tb, 512);
+}
+
 static float bf(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
 static bool run_correct(int N, int row_off, int lbo_rows_extra, const char* name) {
@@ -162,6 +234,28 @@ int main() {
         long long mx = 0; for (auto v : h) mx = v > mx ? v : mx;
         printf("rate grid=%3d N=%3d mode=%d: %.1f cycles/MMA (ideal N/2 = %d; A-read bound 32)\n", grid, N, mode,
                (double)mx / (iters * 64), N / 2);
+      }
+    }
+  }
+  // A-operand collector reuse: triples of MMAs on one A tile
+  {
+    CK(cudaFuncSetAttribute(probe_reuse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    float* dd; CK(cudaMalloc(&dd, (size_t)sms * 128 * 8 * 4));
+    for (int N : {16, 48, 80, 128}) {
+      std::vector<float> ref;
+      for (int reuse = 0; reuse < 2; ++reuse) {
+        CK(cudaMemset(dd, 0, (size_t)sms * 128 * 8 * 4));
+        probe_reuse<<<sms, 128, smem>>>(N, 50, reuse, dcy, dd);
+        CK(cudaDeviceSynchronize());
+        std::vector<long long> h(sms);
+        CK(cudaMemcpy(h.data(), dcy, sms * 8, cudaMemcpyDeviceToHost));
+        std::vector<float> out((size_t)sms * 128 * 8);
+        CK(cudaMemcpy(out.data(), dd, out.size() * 4, cudaMemcpyDeviceToHost));
+        long long mx = 0; for (auto v : h) mx = v > mx ? v : mx;
+        bool same = true;
+        if (reuse == 0) ref = out; else for (size_t i = 0; i < out.size(); ++i) same &= (out[i] == ref[i]);
+        printf("collector N=%3d %s: %.1f cycles/MMA%s (sample acc %.1f)\n", N, reuse ? "fill/use/lastuse" : "plain           ",
+               (double)mx / (50 * 63), reuse ? (same ? "  results identical" : "  RESULTS DIFFER") : "", out[5]);
       }
     }
   }
