@@ -80,6 +80,7 @@ struct LayerK {
   int in_fmt, out_fmt, H, W, xoff, gamma_in, gamma_out;
   // epilogue parameters, expanded per channel on the host
   int n_pre, n_post;
+  int softmax_slot, softmax_log;   // run-time epilogue: slot (0..3) of a channel softmax / log_softmax, -1: none
   int dbg;                 // debugging aid (FSUAE_DBG): 1 = epilogue skips its global stores, 2 = producer re-reads the segment's first row, 4 = one TMA per row, 8 = no MMAs
   int op[4];               // pre0, pre1, post0, post1 (identity-padded)
   float bias[MAXC];
@@ -219,9 +220,9 @@ constexpr uint32_t ACT_PARAM_MASK = (1u << FSUAE_ACT_ELU) | (1u << FSUAE_ACT_SOF
                                     (1u << FSUAE_ACT_PRELU) | (1u << FSUAE_ACT_SINLU) | (1u << FSUAE_ACT_BIASED_RELU) |
                                     (1u << FSUAE_ACT_BIASED_PRELU);
 __device__ __forceinline__ void act_chain_rt(uint32_t ops, const float* __restrict__ prm, int stride, bool has_skip,
-                                             const uint4& skc, float (&o)[8]) {
+                                             const uint4& skc, float (&o)[8], int s_begin = 0, int s_end = 4) {
 #pragma unroll 1
-  for (int s = 0; s < 4; ++s) {
+  for (int s = s_begin; s < s_end; ++s) {
     if (s == 2 && has_skip) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -285,6 +286,54 @@ __device__ __forceinline__ void epi_chain8(uint32_t ops, const float* __restrict
     }
     act_slot8<EPI::kOp2>(2, prm, stride, o);
     act_slot8<EPI::kOp3>(3, prm, stride, o);
+  }
+}
+
+// Channel softmax / log_softmax slot (activations.py:91-92, dim=1) in a run-time chain.  Thread = pixel, so the
+// reduction over channels is thread-local, but it spans every 8-channel chunk of the accumulator row: the row is read
+// back three times (running max of the values entering the slot; sum of exponentials; normalise + rest of the chain +
+// store), recomputing the cheap part of the chain each time.  `emit(c, o)` stores chunk c.
+struct SoftmaxCfg { int slot, log_form; };
+template <class LoadSkip, class Emit>
+__device__ __forceinline__ void softmax_row_rt(uint32_t taddr, int nplanes, int cout, uint32_t ops, const float* __restrict__ prm0,
+                                               int stride, bool has_skip, SoftmaxCfg sm, LoadSkip load_skip, Emit emit) {
+  float mx = -3.0e38f, sum = 0.f;
+  for (int pass = 0; pass < 3; ++pass) {
+    for (int c = 0; c < nplanes; ++c) {
+      const float* prm = prm0 + c * 8;
+      const uint4 skc = load_skip(c);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(prm)), b1 = __ldg(reinterpret_cast<const float4*>(prm + 4));
+      uint32_t v[8];
+      tmem_ld_x8(taddr + c * 8, v);
+      tmem_ld_wait();
+      float o[8];
+      o[0] = __uint_as_float(v[0]) + b0.x; o[1] = __uint_as_float(v[1]) + b0.y; o[2] = __uint_as_float(v[2]) + b0.z;
+      o[3] = __uint_as_float(v[3]) + b0.w; o[4] = __uint_as_float(v[4]) + b1.x; o[5] = __uint_as_float(v[5]) + b1.y;
+      o[6] = __uint_as_float(v[6]) + b1.z; o[7] = __uint_as_float(v[7]) + b1.w;
+      act_chain_rt(ops, prm, stride, has_skip, skc, o, 0, sm.slot);      // the residual is added on the way past slot 2 ...
+      if (sm.slot == 2 && has_skip) {                                    // ... or here, when the softmax is the first slot behind it
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t w = (&skc.x)[i >> 1];
+          o[i] += (i & 1) ? bf16_hi(w) : bf16_lo(w);
+        }
+      }
+      if (pass == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (c * 8 + i < cout) mx = fmaxf(mx, o[i]);
+      } else if (pass == 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (c * 8 + i < cout) sum += __expf(o[i] - mx);
+      } else {
+        const float inv = 1.0f / sum, lse = __logf(sum);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = sm.log_form ? (o[i] - mx) - lse : __expf(o[i] - mx) * inv;
+        act_chain_rt(ops, prm, stride, has_skip && sm.slot < 2, skc, o, sm.slot + 1, 4);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = (c * 8 + i < cout) ? o[i] : 0.f;
+        emit(c, o);
+      }
+    }
   }
 }
 
@@ -743,6 +792,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
           // run-time channel would make the compiler spill the whole 4.7 KB parameter block to local memory.
           unsigned char* dp = P.dst + (size_t)f * P.fs_dst + pix + (size_t)P.dst_plane0 * plane_pitch;
           const uint32_t ops_packed = (uint32_t)P.op[0] | ((uint32_t)P.op[1] << 8) | ((uint32_t)P.op[2] << 16) | ((uint32_t)P.op[3] << 24);
+          if (P.softmax_slot >= 0) {
+            auto load_skip = [&](int c) {
+              uint4 t = make_uint4(0, 0, 0, 0);
+              if constexpr (EPI::kSkip) {
+                if (valid) t = *reinterpret_cast<const uint4*>(sp + c * PLANE_ROW);
+              } else if (P.skip != nullptr) {
+                if (valid) t = __ldg(reinterpret_cast<const uint4*>(P.skip + (size_t)f * P.fs_skip + pix + (size_t)(P.skip_plane0 + c) * plane_pitch));
+              }
+              return t;
+            };
+            auto emit = [&](int c, const float (&o)[8]) {
+              if (valid)
+                *reinterpret_cast<uint4*>(dp + (size_t)c * plane_pitch) =
+                    make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+            };
+            softmax_row_rt(taddr, P.out_planes, P.cout, ops_packed, P.dparams, MAXC, EPI::kSkip || P.skip != nullptr,
+                           SoftmaxCfg{P.softmax_slot, P.softmax_log}, load_skip, emit);
+          } else
           for (int c = 0; c < P.out_planes; ++c) {
             uint4 skc = make_uint4(0, 0, 0, 0);
             if constexpr (EPI::kSkip) {
@@ -1554,13 +1621,19 @@ int bf16_create(fsuae_engine* e) {
     const std::string tag = "bf16 build: layer " + std::to_string(i + 1) + ": ";
     const int P0 = planes_of(L.cin0), P1 = L.cin1 > 0 ? planes_of(L.cin1) : 0, PT = P0 + P1;
     int ops[4] = {0, 0, 0, 0};
-    for (int k = 0; k < L.n_pre + L.n_post; ++k) {
-      const fsuae_act_desc& a = k < L.n_pre ? L.pre[k] : L.post[k - L.n_pre];
-      if (act_is_softmax(a.op)) return set_error(e, FSUAE_ERR_UNSUPPORTED, tag + "channel softmax slots are not implemented (use the fp32 build)");
-    }
     if (L.n_pre > 2 || L.n_post > 2) return set_error(e, FSUAE_ERR_UNSUPPORTED, tag + "at most 2 activation slots before and after the skip add");
     for (int k = 0; k < L.n_pre; ++k) ops[k] = L.pre[k].op;
     for (int k = 0; k < L.n_post; ++k) ops[2 + k] = L.post[k].op;
+    // a channel softmax / log_softmax slot: handled by the run-time store epilogue (three passes over the accumulator row)
+    int softmax_slot = -1, softmax_log = 0;
+    for (int k = 0; k < 4; ++k)
+      if (act_is_softmax(ops[k])) {
+        if (softmax_slot >= 0 || last)
+          return set_error(e, FSUAE_ERR_UNSUPPORTED, tag + "more than one channel softmax slot, or one in the last layer, is not implemented on the bf16 build (use the fp32 build)");
+        softmax_slot = k;
+        softmax_log = ops[k] == FSUAE_ACT_LOG_SOFTMAX;
+        ops[k] = FSUAE_ACT_IDENTITY;
+      }
     const int kind = !last ? EPI_STORE : (d.tail == FSUAE_TAIL_SHUFFLE2_RESIDUAL_RELU ? EPI_TAIL_SHUFFLE : EPI_TAIL_PLAIN);
     // The residual is normally the layer's own input and is then read from the centre row of the shared-memory ring;
     // a residual from another buffer (the 1x1 skip projections of model_pix_shuffle.py:126-128, 143-145) is read from
@@ -1590,7 +1663,8 @@ int bf16_create(fsuae_engine* e) {
         if (!widest || v.NPAD > widest->NPAD) widest = &v;
       }
     }
-    if (global_skip) exact = fit_ops = widest_ops = nullptr;      // only the run-time epilogue knows about a residual in global memory
+    if (global_skip || softmax_slot >= 0) exact = fit_ops = widest_ops = nullptr;   // only the run-time epilogue knows about a residual in global memory / a softmax slot
+    if (softmax_slot >= 0 && fit == nullptr && widest != nullptr) widest = nullptr;      // the softmax needs every channel in one launch: wide kernel, one group
     const Variant* var = exact ? exact : fit_ops ? fit_ops : fit ? fit : widest_ops ? widest_ops : widest;
     // Layers whose weights / full-depth input rows do not fit beside each other in shared memory stream K through the
     // wide tile kernel (thin-input layers are cheap to split over output-channel groups instead).
@@ -1599,9 +1673,11 @@ int bf16_create(fsuae_engine* e) {
                           ((too_wide && (PT >= 4 || !var)) || (getenv("FSUAE_FORCE_WIDE") != nullptr));
     if (use_wide) {
       const int ngroups = kind == EPI_STORE ? (need + 127) / 128 : 1;
+      if (softmax_slot >= 0 && ngroups > 1)
+        return set_error(e, FSUAE_ERR_UNSUPPORTED, tag + "channel softmax over more than 128 channels is not implemented on the bf16 build");
       const int per = ((need + ngroups - 1) / ngroups + 15) / 16 * 16;
       const WideVariant* wv = nullptr;
-      for (int pass = 0; pass < 2 && !wv; ++pass)      // first a variant with this layer's op-codes compiled in, then the run-time one
+      for (int pass = softmax_slot >= 0 ? 1 : 0; pass < 2 && !wv; ++pass)      // first a variant with this layer's op-codes compiled in, then the run-time one
         for (const WideVariant& v : wide_variants()) {
           const bool ops_eq = v.pre0 == ops[0] && v.pre1 == ops[1] && v.post0 == ops[2] && v.post1 == ops[3] && v.skip == any_skip;
           if (v.KIND != kind || v.NT < per || (pass == 0 ? !ops_eq : v.pre0 != -1)) continue;
@@ -1619,6 +1695,7 @@ int bf16_create(fsuae_engine* e) {
       k.P0 = P0; k.pin = PT; k.kchunks = (PT + 1) / 2;
       k.ngroups = ngroups; k.cout = L.cout; k.cpad = ngroups * wv->NT;
       k.has_skip = any_skip;
+      k.softmax_slot = softmax_slot; k.softmax_log = softmax_log;
       k.wpack = ln.d_w;
       std::vector<float> hp((size_t)9 * k.cpad, 0.f);
       for (int c = 0; c < k.cpad; ++c) {
@@ -1665,6 +1742,7 @@ int bf16_create(fsuae_engine* e) {
       k.tail = d.tail;
       k.wpack = ln.d_w;
       k.n_pre = L.n_pre; k.n_post = L.n_post;
+      k.softmax_slot = softmax_slot; k.softmax_log = softmax_log;
       for (int c = 0; c < MAXC; ++c) k.bias[c] = (c < cg && L.b_off >= 0) ? e->h_blob[L.b_off + c0 + c] : 0.f;
       for (int s = 0; s < 4; ++s) {
         k.op[s] = ops[s];

@@ -23,6 +23,7 @@ struct WideK {
   int ngroups, cout, cpad;       // output-channel groups of NT, channels of the layer, stride of the dparams rows
   int rowblocks, n_units;        // 8-row blocks per strip; n_frames * S * rowblocks * ngroups
   int has_skip;
+  int softmax_slot, softmax_log;   // channel softmax slot of the run-time chain (-1: none); needs ngroups == 1
   unsigned long long fs0, fs1, fs_skip, fs_dst;
   const unsigned char* src0;
   const unsigned char* src1;
@@ -208,6 +209,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_wide_kernel(const __gr
         const bool has_skip = EPI::kRuntime ? P.has_skip != 0 : EPI::kSkip;
         const unsigned char* sp = has_skip ? P.skip + (size_t)w.f * P.fs_skip + pix + (size_t)plane0 * plane_pitch : nullptr;
         const uint32_t ops_packed = (uint32_t)P.op[0] | ((uint32_t)P.op[1] << 8) | ((uint32_t)P.op[2] << 16) | ((uint32_t)P.op[3] << 24);
+        if (EPI::kRuntime && P.softmax_slot >= 0) {
+          auto load_skip = [&](int c) {
+            return (has_skip && valid) ? __ldg(reinterpret_cast<const uint4*>(sp + (size_t)c * plane_pitch)) : make_uint4(0, 0, 0, 0);
+          };
+          auto emit = [&](int c, const float (&o)[8]) {
+            if (valid)
+              *reinterpret_cast<uint4*>(dp + (size_t)c * plane_pitch) =
+                  make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+          };
+          softmax_row_rt(taddr, nplanes, P.cout, ops_packed, P.dparams + ch0, P.cpad, has_skip, SoftmaxCfg{P.softmax_slot, P.softmax_log},
+                         load_skip, emit);
+        } else
         for (int c = 0; c < nplanes; ++c) {
           uint4 skc = make_uint4(0, 0, 0, 0);
           if (has_skip && valid) skc = __ldg(reinterpret_cast<const uint4*>(sp + (size_t)c * plane_pitch));

@@ -254,13 +254,30 @@ def test_bf16_full_size_float_and_batch_properties():
 
 
 def test_bf16_unsupported_network_fails_loudly():
-    """A channel-softmax slot has no tensor-core epilogue: explicit error, no fallback."""
+    """A channel softmax in the last layer (it would have to run inside the PixelShuffle tail) is not implemented on
+    the bf16 build: explicit error, no fallback."""
     from fs_uae_image_enhancer_project_b200 import _lib
-    spec = gold_spec("vocab_b")                                   # channel softmax slot
+    spec = O.pix_shuffle_preset("lightweight").with_acts(l7_act1="softmax")
     mb = _bf16_model(spec, O.make_pix_shuffle_state_dict(spec, 1))
     with pytest.raises(_lib.EngineError) as ei:
         mb(torch.rand(1, 3, 16, 16, device=dev()))
     assert ei.value.code == _lib.ERR_UNSUPPORTED
+
+
+def test_bf16_channel_softmax_slots():
+    """vocab_b: softmax behind the residual add of layer 2 (wide kernel, residual from global memory) and log_softmax as
+    the first slot of layer 3 (resident-weight kernel): three passes over the accumulator row in the run-time epilogue."""
+    g = load_gold("pix_shuffle_vocab_b")
+    spec = gold_spec("vocab_b")
+    sd = O.make_pix_shuffle_state_dict(spec, int(g["seed"]))
+    m = _bf16_model(spec, sd)
+    got = m(torch.from_numpy(g["x"]).to(dev())).cpu()
+    want = torch.from_numpy(g["y"])
+    assert (got - want).abs().max().item() <= 2 * BF16_TOL and O.psnr(got, want, 1.0) >= 50.0   # log_softmax amplifies bf16 rounding
+    x = torch.rand(2, 3, 40, 300, generator=torch.Generator().manual_seed(3))
+    got = m(x.to(dev())).cpu()
+    want = O.pix_shuffle_forward(sd, spec, x)
+    assert (got - want).abs().max().item() <= 2 * BF16_TOL and O.psnr(got, want, 1.0) >= 50.0
 
 
 def test_bf16_conv3_heavyweight_wide_kernel():
