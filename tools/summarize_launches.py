@@ -14,6 +14,8 @@ for row in csv.DictReader(lines):
     unit = row["Metric Unit"]
     v = v / 1000 if unit in ("ns", "nsecond") else v * 1000 if unit in ("ms", "msecond") else v
     agg.setdefault(key, []).append(v)
-tot = sum(sum(v) for v in agg.values())
+# a pass launches every kernel once: shares are taken over the per-kernel averages (the capture window may cut a pass)
+tot = sum(sum(v) / len(v) for v in agg.values())
 for k, v in agg.items():
-    print(f"{k:50s} n={len(v):3d} avg={sum(v)/len(v):9.1f} us  share={100*sum(v)/tot:5.1f}%")
+    print(f"{k:50s} n={len(v):3d} avg={sum(v)/len(v):9.1f} us  share of one pass={100*(sum(v)/len(v))/tot:5.1f}%")
+print(f"{'one pass (64 frames), serialised under ncu':50s}       sum={tot:9.1f} us")
