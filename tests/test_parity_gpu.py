@@ -506,3 +506,27 @@ def test_device_generated_stream_through_the_engine():
     want = O.framebuffer_forward(sd, spec, torch.from_numpy(O.synth_rgb444_frames(4, 64, 96, 9)))
     got = m.forward_framebuffer(fb).cpu()
     assert (got.int() - want.int()).abs().max().item() <= 1
+
+
+@pytest.mark.parametrize("family", ["conv3", "conv5"])
+def test_heavyweight_full_size_builds_agree_and_frames_are_independent(family):
+    """BASELINE configs 3-4 at 752x576 (6 strips, 72 eight-row blocks, 2 output-channel groups on the wide kernel): the bf16
+    build against the fp32 build of the same engine, and size-independent properties (frame order, chunking)."""
+    from fs_uae_image_enhancer_project_b200 import model_conv3, model_conv5
+    mod, chans = (model_conv3, O.conv3_channels) if family == "conv3" else (model_conv5, O.conv5_channels)
+    sd = O.make_bn_state_dict(chans("heavyweight"), 21)
+    g = torch.Generator().manual_seed(8)
+    if family == "conv3":
+        x = torch.randint(0, 256, (3, 4, 576, 752), dtype=torch.uint8, generator=g).to(dev())
+        scale = 255.0
+    else:
+        x = torch.rand(3, 3, 576, 752, generator=g).to(dev())
+        scale = 1.0
+    m32 = mod.get_model("heavyweight"); m32.load_state_dict(sd); m32 = m32.to(dev())
+    m16 = mod.get_model("heavyweight"); m16.load_state_dict(sd); m16 = m16.to(dev()).set_precision("bf16")
+    m16.chunk_frames = 2
+    y16 = m16(x).float()
+    y32 = m32(x[:1].contiguous()).float()
+    assert (y16[:1] - y32).abs().max().item() <= scale * BF16_TOL and O.psnr(y16[:1].cpu(), y32.cpu(), scale) >= 50.0
+    assert torch.equal(y16.flip(0), m16(x.flip(0).contiguous()).float())            # frames are independent
+    assert torch.equal(y16[2:3], m16(x[2:3].contiguous()).float())                  # chunking is invisible
