@@ -164,6 +164,10 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = []
+    if world > 1:      # one process per GPU: keep its pinned host buffers on the GPU's NUMA node
+        from fs_uae_image_enhancer_project_b200.sharding import bind_to_gpu_numa_node
+        numa_cpus = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -298,7 +302,8 @@ def main():
             "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "variant": eng.variant, "frames_per_gpu_per_step": BATCH,
                        "l2": "inputs rotate over 2 batches (443 MB in+out) > 126 MB L2",
-                       "sharding": "frame-wise, one replica per GPU, no collective"},
+                       "sharding": "frame-wise, one replica per GPU, no collective",
+                       "host_numa_binding": f"{len(numa_cpus)} CPUs next to GPU 0" if numa_cpus else "none"},
             "latency_p50_ms": lat[len(lat) // 2], "latency_p99_ms": lat[int(len(lat) * 0.99) - 1],
             "us_per_frame": 1e6 * per_gpu_step_s / BATCH,
             "e2e": {"value": BATCH * world * e2e_steps / e2e_s, "unit": "frames/s",

@@ -7,7 +7,8 @@ barrier and the max-over-ranks of the measured time.
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+import os
+from typing import List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -36,3 +37,36 @@ def run_sharded(model, frames_host: torch.Tensor, out_host: torch.Tensor, rank: 
     if hi > lo:
         model.run_host(frames_host[lo:hi], out_host[lo:hi], gamma=gamma, crop16=crop16, device=device)
     return lo, hi
+
+
+def gpu_local_cpus(device: int) -> List[int]:
+    """CPUs of the NUMA node the GPU's PCIe root hangs off (sysfs), [] when the platform does not say."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bdf = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device)).busId
+        bdf = (bdf.decode() if isinstance(bdf, bytes) else bdf).lower()
+        if len(bdf.split(":")[0]) == 8:                      # NVML prints an 8-digit PCI domain, sysfs uses 4
+            bdf = bdf[4:]
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as fh:
+            text = fh.read().strip()
+        cpus: List[int] = []
+        for part in text.split(","):
+            if part:
+                lo, _, hi = part.partition("-")
+                cpus.extend(range(int(lo), int(hi or lo) + 1))
+        return cpus
+    except Exception:
+        return []
+
+
+def bind_to_gpu_numa_node(device: int) -> List[int]:
+    """Pin this process to the CPUs next to its GPU *before* it allocates pinned host buffers, so first-touch places
+    them on the GPU's NUMA node: with one process per GPU, host staging then never crosses the socket interconnect.
+    Best effort; returns the CPU list used ([] = nothing changed)."""
+    cpus = gpu_local_cpus(device)
+    allowed = sorted(set(cpus) & set(os.sched_getaffinity(0))) if cpus else []
+    if allowed and len(allowed) < len(os.sched_getaffinity(0)):
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    return []
