@@ -168,7 +168,12 @@ FSUAE_API int fsuae_engine_create_from_file(const char* path, int device, int pr
 FSUAE_API int fsuae_engine_destroy(fsuae_engine* e);
 
 /* Asynchronous: enqueue the forward of n_frames frames on `cuda_stream` (a cudaStream_t).
- * `in_dev` / `out_dev` are device pointers in the given formats. */
+ * `in_dev` / `out_dev` are device pointers in the given formats.
+ * Ownership / threading (reference: caller owns the tensors, forward is stateless): the caller owns
+ * in_dev / out_dev; the engine owns its workspace, which every call re-uses -- so calls on ONE engine must be ordered
+ * (one host thread at a time, and either one stream or streams the caller orders with events); the host-buffer calls use
+ * the engine's internal streams and must not run concurrently with fsuae_engine_enqueue on the same engine.  Use one
+ * engine per GPU and per concurrent stream; engines are independent. */
 FSUAE_API int fsuae_engine_enqueue(fsuae_engine* e, const void* in_dev, void* out_dev, int n_frames,
                          int in_fmt, int out_fmt, uint32_t flags, void* cuda_stream);
 
