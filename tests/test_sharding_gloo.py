@@ -50,3 +50,13 @@ def test_world_size_2_gloo():
         covered, slow = ret[rank]
         assert covered == [(0, 2048), (2048, 4096)]
         assert slow == 2.0
+
+
+def test_numa_binding_is_best_effort_without_a_gpu():
+    """No GPU / no NVML / no sysfs topology: nothing is bound and nothing raises."""
+    import os
+    from fs_uae_image_enhancer_project_b200 import sharding
+    before = os.sched_getaffinity(0)
+    assert sharding.gpu_local_cpus(97) == []
+    assert sharding.bind_to_gpu_numa_node(97) == []
+    assert os.sched_getaffinity(0) == before
