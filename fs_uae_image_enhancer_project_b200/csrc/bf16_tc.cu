@@ -81,7 +81,7 @@ struct LayerK {
   // epilogue parameters, expanded per channel on the host
   int n_pre, n_post;
   int softmax_slot, softmax_log;   // run-time epilogue: slot (0..3) of a channel softmax / log_softmax, -1: none
-  int dbg;                 // debugging aid (FSUAE_DBG): 1 = epilogue skips its global stores, 2 = producer re-reads the segment's first row, 4 = one TMA per row, 8 = no MMAs
+  int dbg;                 // debugging aid (FSUAE_DBG): 1 = epilogue skips its global stores, 2 = producer re-reads the segment's first row, 4 = one TMA per row, 8 = no MMAs, 16 = all frames alias frame 0's activation buffers
   int op[4];               // pre0, pre1, post0, post1 (identity-padded)
   float bias[MAXC];
   float p0[4][MAXC];
@@ -1872,7 +1872,10 @@ int bf16_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in
     plan->zero_Hw = g.Hw;
     plan->zero_Ww = g.Ww;
   }
-  auto fstride = [&](int id) { return (unsigned long long)plan->planes[id] * (g.Hw + 2 * BORDER) * PW * 16; };
+  // FSUAE_DBG & 16 (timing experiment, garbage results): every frame aliases frame 0's activation buffers, so all
+  // inter-layer traffic stays in L2 -- what the pass would cost if the layers did not stream through HBM
+  const bool alias_frames = getenv("FSUAE_DBG") && (atoi(getenv("FSUAE_DBG")) & 16);
+  auto fstride = [&](int id) { return alias_frames ? 0ull : (unsigned long long)plan->planes[id] * (g.Hw + 2 * BORDER) * PW * 16; };
 
   const int gin = (flags & FSUAE_FLAG_GAMMA_IN) ? 1 : 0;
   { ProfScope ps(e, st, "head");
