@@ -46,6 +46,13 @@ __host__ __device__ constexpr int plane_width(int S) { return STRIP * S + 2 * BO
 constexpr int SMEM_LIMIT = 232448 - 2048;
 constexpr int EPI_WG = 4;                       // epilogue warpgroups; group g owns accumulator stage g
 constexpr int NTHREADS = 64 + 128 * EPI_WG;
+// The layer kernel has a second MMA-issuing warp behind the epilogue warps (two issuers take the input rows in turn and
+// hand the MMA stream to each other: the barrier polling / bookkeeping of one row runs under the other's issue phase).
+#ifndef FSUAE_TWO_ISSUERS
+#define FSUAE_TWO_ISSUERS 1
+#endif
+constexpr int ISSUER2_WARP = NTHREADS / 32;                     // warp 18
+constexpr int NTHREADS_L = NTHREADS + (FSUAE_TWO_ISSUERS ? 32 : 0);
 
 enum { EPI_STORE = 0, EPI_TAIL_SHUFFLE = 1, EPI_TAIL_PLAIN = 2 };
 
@@ -54,13 +61,15 @@ enum { EPI_STORE = 0, EPI_TAIL_SHUFFLE = 1, EPI_TAIL_PLAIN = 2 };
 #endif
 
 #ifdef FSUAE_EPI_TIMING
-__device__ unsigned long long g_epi_timing[8];
+__device__ unsigned long long g_epi_timing[16];
 __device__ __forceinline__ long long clk() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory"); return t; }
 #define EPI_T(var) const long long var = clk()
 #define EPI_ACC(i, v) do { if (blockIdx.x == 0 && warp == 2 && lane == 0) g_epi_timing[i] += (unsigned long long)(v); } while (0)
+#define ISS_ACC(i, v) do { iss_t[i] += (unsigned long long)(v); } while (0)
 #else
 #define EPI_T(var)
 #define EPI_ACC(i, v)
+#define ISS_ACC(i, v)
 #endif
 
 struct LayerK {
@@ -372,7 +381,7 @@ struct SegIter {
 // the layer kernel
 // ------------------------------------------------------------------------------------------------
 template <int PT, int NPAD, int COUT, int KIND, class EPI, int CTAS = 1, bool R3 = false>
-__global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_constant__ LayerK P) {
+__global__ void __launch_bounds__(NTHREADS_L, 1) conv3x3_tc_kernel(const __grid_constant__ LayerK P) {
   using C = Cfg<PT, NPAD, CTAS, R3>;
   static_assert(!R3 || !EPI::kSkip, "R3 mode releases a ring row as soon as its MMAs are done: no residual from the ring");
   const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;   // rank 0 of a pair issues the MMAs
@@ -387,7 +396,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
   uint64_t* tempty = tfull + C::STAGES;        // [STAGES] epilogue -> MMA
   uint64_t* wbar = tempty + C::STAGES;         // weights landed
   uint64_t* pfull = wbar + 1;                  // [RING]  pair only, leader: the peer CTA's ring row has landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pfull + C::RING);
+  uint64_t* tok = pfull + C::RING;             // [2]     the MMA stream is handed from one issuing warp to the other
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tok + 2);
   __shared__ float s_lut[256];
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -398,6 +408,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
     for (int i = 0; i < C::RING; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], EPI::kSkip ? 5 : 1); mbar_init(&pfull[i], 1); }
     for (int i = 0; i < C::STAGES; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * CTAS); }   // pair: both CTAs' epilogues
     mbar_init(wbar, 1);
+    mbar_init(&tok[0], 1); mbar_init(&tok[1], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -407,7 +418,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
     reinterpret_cast<uint32_t*>(s_ring + C::RING * C::ROWBYTES)[threadIdx.x - 64] = 0u;
   }
   if constexpr (KIND == EPI_TAIL_SHUFFLE) {
-    for (int i = threadIdx.x; i < 256; i += NTHREADS) {
+    for (int i = threadIdx.x; i < 256; i += NTHREADS_L) {
       float t = (float)i * (1.0f / 255.0f);
       s_lut[i] = P.gamma_in ? powf(t, 2.2f) : t;
     }
@@ -434,6 +445,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
       tma_load_1d(s_w, P.wpack + (size_t)rank * C::WBYTES, C::WBYTES, wbar);   // constants: fetch before the dependency wait
       asm volatile("griddepcontrol.wait;" ::: "memory");
       uint32_t slot = 0, par = 1;   // waiting on parity 1 of a fresh barrier passes immediately
+#ifdef FSUAE_EPI_TIMING
+      unsigned long long prod_wait = 0, prod_rows = 0;
+      const long long prod_t0 = clk();
+#endif
       SegIter it(P, CTAS, (int)rank);
       Seg sg;
       while (it.next(P, sg)) {
@@ -442,7 +457,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
         const unsigned char* g0 = P.src0 + (size_t)f * P.fs0 + org;
         const unsigned char* g1 = P.P1 ? P.src1 + (size_t)f * P.fs1 + org : nullptr;
         for (int k = 0; k < rows + 2; ++k) {          // padded rows y0 .. y0+rows+1
+#ifdef FSUAE_EPI_TIMING
+          const long long tp0 = clk();
           mbar_wait(&empty[slot], par);
+          prod_wait += (unsigned long long)(clk() - tp0); prod_rows += 1;
+#else
+          mbar_wait(&empty[slot], par);
+#endif
           uint8_t* d = s_ring + slot * C::ROWBYTES;
           const int kk = (P.dbg & 2) ? 0 : k;
           if (P.dbg & 4) {      // timing experiment: one plane only (results are garbage)
@@ -459,25 +480,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
           if (++slot == C::RING) { slot = 0; par ^= 1; }
         }
       }
+#ifdef FSUAE_EPI_TIMING
+      if (blockIdx.x == 0) { g_epi_timing[8] += prod_wait; g_epi_timing[9] += prod_rows; g_epi_timing[10] += (unsigned long long)(clk() - prod_t0); }
+#endif
     }
   } else if (warp == 1 && rank != 0) {
     // ======================= peer CTA of a pair: relay "my ring row has landed" to the leader =======================
-    if (elect_one()) {
-      uint32_t wslot = 0, wpar = 0;
-      mbar_wait(wbar, 0);                 // my half of the weights is part of every MMA the leader issues
+    // One lane per ring slot, all in flight at once: a remote mbarrier arrive is a round trip over the cluster network,
+    // and relayed one row after the other by a single thread it was what the leader's MMA issuers waited for most
+    // (measured: ~1 800 of their ~4 000 cycles per row pair).
+    {
+      uint32_t total = 0;                 // input rows this CTA streams through its ring
       SegIter it(P, CTAS, (int)rank);
       Seg sg;
-      while (it.next(P, sg)) {
-        for (int k = 0; k < sg.rows + 2; ++k) {
-          mbar_wait(&full[wslot], wpar);
-          mbar_arrive_cluster(&pfull[wslot], 0);
-          if (++wslot == C::RING) { wslot = 0; wpar ^= 1; }
+      while (it.next(P, sg)) total += (uint32_t)sg.rows + 2u;
+      if (lane == 0) mbar_wait(wbar, 0);  // my half of the weights is part of every MMA the leader issues
+      __syncwarp();
+      const bool active = lane < C::RING;
+      const uint32_t fills = active && total > (uint32_t)lane ? (total - (uint32_t)lane + C::RING - 1) / C::RING : 0u;   // fills of slot `lane`
+      uint32_t done = 0, par = 0;
+      const long long t0 = clock64();
+      while (__any_sync(0xffffffffu, done < fills)) {
+        if (done < fills && mbar_try_wait(&full[lane], par)) {
+          mbar_arrive_cluster(&pfull[lane], 0);
+          par ^= 1u;
+          ++done;
         }
+        if (clock64() - t0 > (1ll << 33)) __trap();     // bounded like every other wait
       }
     }
-  } else if (warp == 1) {
-    // ======================= MMA issuer (leader CTA of a pair, or the only CTA) =======================
+  } else if (warp == ISSUER2_WARP && (rank != 0 || R3 || !(FSUAE_ROW_MAJOR != 0 && FSUAE_TWO_ISSUERS != 0))) {
+    // the second issuing warp has no work in the peer CTA of a pair, nor in the single-issuer orders
+  } else if (warp == 1 || warp == ISSUER2_WARP) {
+    // ======================= MMA issuers (leader CTA of a pair, or the only CTA) =======================
     if (elect_one()) {
+      const uint32_t me = warp == 1 ? 0u : 1u;       // issuer 0 takes the even input rows of the CTA's row sequence, issuer 1 the odd ones
       constexpr uint32_t IDESC = umma_idesc_bf16(MROWS * CTAS, NPAD);
       auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
         if constexpr (CTAS == 2) umma_bf16_2cta(d, a, b, idesc, acc); else umma_bf16(d, a, b, idesc, acc);
@@ -570,17 +607,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
         // times -- the A read is what bounds narrow-N UMMA.  Each output row keeps its own accumulator stage
         // (block n = blk0 + j in stage n % STAGES): no contiguity constraint, accumulate flags per instruction.
         constexpr uint32_t BSTEP = (C::NB * 32) >> 4;
-        uint32_t blk0 = 0;
+        constexpr bool TWO = FSUAE_TWO_ISSUERS != 0;
+#ifdef FSUAE_EPI_TIMING
+        unsigned long long iss_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+        uint32_t blk0 = 0, grow = 0, tokpar = 0;       // blocks / input rows of the CTA before this segment; parity of my token waits
         while (it.next(P, sg)) {
           const int rows = sg.rows;
-          uint32_t sk = blk0 % C::STAGES, pk = ((blk0 / C::STAGES) & 1u) ^ 1u;   // stage / tempty parity of block blk0 + k
           for (int k = 0; k < rows + 2; ++k) {
-            wait_row(wslot, wpar);
-            const uint32_t rs = wslot;
-            if (++wslot == C::RING) { wslot = 0; wpar ^= 1; }
+            const uint32_t r = grow + (uint32_t)k;           // position in the CTA's input-row sequence = ring fill number
+            if (TWO && (r & 1u) != me) continue;
+            const uint32_t rs = r % C::RING;
+            EPI_T(ti0);
+#ifdef FSUAE_EPI_TIMING
+            mbar_wait(&full[rs], (r / C::RING) & 1u);
+            EPI_T(ti0b);
+            if constexpr (CTAS == 2) mbar_wait(&pfull[rs], (r / C::RING) & 1u);
+            ISS_ACC(5, ti0b - ti0);
+#else
+            wait_row(rs, (r / C::RING) & 1u);
+#endif
+            EPI_T(ti1);
+            const uint32_t n = blk0 + (uint32_t)k;           // block (output row) this input row opens
+            const uint32_t sk = n % C::STAGES, pk = ((n / C::STAGES) & 1u) ^ 1u;
             const bool v0 = k <= rows - 1, v1 = k >= 1 && k <= rows, v2 = k >= 2;
             if (v0) mbar_wait(&tempty[sk], pk);
+            EPI_T(ti2);
+            if (TWO && r > 0) {                               // my turn: the other issuer has issued the previous row
+              mbar_wait(&tok[me], tokpar);
+              tokpar ^= 1u;
+            }
             tc_fence_after();
+            EPI_T(ti3);
+            ISS_ACC(0, ti1 - ti0); ISS_ACC(1, ti2 - ti1); ISS_ACC(2, ti3 - ti2); ISS_ACC(7, 1);
             const uint32_t s1 = sk >= 1u ? sk - 1u : sk + C::STAGES - 1u, s2 = sk >= 2u ? sk - 2u : sk + C::STAGES - 2u;
             const uint32_t d0 = tmem_base + sk * NPAD, d1 = tmem_base + s1 * NPAD, d2 = tmem_base + s2 * NPAD;
             const uint32_t a_row = ring_lo + rs * (C::ROWBYTES >> 4);
@@ -613,12 +672,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
                 if (v0) mma(d0, a_desc, hi | b_st, IDESC, st == 0 ? 0u : 1u);
               }
             }
-            commit(&empty[rs]);                    // the MMAs are done with this input row
+            EPI_T(ti4);
+            commit(&empty[rs]);                    // the MMAs are done with this input row (the pipe completes in issue order)
             if (v2) commit(&tfull[s2]);            // output row k-2 is complete
-            if (++sk == C::STAGES) { sk = 0; pk ^= 1u; }
+            if (TWO) {                             // hand the MMA stream over: tcgen05 ops of two threads are ordered by fence + sync
+              tc_fence_before();
+              mbar_arrive(&tok[me ^ 1u]);
+            }
+            EPI_T(ti5);
+            ISS_ACC(3, ti4 - ti3); ISS_ACC(4, ti5 - ti4);
           }
           blk0 += (uint32_t)rows;
+          grow += (uint32_t)rows + 2u;
         }
+#ifdef FSUAE_EPI_TIMING
+        if (blockIdx.x == 0 && me == 0)
+          for (int i = 0; i < 8; ++i) g_epi_timing[i] += iss_t[i];
+#endif
       } else
       while (it.next(P, sg)) {
         const int rows = sg.rows;
@@ -1090,24 +1160,31 @@ conv3x3_tc_fused_pair_kernel(const __grid_constant__ LayerK A, const __grid_cons
     }
   } else if (warp == 1 && rank != 0) {
     // ======================= peer: relay landed / written rows to the leader, in the leader's wait order =======================
-    if (elect_one()) {
-      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
-      mbar_wait(wbar, 0);
+    // One lane per ring slot (lanes 0.. ringA, lanes 16.. ringB), all in flight at once: no head-of-line blocking between
+    // the two rings, and the remote arrives (a round trip over the cluster network each) overlap.
+    {
+      uint32_t totalA = 0, totalB = 0;    // rows through the rings per segment: rows + 4 input rows of A, rows + 2 output rows of A
       SegIter it(P, 2, (int)rank);
       Seg sg;
-      auto relayA = [&]() { mbar_wait(&fullA[sa], pa); mbar_arrive_cluster(&pfullA[sa], 0); if (++sa == C::RA) { sa = 0; pa ^= 1; } };
-      auto relayB = [&]() { mbar_wait(&fullB[sb], pb); mbar_arrive_cluster(&pfullB[sb], 0); if (++sb == C::RB) { sb = 0; pb ^= 1; } };
-      while (it.next(P, sg)) {
-        for (int i = 0; i < sg.rows + C::LAG; ++i) {
-          if (i < sg.rows + 2) {
-            if (i == 0) { relayA(); relayA(); }
-            relayA();
-          }
-          if (i >= C::LAG) {
-            if (i == C::LAG) { relayB(); relayB(); }
-            relayB();
-          }
+      while (it.next(P, sg)) { totalA += (uint32_t)sg.rows + 4u; totalB += (uint32_t)sg.rows + 2u; }
+      if (lane == 0) mbar_wait(wbar, 0);
+      __syncwarp();
+      static_assert(C::RA <= 16 && C::RB <= 16, "one lane per ring slot");
+      const bool isA = lane < 16;
+      const uint32_t slot = isA ? (uint32_t)lane : (uint32_t)lane - 16u, R = isA ? (uint32_t)C::RA : (uint32_t)C::RB;
+      const uint32_t total = isA ? totalA : totalB;
+      const uint32_t fills = slot < R && total > slot ? (total - slot + R - 1) / R : 0u;
+      uint64_t* src = isA ? &fullA[slot < R ? slot : 0] : &fullB[slot < R ? slot : 0];
+      uint64_t* dst = isA ? &pfullA[slot < R ? slot : 0] : &pfullB[slot < R ? slot : 0];
+      uint32_t done = 0, par = 0;
+      const long long t0 = clock64();
+      while (__any_sync(0xffffffffu, done < fills)) {
+        if (done < fills && mbar_try_wait(src, par)) {
+          mbar_arrive_cluster(dst, 0);
+          par ^= 1u;
+          ++done;
         }
+        if (clock64() - t0 > (1ll << 33)) __trap();
       }
     }
   } else if (warp == 1) {
@@ -1596,10 +1673,10 @@ extern "C" __attribute__((visibility("default"))) long long fsuae_debug_read_bf1
 }
 
 #ifdef FSUAE_EPI_TIMING
-extern "C" __attribute__((visibility("default"))) int fsuae_debug_epi_timing(unsigned long long* out8, int reset) {
+extern "C" __attribute__((visibility("default"))) int fsuae_debug_epi_timing(unsigned long long* out8, int reset) {   // 16 counters
   cudaDeviceSynchronize();
   if (cudaMemcpyFromSymbol(out8, g_epi_timing, sizeof(g_epi_timing)) != cudaSuccess) return -1;
-  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_epi_timing, z, sizeof(z)); }
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_epi_timing, z, sizeof(z)); }
   return 0;
 }
 #endif
@@ -1905,12 +1982,12 @@ int bf16_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in
     if (const char* dbg = getenv("FSUAE_DBG")) k.dbg = atoi(dbg);
     return k;
   };
-  auto launch_cfg = [&](cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int n_blocks, int ctas, int smem) {
+  auto launch_cfg = [&](cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int n_blocks, int ctas, int smem, int threads = NTHREADS) {
     int grid = std::min(n_blocks * ctas, e->sm_count / ctas * ctas);
     if (const char* g_env = getenv("FSUAE_DEBUG_GRID")) grid = std::max(ctas, std::min(n_blocks * ctas, atoi(g_env) / ctas * ctas));   // debugging aid: force the CTA count
     cfg = cudaLaunchConfig_t{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(NTHREADS);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1961,7 +2038,7 @@ int bf16_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in
       const Variant* var = r3 ? ln.var3 : (pair ? ln.var2 : ln.var);
       LayerK k = fill(i, ln, pair);
       if (r3) k.wpack = ln.d_w3;
-      launch_cfg(cfg, attr, k.n_blocks, pair ? 2 : 1, var->smem);
+      launch_cfg(cfg, attr, k.n_blocks, pair ? 2 : 1, var->smem, NTHREADS_L);
       { ProfScope ps(e, st, ("conv" + std::to_string(i + 1) + (r3 ? "_r3" : (pair ? "_pair" : ""))).c_str());
         FSUAE_CUDA_CHECK(e, cudaLaunchKernelEx(&cfg, var->fn, k)); }
       e->launches++;
