@@ -61,7 +61,7 @@ enum { EPI_STORE = 0, EPI_TAIL_SHUFFLE = 1, EPI_TAIL_PLAIN = 2 };
 #endif
 
 #ifdef FSUAE_EPI_TIMING
-__device__ unsigned long long g_epi_timing[16];
+__device__ unsigned long long g_epi_timing[32];
 __device__ __forceinline__ long long clk() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory"); return t; }
 #define EPI_T(var) const long long var = clk()
 #define EPI_ACC(i, v) do { if (blockIdx.x == 0 && warp == 2 && lane == 0) g_epi_timing[i] += (unsigned long long)(v); } while (0)
@@ -687,7 +687,7 @@ __global__ void __launch_bounds__(NTHREADS_L, 1) conv3x3_tc_kernel(const __grid_
         }
 #ifdef FSUAE_EPI_TIMING
         if (blockIdx.x == 0 && me == 0)
-          for (int i = 0; i < 8; ++i) g_epi_timing[i] += iss_t[i];
+          for (int i = 0; i < 8; ++i) g_epi_timing[16 + i] += iss_t[i];      // counters 16..23: the issuer's (0..7 belong to the epilogue probe)
 #endif
       } else
       while (it.next(P, sg)) {
@@ -1676,7 +1676,7 @@ extern "C" __attribute__((visibility("default"))) long long fsuae_debug_read_bf1
 extern "C" __attribute__((visibility("default"))) int fsuae_debug_epi_timing(unsigned long long* out8, int reset) {   // 16 counters
   cudaDeviceSynchronize();
   if (cudaMemcpyFromSymbol(out8, g_epi_timing, sizeof(g_epi_timing)) != cudaSuccess) return -1;
-  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_epi_timing, z, sizeof(z)); }
+  if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(g_epi_timing, z, sizeof(z)); }
   return 0;
 }
 #endif
