@@ -383,6 +383,10 @@ struct SegIter {
 template <int PT, int NPAD, int COUT, int KIND, class EPI, int CTAS = 1, bool R3 = false>
 __global__ void __launch_bounds__(NTHREADS_L, 1) conv3x3_tc_kernel(const __grid_constant__ LayerK P) {
   using C = Cfg<PT, NPAD, CTAS, R3>;
+  // The input-row-major order keeps three accumulators open at a time: it needs TMEM stages to spare for the epilogues
+  // (N <= 80: 6-8 stages).  Wider layers (4 stages) keep the block-major order, one accumulator per block
+  // (measured: conv5 heavyweight's 64 -> 128 layer 49 us/frame block-major, 76 row-major).
+  constexpr bool kRowMajor = FSUAE_ROW_MAJOR != 0 && C::STAGES >= 6;
   static_assert(!R3 || !EPI::kSkip, "R3 mode releases a ring row as soon as its MMAs are done: no residual from the ring");
   const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;   // rank 0 of a pair issues the MMAs
   constexpr int OUT_PLANES = COUT > 0 ? (COUT + 7) / 8 : 1;   // COUT <= 0: channel count is a run-time parameter
@@ -509,7 +513,7 @@ __global__ void __launch_bounds__(NTHREADS_L, 1) conv3x3_tc_kernel(const __grid_
         if (clock64() - t0 > (1ll << 33)) __trap();     // bounded like every other wait
       }
     }
-  } else if (warp == ISSUER2_WARP && (rank != 0 || R3 || !(FSUAE_ROW_MAJOR != 0 && FSUAE_TWO_ISSUERS != 0))) {
+  } else if (warp == ISSUER2_WARP && (rank != 0 || R3 || !(kRowMajor && FSUAE_TWO_ISSUERS != 0))) {
     // the second issuing warp has no work in the peer CTA of a pair, nor in the single-issuer orders
   } else if (warp == 1 || warp == ISSUER2_WARP) {
     // ======================= MMA issuers (leader CTA of a pair, or the only CTA) =======================
@@ -600,7 +604,7 @@ __global__ void __launch_bounds__(NTHREADS_L, 1) conv3x3_tc_kernel(const __grid_
           }
           blk0 += (uint32_t)rows;
         }
-      } else if constexpr (FSUAE_ROW_MAJOR != 0 && PT > 0) {      // (PT > 0 keeps the condition value-dependent: the front end mis-parses a non-dependent one here)
+      } else if constexpr (kRowMajor) {
         // ---- input-row-major issue order with A-collector reuse ----
         // Input row k of a segment feeds output rows j = k-2 (kernel row 2), k-1 (row 1), k (row 0).  For every step the
         // three MMAs share the A tile (fill / use / lastuse), so it is read from shared memory once instead of three

@@ -167,18 +167,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_wide_kernel(const __gr
           const uint32_t a0 = base_lo + stage * (C::STAGE >> 4);
           const uint32_t b0 = a0 + (C::A_BYTES >> 4);
           const bool first = kc == 0, last = kc == P.kchunks - 1;
+          // Input-row-major order: input row i of the stage (image row y0 - 1 + i) feeds output rows r = i - dy for the three
+          // kernel rows dy; the MMAs of one (i, dx) share the A tile -- collector fill / use / lastuse, so it is read from
+          // shared memory once.  Output row r is first touched at (i = r, dx = 0, dy = 0) and complete after i = r + 2.
 #pragma unroll
-          for (int r = 0; r < C::ROWS; ++r) {
-            if (first) { mbar_wait(&tempty[r], tpar); tc_fence_after(); }
-            const uint32_t d_tmem = tmem_base + r * NT;
+          for (int i = 0; i < C::ROWS + 2; ++i) {
+            if (first && i < C::ROWS) { mbar_wait(&tempty[i], tpar); tc_fence_after(); }     // row i's accumulator opens here
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              const uint32_t a_lo = a0 + (uint32_t)((r + tap / 3) * 2 * (PLANE_ROW >> 4) + tap % 3);
-              const uint32_t b_lo = b0 + tap * B_TAP;
-              umma_bf16_2cta(d_tmem, ((uint64_t)HI << 32) | (a_lo | A_LBO), ((uint64_t)HI << 32) | (b_lo | B_LBO), IDESC,
-                             (first && tap == 0) ? 0u : 1u);
+            for (int dx = 0; dx < 3; ++dx) {
+              const uint64_t a_desc = ((uint64_t)HI << 32) | ((a0 + (uint32_t)(i * 2 * (PLANE_ROW >> 4) + dx)) | A_LBO);
+              const int dy_lo = i - (C::ROWS - 1) > 0 ? i - (C::ROWS - 1) : 0, dy_hi = i < 2 ? i : 2;      // kernel rows with 0 <= i - dy < ROWS
+#pragma unroll
+              for (int dy = 0; dy < 3; ++dy) {
+                if (dy < dy_lo || dy > dy_hi) continue;
+                const int r = i - dy;
+                const uint64_t b_desc = ((uint64_t)HI << 32) | ((b0 + (uint32_t)(dy * 3 + dx) * B_TAP) | B_LBO);
+                const uint32_t acc = (first && dy == 0 && dx == 0) ? 0u : 1u;
+                const uint32_t d_tmem = tmem_base + r * NT;
+                if (dy_lo == dy_hi) umma_bf16_2cta(d_tmem, a_desc, b_desc, IDESC, acc);
+                else if (dy == dy_lo) umma_bf16_coll<2, 1>(d_tmem, a_desc, b_desc, IDESC, acc);
+                else if (dy == dy_hi) umma_bf16_coll<2, 3>(d_tmem, a_desc, b_desc, IDESC, acc);
+                else umma_bf16_coll<2, 2>(d_tmem, a_desc, b_desc, IDESC, acc);
+              }
             }
-            if (last) umma_commit_2cta(&tfull[r]);
+            if (last && i >= 2) umma_commit_2cta(&tfull[i - 2]);
           }
           umma_commit_2cta(&empty[stage]);
           if (++stage == C::NSTAGE) { stage = 0; par ^= 1; }
