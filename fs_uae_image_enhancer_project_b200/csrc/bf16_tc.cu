@@ -112,7 +112,7 @@ struct Cfg {
   static constexpr int ROWBYTES = PT * PLANE_ROW;
   static constexpr int RING_FIT = (SMEM_LIMIT - WBYTES - 64 - 512) / ROWBYTES;
   static constexpr int RING = RING_FIT > 10 ? 10 : RING_FIT;
-  static constexpr int STAGES_CAP = R3 ? 12 : 8;
+  static constexpr int STAGES_CAP = R3 ? 12 : 10;     // the row-major order keeps three accumulators open: 10 stages leave 7 for the epilogues (N <= 48)
   static constexpr int STAGES = (512 / NPAD) > STAGES_CAP ? STAGES_CAP : (512 / NPAD);   // accumulator stages: more than warpgroups, so the MMAs run ahead of the (MUFU-bound) epilogues
   static constexpr int BAR_OFF = WBYTES + RING * ROWBYTES + 64;
   static constexpr int SMEM = BAR_OFF + 512;
