@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(NTHREADS_L, 1) conv3x3_tc_kernel(const __grid_
         if (clock64() - t0 > (1ll << 33)) __trap();     // bounded like every other wait
       }
     }
-  } else if (warp == ISSUER2_WARP && (rank != 0 || R3 || !(kRowMajor && FSUAE_TWO_ISSUERS != 0))) {
+  } else if (warp == ISSUER2_WARP && (rank != 0 || !((kRowMajor || R3) && FSUAE_TWO_ISSUERS != 0))) {
     // the second issuing warp has no work in the peer CTA of a pair, nor in the single-issuer orders
   } else if (warp == 1 || warp == ISSUER2_WARP) {
     // ======================= MMA issuers (leader CTA of a pair, or the only CTA) =======================
@@ -548,21 +548,26 @@ __global__ void __launch_bounds__(NTHREADS_L, 1) conv3x3_tc_kernel(const __grid_
         constexpr uint32_t N3 = 3 * NPAD;
         constexpr uint32_t BSTEP3 = (N3 * 32) >> 4;
         const uint32_t w3_lo = ((smem_u32(s_w) & 0x3FFFFu) >> 4) | ((uint32_t)((N3 * 16) >> 4) << 16);
-        uint32_t blk0 = 0;
+        uint32_t blk0 = 0, grow3 = 0, tokpar3 = 0;
+        constexpr bool TWO3 = FSUAE_TWO_ISSUERS != 0;       // the two issuing warps take the input rows in turn, as in the row-major order below
         constexpr uint32_t IDESC0 = umma_idesc_bf16(MROWS, 0);             // N field (bits 17..22, N >> 3) added per run
         constexpr uint32_t IDN = (uint32_t)(NPAD >> 3) << 17;
         while (it.next(P, sg)) {
           const int rows = sg.rows;
-          // slot / tempty parity of block blk0 + k, kept incrementally (one thread issues everything: every integer
-          // division here would cost more than an MMA)
-          uint32_t sk = blk0 % C::STAGES, pk = ((blk0 / C::STAGES) & 1u) ^ 1u;
           for (int k = 0; k < rows + 2; ++k) {
-            wait_row(wslot, wpar);
-            const uint32_t rs = wslot;
-            if (++wslot == C::RING) { wslot = 0; wpar ^= 1; }
+            const uint32_t r3 = grow3 + (uint32_t)k;         // position in the CTA's input-row sequence = ring fill number
+            if (TWO3 && (r3 & 1u) != me) continue;
+            const uint32_t rs = r3 % C::RING;
+            wait_row(rs, (r3 / C::RING) & 1u);
+            const uint32_t nb = blk0 + (uint32_t)k;
+            const uint32_t sk = nb % C::STAGES, pk = ((nb / C::STAGES) & 1u) ^ 1u;      // stage / tempty parity of block blk0 + k
             const int jlo = max(k - 2, 0), jhi = min(k, rows - 1);
             const bool has_new = k <= rows - 1;
             if (has_new) mbar_wait(&tempty[sk], pk);
+            if (TWO3 && r3 > 0) {
+              mbar_wait(&tok[me], tokpar3);
+              tokpar3 ^= 1u;
+            }
             tc_fence_after();
             const int back = k - jlo;                                           // 0..2 older rows in flight
             const uint32_t slot_lo = sk >= (uint32_t)back ? sk - (uint32_t)back : sk + C::STAGES - (uint32_t)back;
@@ -579,7 +584,6 @@ __global__ void __launch_bounds__(NTHREADS_L, 1) conv3x3_tc_kernel(const __grid_
             const uint32_t boo1 = boff0 + (uint32_t)(co0 * NPAD);
             const uint32_t dn = tmem_base + sk * NPAD, bon = 2u * NPAD;
             const uint32_t s_done = sk >= 2u ? sk - 2u : sk + C::STAGES - 2u;   // slot of output row k-2
-            if (++sk == C::STAGES) { sk = 0; pk ^= 1u; }
             const uint32_t a_row = ring_lo + rs * (C::ROWBYTES >> 4);
 #pragma unroll
             for (int st = 0; st < C::STEPS_ROW; ++st) {
@@ -601,8 +605,13 @@ __global__ void __launch_bounds__(NTHREADS_L, 1) conv3x3_tc_kernel(const __grid_
             }
             commit(&empty[rs]);                                              // this input row is not needed again
             if (k >= 2) commit(&tfull[s_done]);                               // output row k-2 is complete
+            if (TWO3) {
+              tc_fence_before();
+              mbar_arrive(&tok[me ^ 1u]);
+            }
           }
           blk0 += (uint32_t)rows;
+          grow3 += (uint32_t)rows + 2u;
         }
       } else if constexpr (kRowMajor) {
         // ---- input-row-major issue order with A-collector reuse ----
