@@ -146,7 +146,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="auto", choices=["auto", "bf16", "fp32"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "bf16", "fp16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunk", type=int, default=64, help="frames per internal engine pass")
     ap.add_argument("--quick", action="store_true", help="skip latency / e2e legs (tuning runs)")
@@ -183,8 +183,8 @@ def main():
             if args.precision == "bf16" or exc.code != _lib.ERR_UNSUPPORTED:
                 raise
             precision = "fp32"
-    if precision == "fp32":
-        model.set_precision("fp32")
+    if precision in ("fp32", "fp16"):
+        model.set_precision(precision)
     eng = model.engine_for(dev, FRAME_H, FRAME_W)
 
     # two rotating batches: 2 x 64 frames x (1.73 MB in + 1.73 MB out) = 443 MB > 126 MB L2
@@ -219,6 +219,21 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
+
+    # the bytes just timed, checked outside the timed region: two frames of the last step's output against the oracle
+    parity = None
+    if rank == 0:
+        from oracle import enhancer_oracle as O                      # checker only (never inside a timed region)
+        last = (args.steps - 1) & 1
+        sd_cpu = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+        worst, exact = 0, 1.0
+        for k in (0, BATCH - 1):
+            want = O.framebuffer_forward(sd_cpu, O.pix_shuffle_preset("lightweight"), host[last][k:k + 1])
+            d = (d_out[last][k:k + 1].cpu().int() - want.int()).abs()
+            worst, exact = max(worst, int(d.max())), min(exact, float((d == 0).float().mean()))
+        gate = {"bf16": 6, "fp16": 2, "fp32": 1}[precision]
+        parity = {"checked": "frames 0 and 63 of the last timed step vs the CPU oracle (u8 RGBA)", "max_lsb": worst,
+                  "exact_frac": round(exact, 5), "gate_lsb": gate, "ok": worst <= gate}
 
     # per-kernel device times (CUDA events around every launch, on the launching stream), outside the timed region
     eng.set_profiling(True)
@@ -299,7 +314,7 @@ def main():
         line = {
             "metric": "752x576 frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[precision], "data": "synthetic",
             "config": {"workload": WORKLOAD, "variant": eng.variant, "frames_per_gpu_per_step": BATCH,
                        "l2": "inputs rotate over 2 batches (443 MB in+out) > 126 MB L2",
                        "sharding": "frame-wise, one replica per GPU, no collective",
@@ -324,6 +339,7 @@ def main():
                                     "note": f"algorithmic 29.472 GFLOP/frame x {BATCH} frames / step device time (all kernels of the "
                                             f"pass); HBM floor: {BYTES_PER_FRAME_U8 * BATCH / 1e9 / (hbm_peak) * 1e3:.3f} ms/step"},
             "kernel_ms": per_kernel,
+            "parity_check": parity,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

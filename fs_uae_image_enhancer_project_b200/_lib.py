@@ -24,7 +24,8 @@ ACT["swish"] = ACT["silu"]
 
 HEAD_PLAIN, HEAD_UNSHUFFLE2 = 0, 1
 TAIL_PLAIN, TAIL_SHUFFLE2_RESIDUAL_RELU, TAIL_SCALE255_ALPHA = 0, 1, 2
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2
+MAX_CHUNK_FRAMES = 1024
 FMT_F32_NCHW3, FMT_U8_NHWC4, FMT_U8_NCHW4, FMT_F32_NCHW4 = 0, 1, 2, 3
 FLAG_GAMMA_IN, FLAG_GAMMA_OUT, FLAG_CROP16 = 1, 2, 4
 

@@ -12,8 +12,11 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.environ.get("FSUAE_LIB_PATH") or os.path.join(PKG_DIR, "libfsuae_enhancer.so")   # override: A/B builds side by side
-SOURCES = ["abi.cu", "fp32_path.cu", "bf16_tc.cu", "synth.cu"]
-FAST_MATH_SOURCES = {"bf16_tc.cu"}   # approximate transcendentals + flush-to-zero: bf16 build only, never the fp32 build
+# (source, object, extra flags): bf16_tc.cu is compiled twice -- bf16 operands and, with -DFSUAE_OPERAND_FP16, fp16 operands
+UNITS = [("abi.cu", "abi.o", []), ("fp32_path.cu", "fp32_path.o", []), ("synth.cu", "synth.o", []),
+         # approximate transcendentals + flush-to-zero: tensor-core builds only, never the fp32 build
+         ("bf16_tc.cu", "bf16_tc.o", ["--use_fast_math"]),
+         ("bf16_tc.cu", "fp16_tc.o", ["--use_fast_math", "-DFSUAE_OPERAND_FP16"])]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
@@ -33,17 +36,15 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     objs = []
     os.makedirs(os.path.join(PKG_DIR, "build"), exist_ok=True)
     procs = []
-    for src in SOURCES:
-        obj = os.path.join(PKG_DIR, "build", src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-c",
+    for src, objname, unit_flags in UNITS:
+        obj = os.path.join(PKG_DIR, "build", objname)
+        cmd = [nvcc, *NVCC_FLAGS, *unit_flags, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-c",
                os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
-        if src in FAST_MATH_SOURCES:
-            cmd.insert(1, "--use_fast_math")
         for extra in os.environ.get("FSUAE_EXTRA_NVCC_FLAGS", "").split():   # debugging aids (e.g. -DFSUAE_EPI_TIMING)
             cmd.insert(1, extra)
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        procs.append((objname, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:
         out, _ = p.communicate()

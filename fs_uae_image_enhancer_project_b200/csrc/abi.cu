@@ -2,8 +2,10 @@
 // host-buffer pipeline.  The arithmetic lives in fp32_path.cu / bf16_tc.cu.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <new>
 
 #include "engine.h"
 
@@ -20,6 +22,30 @@ int set_error(fsuae_engine* e, int code, const std::string& msg) {
     g_create_error = msg;
   }
   return code;
+}
+
+// experiment switches: environment -> Tuning, once per engine
+static Tuning read_tuning() {
+  Tuning t;
+  auto flag = [&](const char* name, bool& dst) {
+    if (const char* v = getenv(name); v && *v) { dst = true; t.tag += std::string(" ") + name; }
+  };
+  auto num = [&](const char* name, int& dst) {
+    if (const char* v = getenv(name); v && *v) { dst = atoi(v); t.tag += std::string(" ") + name + "=" + v; }
+  };
+  num("FSUAE_DEBUG_GRID", t.grid);
+  num("FSUAE_R3", t.r3);
+  num("FSUAE_MEGA_MIN_FRAMES", t.mega_min_frames);
+  flag("FSUAE_NO_FUSION", t.no_fusion);
+  flag("FSUAE_NO_PAIRS", t.no_pairs);
+  flag("FSUAE_NO_WIDE", t.no_wide);
+  flag("FSUAE_FORCE_WIDE", t.force_wide);
+  flag("FSUAE_NO_MEGA", t.no_mega);
+  if (const char* env = getenv("FSUAE_HOST_STAGES"); env && *env) {
+    for (const char* c = env; *c;) { t.host_stages.push_back(std::max(1, atoi(c))); while (*c && *c != ',') ++c; if (*c) ++c; }
+    t.tag += std::string(" FSUAE_HOST_STAGES=") + env;
+  }
+  return t;
 }
 
 static int act_param_counts(int op, int* need0, int* need1) {
@@ -121,8 +147,10 @@ int fsuae_engine_create(const fsuae_net_desc* desc, const float* blob, size_t bl
   std::string why;
   int rc = validate(desc, blob_floats, height, width, &why);
   if (rc != FSUAE_OK) return set_error(nullptr, rc, why);
-  if (precision != FSUAE_PREC_FP32 && precision != FSUAE_PREC_BF16)
+  if (precision != FSUAE_PREC_FP32 && precision != FSUAE_PREC_BF16 && precision != FSUAE_PREC_FP16)
     return set_error(nullptr, FSUAE_ERR_INVALID, "unknown precision");
+  if (max_chunk_frames > FSUAE_MAX_CHUNK_FRAMES)
+    return set_error(nullptr, FSUAE_ERR_INVALID, "max_chunk_frames above FSUAE_MAX_CHUNK_FRAMES (enqueue accepts any frame count and loops)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return set_error(nullptr, FSUAE_ERR_NO_DEVICE, "no CUDA device visible (this engine has no CPU path)");
@@ -134,7 +162,9 @@ int fsuae_engine_create(const fsuae_net_desc* desc, const float* blob, size_t bl
     return set_error(nullptr, FSUAE_ERR_NO_DEVICE,
                      std::string("kernels are built for sm_100a only; device is ") + prop.name);
 
-  fsuae_engine* e = new fsuae_engine();
+  fsuae_engine* e = new (std::nothrow) fsuae_engine();
+  if (!e) return set_error(nullptr, FSUAE_ERR_CUDA, "out of host memory");
+  e->tuning = read_tuning();
   e->desc = *desc;
   e->device = device;
   e->precision = precision;
@@ -162,7 +192,8 @@ int fsuae_engine_create(const fsuae_net_desc* desc, const float* blob, size_t bl
   }
   e->device_bytes += blob_floats * sizeof(float);
 
-  rc = precision == FSUAE_PREC_FP32 ? fp32_create(e) : bf16_create(e);
+  rc = precision == FSUAE_PREC_FP32 ? fp32_create(e) : precision == FSUAE_PREC_BF16 ? bf16_create(e) : fp16_create(e);
+  if (rc == FSUAE_OK) e->variant += e->tuning.tag.empty() ? "" : " [" + e->tuning.tag.substr(1) + "]";
   if (rc != FSUAE_OK) {
     cudaSetDevice(prev);
     return fail(rc);
@@ -203,9 +234,19 @@ int fsuae_engine_create_from_file(const char* path, int device, int precision, i
   std::vector<float> blob;
   bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, "FSUAEENG", 8) == 0 && fread(hdr, 4, 2, f) == 2 &&
             hdr[0] == FSUAE_ABI_VERSION && fread(&desc, sizeof(desc), 1, f) == 1;
+  if (ok) {      // the header's float count must be what the file actually holds (a corrupt count must not drive an allocation)
+    const long pos = ftell(f);
+    ok = pos >= 0 && fseek(f, 0, SEEK_END) == 0;
+    const long end = ok ? ftell(f) : -1;
+    ok = ok && end >= pos && (unsigned long long)(end - pos) == 4ull * hdr[1] && fseek(f, pos, SEEK_SET) == 0;
+  }
   if (ok) {
-    blob.resize(hdr[1]);
-    ok = fread(blob.data(), 4, blob.size(), f) == blob.size();
+    try {
+      blob.resize(hdr[1]);
+    } catch (const std::exception&) {
+      ok = false;
+    }
+    ok = ok && fread(blob.data(), 4, blob.size(), f) == blob.size();
   }
   fclose(f);
   if (!ok) return set_error(nullptr, FSUAE_ERR_INVALID, std::string("malformed engine file ") + path);
@@ -220,6 +261,7 @@ int fsuae_engine_destroy(fsuae_engine* e) {
   cudaDeviceSynchronize();
   fp32_destroy(e);
   bf16_destroy(e);
+  fp16_destroy(e);
   for (cudaEvent_t ev : e->prof_ev) cudaEventDestroy(ev);
   for (int i = 0; i < FSUAE_STAGE_BUFS; ++i) {
     if (e->d_stage_in[i]) cudaFree(e->d_stage_in[i]);
@@ -244,9 +286,7 @@ static int enqueue_impl(fsuae_engine* e, const void* in_dev, void* out_dev, int 
     int n = std::min(e->chunk, n_frames - f0);
     const char* ip = (const char*)in_dev + (size_t)f0 * in_fb;
     char* op = (char*)out_dev + (size_t)f0 * out_fb;
-    int rc = e->precision == FSUAE_PREC_FP32
-                 ? fp32_enqueue_chunk(e, ip, op, n, in_fmt, out_fmt, flags, st)
-                 : bf16_enqueue_chunk(e, ip, op, n, in_fmt, out_fmt, flags, st);
+    int rc = enqueue_chunk(e, ip, op, n, in_fmt, out_fmt, flags, st);
     if (rc != FSUAE_OK) return rc;
   }
   return FSUAE_OK;
@@ -276,6 +316,7 @@ int fsuae_engine_submit_host(fsuae_engine* e, const void* in_host, void* out_hos
   int rc = check_formats(e, in_fmt, out_fmt, flags);
   if (rc != FSUAE_OK) return rc;
   e->launches = 0;
+  e->prof_n = 0;
   if (n_frames == 0) return FSUAE_OK;
   int prev = 0;
   cudaGetDevice(&prev);
@@ -287,10 +328,9 @@ int fsuae_engine_submit_host(fsuae_engine* e, const void* in_host, void* out_hos
   // pipeline is idle the call is most likely a blocking one that pays fill (first upload) and drain (last download),
   // so stages ramp up 4, 6, 8, 10, 12 ... and back down ... 10, 8, 6 (19.5 k frames/s against 16.9 k for uniform 16).
   std::vector<int> stages;
-  if (const char* env = getenv("FSUAE_HOST_STAGES"); env && *env) {      // debugging aid: explicit schedule "2,4,8,..." (repeated to cover n_frames)
-    std::vector<int> pat;
-    for (const char* c = env; *c;) { pat.push_back(std::max(1, std::min(e->host_chunk, atoi(c)))); while (*c && *c != ',') ++c; if (*c) ++c; }
-    for (int rem = n_frames, i = 0; rem > 0 && !pat.empty(); ++i) { int t = std::min(pat[i % pat.size()], rem); stages.push_back(t); rem -= t; }
+  if (!e->tuning.host_stages.empty()) {      // experiment aid (FSUAE_HOST_STAGES at creation): explicit schedule "2,4,8,..." (repeated to cover n_frames)
+    const std::vector<int>& pat = e->tuning.host_stages;
+    for (int rem = n_frames, i = 0; rem > 0; ++i) { int t = std::min(std::min(pat[i % pat.size()], e->host_chunk), rem); stages.push_back(t); rem -= t; }
   } else if (e->stage_seq > 0 && cudaStreamQuery(e->s_out) == cudaErrorNotReady) {
     for (int rem = n_frames; rem > 0; rem -= stages.back()) stages.push_back(std::min(e->host_chunk, rem));
   } else {
@@ -325,9 +365,7 @@ int fsuae_engine_submit_host(fsuae_engine* e, const void* in_host, void* out_hos
     if (ce == cudaSuccess && reused) ce = cudaStreamWaitEvent(e->s_comp, e->ev_out[b], 0);
     if (ce != cudaSuccess) { rc = set_error(e, FSUAE_ERR_CUDA, cudaGetErrorString(ce)); break; }
     const int64_t launches = e->launches;
-    rc = e->precision == FSUAE_PREC_FP32
-             ? fp32_enqueue_chunk(e, e->d_stage_in[b], e->d_stage_out[b], n, in_fmt, out_fmt, flags, e->s_comp)
-             : bf16_enqueue_chunk(e, e->d_stage_in[b], e->d_stage_out[b], n, in_fmt, out_fmt, flags, e->s_comp);
+    rc = enqueue_chunk(e, e->d_stage_in[b], e->d_stage_out[b], n, in_fmt, out_fmt, flags, e->s_comp);
     (void)launches;
     if (rc != FSUAE_OK) break;
     ce = cudaEventRecord(e->ev_comp[b], e->s_comp);

@@ -31,6 +31,30 @@
 #include "engine.h"
 #include "tc_ptx.cuh"
 
+// This translation unit is compiled twice: as the bf16 build and, with -DFSUAE_OPERAND_FP16, as the fp16 build
+// (same kernels, fp16 A/B operands: the precision the reference deploys, convertion_tools/torch2onnx.py:58, 358-412).
+#ifdef FSUAE_OPERAND_FP16
+#define TC_FN(name) fp16_##name
+#define TC_FIELD fp16
+#define TcPlan Fp16Plan
+#define TC_VARIANT_NAME "fp16_tcgen05"
+#define TC_BUILD_TAG "fp16 build: "
+#else
+#define TC_FN(name) bf16_##name
+#define TC_FIELD bf16
+#define TcPlan Bf16Plan
+#define TC_VARIANT_NAME "bf16_tcgen05"
+#define TC_BUILD_TAG "bf16 build: "
+#endif
+
+// Experiment switches that make a launch produce garbage (bound analysis of DESIGN.md section 5) exist only in builds
+// with -DFSUAE_DEBUG_SWITCHES; the production library has no such code path.
+#ifdef FSUAE_DEBUG_SWITCHES
+#define FSUAE_DBG_BIT(P, bit) (((P).dbg & (bit)) != 0)
+#else
+#define FSUAE_DBG_BIT(P, bit) false
+#endif
+
 namespace fsuae {
 
 namespace {
@@ -207,12 +231,22 @@ struct Epi {
   }
 };
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+// two activations -> one 32-bit word of the operand type (bf16, or fp16 with -DFSUAE_OPERAND_FP16) and back
+#ifdef FSUAE_OPERAND_FP16
+__device__ __forceinline__ uint32_t pack_op2(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float op_lo(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xFFFFu))); }
+__device__ __forceinline__ float op_hi(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
+#else
+__device__ __forceinline__ uint32_t pack_op2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
-__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
-__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+__device__ __forceinline__ float op_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float op_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+#endif
 
 __device__ __forceinline__ uint8_t to_u8_fast(float v, int gamma_out) {
   if (gamma_out) v = __powf(fmaxf(v, 0.f), 1.0f / 2.2f);
@@ -236,7 +270,7 @@ __device__ __forceinline__ void act_chain_rt(uint32_t ops, const float* __restri
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const uint32_t w = (&skc.x)[i >> 1];
-        o[i] += (i & 1) ? bf16_hi(w) : bf16_lo(w);
+        o[i] += (i & 1) ? op_hi(w) : op_lo(w);
       }
     }
     const int op = (int)((ops >> (8 * s)) & 0xFFu);
@@ -290,7 +324,7 @@ __device__ __forceinline__ void epi_chain8(uint32_t ops, const float* __restrict
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const uint32_t w = (&skc.x)[i >> 1];
-        o[i] += (i & 1) ? bf16_hi(w) : bf16_lo(w);
+        o[i] += (i & 1) ? op_hi(w) : op_lo(w);
       }
     }
     act_slot8<EPI::kOp2>(2, prm, stride, o);
@@ -324,7 +358,7 @@ __device__ __forceinline__ void softmax_row_rt(uint32_t taddr, int nplanes, int 
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const uint32_t w = (&skc.x)[i >> 1];
-          o[i] += (i & 1) ? bf16_hi(w) : bf16_lo(w);
+          o[i] += (i & 1) ? op_hi(w) : op_lo(w);
         }
       }
       if (pass == 0) {
@@ -469,8 +503,8 @@ __global__ void __launch_bounds__(NTHREADS_L, 1) conv3x3_tc_kernel(const __grid_
           mbar_wait(&empty[slot], par);
 #endif
           uint8_t* d = s_ring + slot * C::ROWBYTES;
-          const int kk = (P.dbg & 2) ? 0 : k;
-          if (P.dbg & 4) {      // timing experiment: one plane only (results are garbage)
+          const int kk = FSUAE_DBG_BIT(P, 2) ? 0 : k;
+          if (FSUAE_DBG_BIT(P, 4)) {      // timing experiment: one plane only (results are garbage)
             mbar_arrive_expect_tx(&full[slot], PLANE_ROW);
             tma_load_1d(d, g0 + (size_t)kk * row_pitch, PLANE_ROW, &full[slot]);
             if (++slot == C::RING) { slot = 0; par ^= 1; }
@@ -519,7 +553,7 @@ __global__ void __launch_bounds__(NTHREADS_L, 1) conv3x3_tc_kernel(const __grid_
     // ======================= MMA issuers (leader CTA of a pair, or the only CTA) =======================
     if (elect_one()) {
       const uint32_t me = warp == 1 ? 0u : 1u;       // issuer 0 takes the even input rows of the CTA's row sequence, issuer 1 the odd ones
-      constexpr uint32_t IDESC = umma_idesc_bf16(MROWS * CTAS, NPAD);
+      constexpr uint32_t IDESC = umma_idesc_op(MROWS * CTAS, NPAD);
       auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
         if constexpr (CTAS == 2) umma_bf16_2cta(d, a, b, idesc, acc); else umma_bf16(d, a, b, idesc, acc);
       };
@@ -550,7 +584,7 @@ __global__ void __launch_bounds__(NTHREADS_L, 1) conv3x3_tc_kernel(const __grid_
         const uint32_t w3_lo = ((smem_u32(s_w) & 0x3FFFFu) >> 4) | ((uint32_t)((N3 * 16) >> 4) << 16);
         uint32_t blk0 = 0, grow3 = 0, tokpar3 = 0;
         constexpr bool TWO3 = FSUAE_TWO_ISSUERS != 0;       // the two issuing warps take the input rows in turn, as in the row-major order below
-        constexpr uint32_t IDESC0 = umma_idesc_bf16(MROWS, 0);             // N field (bits 17..22, N >> 3) added per run
+        constexpr uint32_t IDESC0 = umma_idesc_op(MROWS, 0);             // N field (bits 17..22, N >> 3) added per run
         constexpr uint32_t IDN = (uint32_t)(NPAD >> 3) << 17;
         while (it.next(P, sg)) {
           const int rows = sg.rows;
@@ -657,7 +691,7 @@ __global__ void __launch_bounds__(NTHREADS_L, 1) conv3x3_tc_kernel(const __grid_
             const uint32_t d0 = tmem_base + sk * NPAD, d1 = tmem_base + s1 * NPAD, d2 = tmem_base + s2 * NPAD;
             const uint32_t a_row = ring_lo + rs * (C::ROWBYTES >> 4);
             const uint64_t hi = (uint64_t)HI << 32;
-            if (P.dbg & 8) {
+            if (FSUAE_DBG_BIT(P, 8)) {
               // timing experiment: no MMAs at all (garbage results): what the barrier / commit chain alone costs
             } else if (v0 && v1 && v2) {
 #pragma unroll
@@ -776,7 +810,7 @@ __global__ void __launch_bounds__(NTHREADS_L, 1) conv3x3_tc_kernel(const __grid_
     while (it.next(P, sg)) {
       const int f = sg.f, s = sg.s, y0 = sg.y0, rows = sg.rows;
       const int x = s * STRIP + m;
-      const bool valid = m < STRIP && x < P.Ww && !(P.dbg & 1);
+      const bool valid = m < STRIP && x < P.Ww && !FSUAE_DBG_BIT(P, 1);
       for (int b = 0; b < rows; ++b, ++blk) {
         if ((blk & (EPI_WG - 1)) != group) continue;
         const uint32_t stage = blk % C::STAGES, spar = (blk / C::STAGES) & 1u;
@@ -854,14 +888,14 @@ __global__ void __launch_bounds__(NTHREADS_L, 1) conv3x3_tc_kernel(const __grid_
               float t = EPI::pre(P, ch, __uint_as_float(v[i]) + P.bias[ch]);
               if constexpr (EPI::kSkip) {
                 const uint32_t w = (&sk[c].x)[i >> 1];
-                t += (i & 1) ? bf16_hi(w) : bf16_lo(w);
+                t += (i & 1) ? op_hi(w) : op_lo(w);
               }
               t = EPI::post(P, ch, t);
               o[i] = t;
             }
             if (valid) {
-              uint4 pk = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
-                                    pack_bf16x2(o[6], o[7]));
+              uint4 pk = make_uint4(pack_op2(o[0], o[1]), pack_op2(o[2], o[3]), pack_op2(o[4], o[5]),
+                                    pack_op2(o[6], o[7]));
               *reinterpret_cast<uint4*>(dp + (size_t)c * plane_pitch) = pk;
             }
           }
@@ -888,7 +922,7 @@ __global__ void __launch_bounds__(NTHREADS_L, 1) conv3x3_tc_kernel(const __grid_
             auto emit = [&](int c, const float (&o)[8]) {
               if (valid)
                 *reinterpret_cast<uint4*>(dp + (size_t)c * plane_pitch) =
-                    make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+                    make_uint4(pack_op2(o[0], o[1]), pack_op2(o[2], o[3]), pack_op2(o[4], o[5]), pack_op2(o[6], o[7]));
             };
             softmax_row_rt(taddr, P.out_planes, P.cout, ops_packed, P.dparams, MAXC, EPI::kSkip || P.skip != nullptr,
                            SoftmaxCfg{P.softmax_slot, P.softmax_log}, load_skip, emit);
@@ -920,8 +954,8 @@ __global__ void __launch_bounds__(NTHREADS_L, 1) conv3x3_tc_kernel(const __grid_
               for (int i = 0; i < 8; ++i) o[i] = (c * 8 + i < P.cout) ? o[i] : 0.f;
             }
             if (valid) {
-              uint4 pk = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
-                                    pack_bf16x2(o[6], o[7]));
+              uint4 pk = make_uint4(pack_op2(o[0], o[1]), pack_op2(o[2], o[3]), pack_op2(o[4], o[5]),
+                                    pack_op2(o[6], o[7]));
               *reinterpret_cast<uint4*>(dp + (size_t)c * plane_pitch) = pk;
             }
             EPI_T(t_g);
@@ -1203,7 +1237,7 @@ conv3x3_tc_fused_pair_kernel(const __grid_constant__ LayerK A, const __grid_cons
   } else if (warp == 1) {
     // ======================= leader: MMA issue for both layers =======================
     if (elect_one()) {
-      constexpr uint32_t IDA = umma_idesc_bf16(2 * MROWS, NA), IDB = umma_idesc_bf16(2 * MROWS, NBP);
+      constexpr uint32_t IDA = umma_idesc_op(2 * MROWS, NA), IDB = umma_idesc_op(2 * MROWS, NBP);
       const uint32_t ra_lo = (smem_u32(s_ra) & 0x3FFFFu) >> 4, rb_lo = (smem_u32(s_rb) & 0x3FFFFu) >> 4;
       const uint32_t wa_lo = ((smem_u32(s_wa) & 0x3FFFFu) >> 4) | ((uint32_t)((C::NBA * 16) >> 4) << 16);
       const uint32_t wb_lo = ((smem_u32(s_wb) & 0x3FFFFu) >> 4) | ((uint32_t)((C::NBB * 16) >> 4) << 16);
@@ -1301,7 +1335,7 @@ conv3x3_tc_fused_pair_kernel(const __grid_constant__ LayerK A, const __grid_cons
               o[e] = inframe ? t : 0.f;         // B's conv sees zero padding outside the frame
             }
             *reinterpret_cast<uint4*>(dp + c * PLANE_ROW) =
-                make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+                make_uint4(pack_op2(o[0], o[1]), pack_op2(o[2], o[3]), pack_op2(o[4], o[5]), pack_op2(o[6], o[7]));
           }
           fence_proxy_async_smem();             // generic-proxy stores -> visible to the tensor core's reads
           tc_fence_before();
@@ -1341,13 +1375,13 @@ conv3x3_tc_fused_pair_kernel(const __grid_constant__ LayerK A, const __grid_cons
                 float t = EPIB::pre(P, ch, __uint_as_float(v[e]) + P.bias[ch]);
                 if constexpr (EPIB::kSkip) {
                   const uint32_t w = (&sk[c].x)[e >> 1];
-                  t += (e & 1) ? bf16_hi(w) : bf16_lo(w);
+                  t += (e & 1) ? op_hi(w) : op_lo(w);
                 }
                 o[e] = EPIB::post(P, ch, t);
               }
               if (valid)
                 *reinterpret_cast<uint4*>(dp + (size_t)c * plane_pitch) =
-                    make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+                    make_uint4(pack_op2(o[0], o[1]), pack_op2(o[2], o[3]), pack_op2(o[4], o[5]), pack_op2(o[6], o[7]));
             }
             tc_fence_before();
             __syncwarp();
@@ -1418,9 +1452,9 @@ __global__ void head_unshuffle_bf16_kernel(const void* __restrict__ in, unsigned
       }
     }
     unsigned char* dp = dst + (size_t)f * fs_dst + (size_t)(h + BORDER) * row_pitch + (size_t)(w + BORDER) * 16;
-    *reinterpret_cast<uint4*>(dp) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                                               pack_bf16x2(v[6], v[7]));
-    *reinterpret_cast<uint4*>(dp + plane_pitch) = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), 0u, 0u);
+    *reinterpret_cast<uint4*>(dp) = make_uint4(pack_op2(v[0], v[1]), pack_op2(v[2], v[3]), pack_op2(v[4], v[5]),
+                                               pack_op2(v[6], v[7]));
+    *reinterpret_cast<uint4*>(dp + plane_pitch) = make_uint4(pack_op2(v[8], v[9]), pack_op2(v[10], v[11]), 0u, 0u);
   }
 }
 
@@ -1453,7 +1487,7 @@ __global__ void head_plain_bf16_kernel(const void* __restrict__ in, unsigned cha
       v[0] = lut[ip[0]]; v[1] = lut[ip[fpl]]; v[2] = lut[ip[2 * fpl]];
     }
     unsigned char* dp = dst + (size_t)f * fs_dst + (size_t)(h + BORDER) * row_pitch + (size_t)(w + BORDER) * 16;
-    *reinterpret_cast<uint4*>(dp) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], 0.f), 0u, 0u);
+    *reinterpret_cast<uint4*>(dp) = make_uint4(pack_op2(v[0], v[1]), pack_op2(v[2], 0.f), 0u, 0u);
   }
 }
 
@@ -1480,13 +1514,33 @@ __global__ void black_columns_bf16_kernel(void* __restrict__ out, int n_frames, 
 // host: weight packing, kernel table, plan
 // ------------------------------------------------------------------------------------------------
 
-uint16_t f2bf(float f) {   // round to nearest even, like __float2bfloat16_rn
+#ifdef FSUAE_OPERAND_FP16
+uint16_t f2op(float f) {   // float -> IEEE half, round to nearest even (like __float2half_rn), subnormals kept, overflow -> inf
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  const uint32_t sign = (u >> 16) & 0x8000u;
+  u &= 0x7FFFFFFFu;
+  if (u >= 0x7F800000u) return (uint16_t)(sign | 0x7C00u | (u > 0x7F800000u ? 0x200u : 0u));
+  if (u >= 0x477FF000u) return (uint16_t)(sign | 0x7C00u);                  // rounds to >= 65520 -> inf
+  if (u < 0x33000001u) return (uint16_t)sign;                               // <= 2^-25 -> 0
+  const int e = (int)(u >> 23) - 127;
+  uint32_t man = (u & 0x7FFFFFu) | 0x800000u;
+  int shift = e < -14 ? 13 + (-14 - e) : 13;                                // subnormal halves lose more bits
+  uint32_t half_man = man >> shift;
+  const uint32_t rem = man & ((1u << shift) - 1u), halfway = 1u << (shift - 1);
+  if (rem > halfway || (rem == halfway && (half_man & 1u))) ++half_man;
+  uint32_t out = e < -14 ? half_man : (((uint32_t)(e + 15) << 10) + (half_man - 0x400u));   // mantissa carry bumps the exponent
+  return (uint16_t)(sign | out);
+}
+#else
+uint16_t f2op(float f) {   // round to nearest even, like __float2bfloat16_rn
   uint32_t u;
   std::memcpy(&u, &f, 4);
   if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);
   u += 0x7FFFu + ((u >> 16) & 1u);
   return (uint16_t)(u >> 16);
 }
+#endif
 
 // B operand of instruction (dy, st): [2 halves][NPAD rows][8 k]; half h <-> unit u = 2 st + h (see the kernel for the odd tail),
 // chunk j = u / 3 (plane of the concatenated sources), tap dx = u % 3, channels 8j .. 8j+7.
@@ -1510,7 +1564,7 @@ std::vector<uint16_t> pack_weights(const float* w, int cout, int cin0, int cin1,
             if (j < P0) { ci = j * 8 + k; if (ci >= cin0) continue; }
             else { ci = (j - P0) * 8 + k; if (ci >= cin1) continue; ci += cin0; }
             const float v = w[((size_t)n * cin + ci) * 9 + dy * 3 + dx];
-            out[(size_t)(n / NB) * 3 * steps_row * NB * 16 + (((size_t)(dy * steps_row + st) * 2 + h) * NB + n % NB) * 8 + k] = f2bf(v);
+            out[(size_t)(n / NB) * 3 * steps_row * NB * 16 + (((size_t)(dy * steps_row + st) * 2 + h) * NB + n % NB) * 8 + k] = f2op(v);
           }
       }
   return out;
@@ -1539,7 +1593,7 @@ std::vector<uint16_t> pack_weights_r3(const float* w, int cout, int cin0, int ci
             if (j < P0) { ci = j * 8 + k; if (ci >= cin0) continue; }
             else { ci = (j - P0) * 8 + k; if (ci >= cin1) continue; ci += cin0; }
             const float v = w[((size_t)n * cin + ci) * 9 + (2 - b) * 3 + dx];
-            out[(((size_t)st * 2 + h) * N3 + b * NPAD + n) * 8 + k] = f2bf(v);
+            out[(((size_t)st * 2 + h) * N3 + b * NPAD + n) * 8 + k] = f2op(v);
           }
     }
   return out;
@@ -1661,7 +1715,7 @@ struct LayerPlan {
 
 }  // namespace
 
-struct Bf16Plan {
+struct TcPlan {
   std::vector<LayerPlan> layers;
   std::vector<unsigned char*> buf;     // chunk-planar activation buffers, id 0..n_layers-1 (the last layer writes the frame)
   std::vector<int> planes;
@@ -1676,6 +1730,7 @@ struct Bf16Plan {
 static int planes_of(int c) { return (c + 7) / 8; }
 
 // debugging aid (not part of the public header): raw chunk-planar bytes of activation buffer `id`
+#ifndef FSUAE_OPERAND_FP16
 extern "C" __attribute__((visibility("default"))) long long fsuae_debug_read_bf16_buffer(fsuae_engine* e, int id, void* dst,
                                                                                         long long max_bytes) {
   if (!e || !e->bf16 || id < 0 || id >= (int)e->bf16->buf.size()) return -1;
@@ -1684,8 +1739,9 @@ extern "C" __attribute__((visibility("default"))) long long fsuae_debug_read_bf1
   if (cudaMemcpy(dst, e->bf16->buf[id], n, cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
   return n;
 }
+#endif
 
-#ifdef FSUAE_EPI_TIMING
+#if defined(FSUAE_EPI_TIMING) && !defined(FSUAE_OPERAND_FP16)
 extern "C" __attribute__((visibility("default"))) int fsuae_debug_epi_timing(unsigned long long* out8, int reset) {   // 16 counters
   cudaDeviceSynchronize();
   if (cudaMemcpyFromSymbol(out8, g_epi_timing, sizeof(g_epi_timing)) != cudaSuccess) return -1;
@@ -1694,11 +1750,11 @@ extern "C" __attribute__((visibility("default"))) int fsuae_debug_epi_timing(uns
 }
 #endif
 
-int bf16_create(fsuae_engine* e) {
+int TC_FN(create)(fsuae_engine* e) {
   const fsuae_net_desc& d = e->desc;
   const bool unshuffle = d.head == FSUAE_HEAD_UNSHUFFLE2;
-  Bf16Plan* plan = new Bf16Plan();
-  e->bf16 = plan;
+  TcPlan* plan = new TcPlan();
+  e->TC_FIELD = plan;
   std::vector<int> ch(d.n_layers + 1);
   ch[0] = unshuffle ? 12 : 3;
   for (int i = 0; i < d.n_layers; ++i) ch[i + 1] = d.layers[i].cout;
@@ -1708,7 +1764,7 @@ int bf16_create(fsuae_engine* e) {
     const fsuae_layer_desc& L = d.layers[i];
     LayerPlan& lp = plan->layers[i];
     const bool last = i == d.n_layers - 1;
-    const std::string tag = "bf16 build: layer " + std::to_string(i + 1) + ": ";
+    const std::string tag = std::string(TC_BUILD_TAG) + "layer " + std::to_string(i + 1) + ": ";
     const int P0 = planes_of(L.cin0), P1 = L.cin1 > 0 ? planes_of(L.cin1) : 0, PT = P0 + P1;
     int ops[4] = {0, 0, 0, 0};
     if (L.n_pre > 2 || L.n_post > 2) return set_error(e, FSUAE_ERR_UNSUPPORTED, tag + "at most 2 activation slots before and after the skip add");
@@ -1759,8 +1815,7 @@ int bf16_create(fsuae_engine* e) {
     // Layers whose weights / full-depth input rows do not fit beside each other in shared memory stream K through the
     // wide tile kernel (thin-input layers are cheap to split over output-channel groups instead).
     const bool too_wide = !var || var->NPAD < need;
-    const bool use_wide = !exact && !getenv("FSUAE_NO_WIDE") &&
-                          ((too_wide && (PT >= 4 || !var)) || (getenv("FSUAE_FORCE_WIDE") != nullptr));
+    const bool use_wide = !exact && !e->tuning.no_wide && ((too_wide && (PT >= 4 || !var)) || e->tuning.force_wide);
     if (use_wide) {
       const int ngroups = kind == EPI_STORE ? (need + 127) / 128 : 1;
       if (softmax_slot >= 0 && ngroups > 1)
@@ -1862,8 +1917,7 @@ int bf16_create(fsuae_engine* e) {
       // prologue of the single issuing thread eat the difference.
       const bool matched = var == exact || var == fit_ops;      // op-codes compiled in: sibling kernels exist for the same signature
       const bool r3_default = var->KIND == EPI_TAIL_PLAIN;      // N = 16 tails: clear win (conv3 lightweight tail 21.7 -> see profiles)
-      const char* r3_env = getenv("FSUAE_R3");
-      if (matched && (r3_env ? atoi(r3_env) != 0 : r3_default)) {
+      if (matched && (e->tuning.r3 >= 0 ? e->tuning.r3 != 0 : r3_default)) {
         for (const Variant& v : variants())
           if (v.R3 && v.PT == var->PT && v.NPAD == var->NPAD && v.COUT == var->COUT && v.KIND == var->KIND && v.skip == var->skip &&
               v.pre0 == var->pre0 && v.pre1 == var->pre1 && v.post0 == var->post0 && v.post1 == var->post1)
@@ -1876,7 +1930,7 @@ int bf16_create(fsuae_engine* e) {
           FSUAE_CUDA_CHECK(e, cudaFuncSetAttribute((const void*)ln.var3->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ln.var3->smem));
         }
       }
-      if (matched && !getenv("FSUAE_NO_PAIRS")) {
+      if (matched && !e->tuning.no_pairs) {
         for (const Variant& v : variants())
           if (v.CTAS == 2 && !v.R3 && v.PT == var->PT && v.NPAD == var->NPAD && v.COUT == var->COUT && v.KIND == var->KIND &&
               v.skip == var->skip && v.pre0 == var->pre0 && v.pre1 == var->pre1 && v.post0 == var->post0 && v.post1 == var->post1)
@@ -1894,7 +1948,7 @@ int bf16_create(fsuae_engine* e) {
     FSUAE_CUDA_CHECK(e, cudaFuncSetAttribute((const void*)var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, var->smem));
   }
   // conv3 -> conv4 of the flagship preset can run as one fused kernel on CTA pairs
-  if (!getenv("FSUAE_NO_FUSION")) {
+  if (!e->tuning.no_fusion) {
     using FusedEpiA = Epi<0, 0, 0, 0, false>;
     using FusedEpiB = Epi<FSUAE_ACT_MISH, FSUAE_ACT_BIASED_PRELU, FSUAE_ACT_TANH, FSUAE_ACT_RELU, true>;
     for (int i = 0; i + 1 < d.n_layers - 1; ++i) {
@@ -1936,24 +1990,24 @@ int bf16_create(fsuae_engine* e) {
     plan->buf_bytes[i] = bytes;
     e->device_bytes += bytes;
   }
-  e->variant = "bf16_tcgen05";
+  e->variant = TC_VARIANT_NAME;
   return FSUAE_OK;
 }
 
-void bf16_destroy(fsuae_engine* e) {
-  if (!e->bf16) return;
-  for (auto& lp : e->bf16->layers)
+void TC_FN(destroy)(fsuae_engine* e) {
+  if (!e->TC_FIELD) return;
+  for (auto& lp : e->TC_FIELD->layers)
     for (auto& ln : lp.launches)
       { if (ln.d_w) cudaFree(ln.d_w); if (ln.d_w2) cudaFree(ln.d_w2); if (ln.d_w3) cudaFree(ln.d_w3); if (ln.d_params) cudaFree(ln.d_params); }
-  for (unsigned char* p : e->bf16->buf)
+  for (unsigned char* p : e->TC_FIELD->buf)
     if (p) cudaFree(p);
-  delete e->bf16;
-  e->bf16 = nullptr;
+  delete e->TC_FIELD;
+  e->TC_FIELD = nullptr;
 }
 
-int bf16_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in_fmt, int out_fmt, uint32_t flags,
-                       cudaStream_t st) {
-  Bf16Plan* plan = e->bf16;
+int TC_FN(enqueue_chunk)(fsuae_engine* e, const void* in, void* out, int n, int in_fmt, int out_fmt, uint32_t flags,
+                          cudaStream_t st) {
+  TcPlan* plan = e->TC_FIELD;
   const fsuae_net_desc& d = e->desc;
   const Geom g = make_geom(e, flags);
   const int S = (g.Ww + STRIP - 1) / STRIP, PW = plane_width(S);
@@ -1964,7 +2018,11 @@ int bf16_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in
   }
   // FSUAE_DBG & 16 (timing experiment, garbage results): every frame aliases frame 0's activation buffers, so all
   // inter-layer traffic stays in L2 -- what the pass would cost if the layers did not stream through HBM
+#ifdef FSUAE_DEBUG_SWITCHES
   const bool alias_frames = getenv("FSUAE_DBG") && (atoi(getenv("FSUAE_DBG")) & 16);
+#else
+  const bool alias_frames = false;
+#endif
   auto fstride = [&](int id) { return alias_frames ? 0ull : (unsigned long long)plan->planes[id] * (g.Hw + 2 * BORDER) * PW * 16; };
 
   const int gin = (flags & FSUAE_FLAG_GAMMA_IN) ? 1 : 0;
@@ -1992,12 +2050,14 @@ int bf16_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in
     k.H = g.H; k.W = g.W; k.xoff = g.xoff;
     k.gamma_in = gin;
     k.gamma_out = (flags & FSUAE_FLAG_GAMMA_OUT) ? 1 : 0;
+#ifdef FSUAE_DEBUG_SWITCHES
     if (const char* dbg = getenv("FSUAE_DBG")) k.dbg = atoi(dbg);
+#endif
     return k;
   };
   auto launch_cfg = [&](cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int n_blocks, int ctas, int smem, int threads = NTHREADS) {
     int grid = std::min(n_blocks * ctas, e->sm_count / ctas * ctas);
-    if (const char* g_env = getenv("FSUAE_DEBUG_GRID")) grid = std::max(ctas, std::min(n_blocks * ctas, atoi(g_env) / ctas * ctas));   // debugging aid: force the CTA count
+    if (e->tuning.grid > 0) grid = std::max(ctas, std::min(n_blocks * ctas, e->tuning.grid / ctas * ctas));   // test aid (FSUAE_DEBUG_GRID at creation): force the CTA count
     cfg = cudaLaunchConfig_t{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(threads);

@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_wide_kernel(const __gr
   } else if (warp == 1) {
     // ======================= MMA issuer (leader) =======================
     if (elect_one()) {
-      constexpr uint32_t IDESC = umma_idesc_bf16(2 * MROWS, NT);
+      constexpr uint32_t IDESC = umma_idesc_op(2 * MROWS, NT);
       constexpr uint32_t HI = (uint32_t)((128u >> 4)) | (1u << 14);                  // SBO = 128 B, descriptor version 1
       constexpr uint32_t A_LBO = (uint32_t)(PLANE_ROW >> 4) << 16;                   // second K half = the other plane of the row
       constexpr uint32_t B_LBO = (uint32_t)(((NT / 2) * 16) >> 4) << 16;
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_wide_kernel(const __gr
           auto emit = [&](int c, const float (&o)[8]) {
             if (valid)
               *reinterpret_cast<uint4*>(dp + (size_t)c * plane_pitch) =
-                  make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+                  make_uint4(pack_op2(o[0], o[1]), pack_op2(o[2], o[3]), pack_op2(o[4], o[5]), pack_op2(o[6], o[7]));
           };
           softmax_row_rt(taddr, nplanes, P.cout, ops_packed, P.dparams + ch0, P.cpad, has_skip, SoftmaxCfg{P.softmax_slot, P.softmax_log},
                          load_skip, emit);
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_wide_kernel(const __gr
           }
           if (valid)
             *reinterpret_cast<uint4*>(dp + (size_t)c * plane_pitch) =
-                make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+                make_uint4(pack_op2(o[0], o[1]), pack_op2(o[2], o[3]), pack_op2(o[4], o[5]), pack_op2(o[6], o[7]));
         }
       } else if constexpr (KIND == EPI_TAIL_SHUFFLE) {
         // ---- 12 channels -> PixelShuffle(2) + network input + ReLU straight to the frame (model_pix_shuffle.py:293-296) ----
@@ -379,7 +379,7 @@ std::vector<uint16_t> pack_weights_wide(const float* w, int cout, int cin0, int 
                 if (j < P0) { ci = j * 8 + k; if (ci >= cin0) continue; }
                 else { ci = (j - P0) * 8 + k; if (ci >= cin1) continue; ci += cin0; }
                 const float v = w[((size_t)n * cin + ci) * 9 + tap];
-                out[(((((size_t)(ng * kchunks + kc) * 2 + r) * 9 + tap) * 2 + h) * NB + nn) * 8 + k] = f2bf(v);
+                out[(((((size_t)(ng * kchunks + kc) * 2 + r) * 9 + tap) * 2 + h) * NB + nn) * 8 + k] = f2op(v);
               }
             }
           }

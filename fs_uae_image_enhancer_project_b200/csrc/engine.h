@@ -12,6 +12,22 @@
 namespace fsuae {
 
 struct Bf16Plan;  // bf16_tc.cu
+struct Fp16Plan;  // bf16_tc.cu built with -DFSUAE_OPERAND_FP16
+
+// Experiment / test switches.  They are read from the environment ONCE, when an engine is created, and every one that is
+// set is appended to fsuae_engine_variant(); no launch reads the environment.  None is needed in production.
+struct Tuning {
+  int grid = 0;                 // FSUAE_DEBUG_GRID=n: CTA count of the persistent tensor-core kernels (partition tests)
+  int r3 = -1;                  // FSUAE_R3=0|1: three-output-rows-per-instruction kernels for no / every layer that has one
+  bool no_fusion = false;       // FSUAE_NO_FUSION: conv3 -> conv4 as two kernels
+  bool no_pairs = false;        // FSUAE_NO_PAIRS: single-CTA kernels only
+  bool no_wide = false;         // FSUAE_NO_WIDE / FSUAE_FORCE_WIDE: K-streamed wide kernel off / for every layer without a
+  bool force_wide = false;      //   compile-time variant
+  bool no_mega = false;         // FSUAE_NO_MEGA: never use the single fused pass (layer-by-layer kernels only)
+  int mega_min_frames = -1;     // FSUAE_MEGA_MIN_FRAMES=n: smallest pass the fused kernel takes
+  std::vector<int> host_stages; // FSUAE_HOST_STAGES=a,b,...: stage sizes of the host-buffer pipeline
+  std::string tag;              // " [FSUAE_R3=1 ...]" for the variant string
+};
 
 }  // namespace fsuae
 
@@ -39,8 +55,10 @@ struct fsuae_engine {
   std::vector<float*> f32_buf;      // [n_layers + 1]
   std::vector<int> buf_channels;    // channels of each buffer
 
-  // bf16 build
+  // tensor-core builds (bf16 / fp16 operands)
   fsuae::Bf16Plan* bf16 = nullptr;
+  fsuae::Fp16Plan* fp16 = nullptr;
+  fsuae::Tuning tuning;
 
   // optional per-launch timing (fsuae_engine_set_profiling)
   bool profiling = false;
@@ -104,7 +122,22 @@ void bf16_destroy(fsuae_engine* e);
 int bf16_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in_fmt, int out_fmt,
                        uint32_t flags, cudaStream_t st);
 
+// fp16 build (bf16_tc.cu with -DFSUAE_OPERAND_FP16)
+int fp16_create(fsuae_engine* e);
+void fp16_destroy(fsuae_engine* e);
+int fp16_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in_fmt, int out_fmt,
+                       uint32_t flags, cudaStream_t st);
+
 int set_error(fsuae_engine* e, int code, const std::string& msg);
+
+inline int enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in_fmt, int out_fmt, uint32_t flags,
+                         cudaStream_t st) {
+  switch (e->precision) {
+    case FSUAE_PREC_FP32: return fp32_enqueue_chunk(e, in, out, n, in_fmt, out_fmt, flags, st);
+    case FSUAE_PREC_BF16: return bf16_enqueue_chunk(e, in, out, n, in_fmt, out_fmt, flags, st);
+    default: return fp16_enqueue_chunk(e, in, out, n, in_fmt, out_fmt, flags, st);
+  }
+}
 
 // bracket one kernel launch with events when profiling is on
 struct ProfScope {

@@ -3,6 +3,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -83,9 +84,15 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
-// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// kind::f16 instruction descriptor: 16-bit operands (bf16, or fp16 when the translation unit is built with
+// -DFSUAE_OPERAND_FP16) -> fp32 accumulator, both operands K-major.  Bits 7..9 / 10..12 = A / B format (0 = f16, 1 = bf16).
+#ifdef FSUAE_OPERAND_FP16
+#define FSUAE_UMMA_AB_FORMAT 0u
+#else
+#define FSUAE_UMMA_AB_FORMAT ((1u << 7) | (1u << 10))
+#endif
+__host__ __device__ constexpr uint32_t umma_idesc_op(int M, int N) {
+  return (1u << 4) | FSUAE_UMMA_AB_FORMAT | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,

@@ -15,8 +15,11 @@ from .engine import Engine
 class FusedEnhancer(nn.Module):
     """Subclasses provide ``_layer_specs()``, ``_head`` and ``_tail``.
 
-    * fp32 parameters -> the fp32 FMA build; after ``.half()`` / ``.bfloat16()`` -> the bf16
-      tensor-core build (``precision`` can also be forced with ``set_precision``).
+    * fp32 parameters -> the fp32 FMA build; after ``.half()`` -> the fp16 tensor-core build (what the
+      reference deploys, torch2onnx.py:58); after ``.bfloat16()`` -> the bf16 tensor-core build
+      (``precision`` can also be forced with ``set_precision``).  Any other parameter dtype raises.
+    * ``load_state_dict`` accepts genuine reference checkpoints: the ``perceptual_criterion.*`` entries
+      (the VGG16 of the training loss, saved by train.py:236/246 with every ``state_dict``) are dropped.
     * Engines are cached per (device, H, W, precision) and rebuilt when a parameter changes
       (``load_state_dict``, optimiser step, ``.to``).
     * CUDA tensors only.  There is no CPU path: a CPU tensor raises.
@@ -37,15 +40,28 @@ class FusedEnhancer(nn.Module):
 
     # -- engine management --------------------------------------------------------------------
     def set_precision(self, precision: Optional[str]):
-        """Force 'fp32' or 'bf16' regardless of the parameter dtype (None: follow the parameters)."""
-        self._forced_precision = {None: None, "fp32": L.PREC_FP32, "bf16": L.PREC_BF16}[precision]
+        """Force 'fp32', 'fp16' or 'bf16' regardless of the parameter dtype (None: follow the parameters)."""
+        self._forced_precision = {None: None, "fp32": L.PREC_FP32, "bf16": L.PREC_BF16, "fp16": L.PREC_FP16}[precision]
         return self
 
     def _precision(self) -> int:
         if self._forced_precision is not None:
             return self._forced_precision
         p = next(self.parameters())
-        return L.PREC_FP32 if p.dtype == torch.float32 else L.PREC_BF16
+        try:
+            return {torch.float32: L.PREC_FP32, torch.float16: L.PREC_FP16, torch.bfloat16: L.PREC_BF16}[p.dtype]
+        except KeyError:
+            raise TypeError(f"parameters are {p.dtype}: the engine has fp32, fp16 and bf16 builds only") from None
+
+    # -- checkpoints ----------------------------------------------------------------------------
+    _IGNORED_STATE_PREFIXES = ("perceptual_criterion.",)
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kwargs):
+        """Reference checkpoints carry the training loss's VGG16 (`self.perceptual_criterion = PerceptualLoss(...)`,
+        model_pix_shuffle.py:172-182; saved by train.py:236/246): those keys are not part of the network and are
+        dropped, so `m.load_state_dict(torch.load('best.pth'))` works with the default strict=True."""
+        kept = {k: v for k, v in state_dict.items() if not k.startswith(self._IGNORED_STATE_PREFIXES)}
+        return super().load_state_dict(kept, strict=strict, **kwargs)
 
     def _stamp(self):
         return tuple((id(p), p._version, p.dtype, p.device) for p in list(self.parameters()) + list(self.buffers()))

@@ -55,6 +55,7 @@ extern "C" {
 #define FSUAE_ABI_VERSION 1
 #define FSUAE_MAX_LAYERS 16
 #define FSUAE_MAX_ACTS 4 /* activation slots before / after the skip add (reference uses <= 2) */
+#define FSUAE_MAX_CHUNK_FRAMES 1024 /* upper bound of fsuae_engine_create's max_chunk_frames */
 
 /* status codes */
 enum {
@@ -132,7 +133,9 @@ typedef struct fsuae_net_desc {
 /* arithmetic builds */
 enum {
   FSUAE_PREC_FP32 = 0, /* fp32 FMA kernels, accurate libm activations */
-  FSUAE_PREC_BF16 = 1  /* bf16 operands on tcgen05 tensor cores, fp32 accumulate + epilogue */
+  FSUAE_PREC_BF16 = 1, /* bf16 operands on tcgen05 tensor cores, fp32 accumulate + epilogue */
+  FSUAE_PREC_FP16 = 2  /* fp16 operands on the same tensor-core kernels (tcgen05 kind::f16, same rate, 8x finer mantissa):
+                          the precision the reference deploys (convertion_tools/torch2onnx.py:58 .half(), :358-412 Cast) */
 };
 
 /* frame formats at the boundary (all row-major, contiguous) */
@@ -218,7 +221,9 @@ FSUAE_API int fsuae_synth_rgb444_frames(void* out_dev_rgba, int n_frames, int he
 FSUAE_API size_t fsuae_engine_device_bytes(const fsuae_engine* e);
 /* Number of kernel launches the last enqueue / run_host issued (bench.py's gpu_launches). */
 FSUAE_API int64_t fsuae_engine_last_launch_count(const fsuae_engine* e);
-/* Name of the kernel variant the engine selected, e.g. "fp32_fma" / "bf16_tcgen05". */
+/* Name of the kernel variant the engine selected, e.g. "fp32_fma" / "bf16_tcgen05" / "fp16_tcgen05"; experiment
+ * switches found in the environment when the engine was created (FSUAE_R3, FSUAE_NO_PAIRS, ... -- read once, never per
+ * launch) are listed behind it in brackets. */
 FSUAE_API const char* fsuae_engine_variant(const fsuae_engine* e);
 
 /* Optional per-kernel timing (measurement aid for bench.py's roofline line, no reference counterpart): when

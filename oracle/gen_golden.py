@@ -127,7 +127,43 @@ def gen_quantize_cases():
     os.chmod(os.path.join(GOLD, "quantize.npz"), 0o644)
 
 
+def gen_round2_fixtures():
+    """Added in round 2 (own option: the earlier fixtures keep their bytes): the other five screenshots + shipped
+    predictions of pix_shuffle, conv3_heavy's trained weights with two of its shipped predictions, and the names of the
+    `perceptual_criterion.*` state_dict entries a genuine reference checkpoint carries (train.py:236/246 saves
+    model.state_dict(); every reference Model owns a PerceptualLoss with a torchvision VGG16, loss_vgg.py:60)."""
+    for i in range(8):
+        for src, dst in ((f"model/samples/sample{i}.png", "samples"),
+                         (f"model/model_pix_shuffle/predicted/sample{i}.png", "predicted_pix_shuffle")):
+            os.makedirs(os.path.join(GOLD, dst), exist_ok=True)
+            if not os.path.exists(os.path.join(GOLD, dst, f"sample{i}.png")):
+                shutil.copy(os.path.join(REF, src), os.path.join(GOLD, dst))
+    os.makedirs(os.path.join(GOLD, "predicted_conv3_heavy"), exist_ok=True)
+    for i in (5, 6):
+        shutil.copy(os.path.join(REF, f"model/model_conv3_heavy/predicted/sample{i}.png"), os.path.join(GOLD, "predicted_conv3_heavy"))
+        shutil.copy(os.path.join(REF, f"model/model_conv3/predicted/sample{i}.png"), os.path.join(GOLD, "predicted_conv3"))
+    sd3 = onnx_weights.conv3_state_dict_from_onnx(os.path.join(REF, "model/model_conv3_heavy/conv3_heavy.onnx"))
+    np.savez_compressed(os.path.join(GOLD, "conv3_heavy_trained_fp16.npz"),
+                        **{k: (v.numpy().astype(np.float16) if v.dtype.is_floating_point else v.numpy()) for k, v in sd3.items()})
+    # key names of the loss module inside a reference checkpoint: PerceptualLoss.vgg = torchvision vgg16 (loss_vgg.py:60);
+    # torchvision is present here, the ImageNet weights are not needed for the names
+    import torchvision
+    vgg = torchvision.models.vgg16(weights=None)
+    keys = ["perceptual_criterion.vgg." + k for k in vgg.state_dict()]
+    shapes = [list(v.shape) for v in vgg.state_dict().values()]
+    import json
+    with open(os.path.join(GOLD, "reference_checkpoint_loss_keys.json"), "w") as f:
+        json.dump({"keys": keys, "shapes": shapes}, f)
+    for root, _, files in os.walk(GOLD):
+        for f in files:
+            os.chmod(os.path.join(root, f), 0o644)
+    print(f"round-2 fixtures written: 8 screenshots, conv3_heavy weights, {len(keys)} loss-module keys")
+
+
 def main():
+    if "--only-round2" in sys.argv:
+        gen_round2_fixtures()
+        return
     if "--only-quantize" in sys.argv:
         gen_quantize_cases()
         return
@@ -206,6 +242,7 @@ def main():
                     os.path.join(GOLD, "predicted_conv3"))
     gen_projection_cases(mps)
     gen_quantize_cases()
+    gen_round2_fixtures()
     for root, _, files in os.walk(GOLD):
         for f in files:
             os.chmod(os.path.join(root, f), 0o644)

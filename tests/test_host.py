@@ -72,6 +72,58 @@ def test_pix_shuffle_state_dict_keys_match_reference(preset):
     assert model_pix_shuffle.get_model("nope") is None
 
 
+@pytest.mark.parametrize("family", ["pix_shuffle", "conv3", "conv5"])
+def test_genuine_reference_checkpoints_load_with_strict_true(family):
+    """train.py:236/246 saves model.state_dict() of a Model that owns `perceptual_criterion` (a PerceptualLoss with a
+    torchvision VGG16, loss_vgg.py:60): real best.pth files carry those keys.  README quick-start:
+    m.load_state_dict(torch.load('best.pth')) -- default strict=True -- must work."""
+    import json
+    from fs_uae_image_enhancer_project_b200 import model_conv3, model_conv5, model_pix_shuffle
+    from tests.util import GOLD
+    extra = json.load(open(os.path.join(GOLD, "reference_checkpoint_loss_keys.json")))
+    if family == "pix_shuffle":
+        m = model_pix_shuffle.get_model("lightweight")
+        sd = O.make_pix_shuffle_state_dict(O.pix_shuffle_preset("lightweight"), 3)
+    else:
+        mod, chans = (model_conv3, O.conv3_channels) if family == "conv3" else (model_conv5, O.conv5_channels)
+        m = mod.get_model("lightweight")
+        sd = O.make_bn_state_dict(chans("lightweight"), 3)
+    ckpt = dict(sd)
+    for k, shape in zip(extra["keys"], extra["shapes"]):
+        ckpt[k] = torch.zeros([min(d, 2) for d in shape])           # contents are irrelevant: the entries are dropped
+    assert any(k.startswith("perceptual_criterion.vgg.features.") for k in ckpt)
+    res = m.load_state_dict(ckpt)                                   # strict=True
+    assert not res.missing_keys and not res.unexpected_keys
+    assert all(torch.equal(m.state_dict()[k], v) for k, v in sd.items())
+    with pytest.raises(RuntimeError, match="Unexpected key"):
+        m.load_state_dict({**sd, "bogus.weight": torch.zeros(1)})   # anything else unexpected still raises
+
+
+def test_parameter_dtype_selects_the_build():
+    from fs_uae_image_enhancer_project_b200 import _lib, model_pix_shuffle
+    m = model_pix_shuffle.get_model("lightweight")
+    assert m._precision() == _lib.PREC_FP32
+    assert m.half()._precision() == _lib.PREC_FP16          # what the reference deploys (torch2onnx.py:58)
+    assert m.bfloat16()._precision() == _lib.PREC_BF16
+    with pytest.raises(TypeError, match="fp32, fp16 and bf16"):
+        m.double()._precision()
+    assert m.set_precision("fp16")._precision() == _lib.PREC_FP16
+    with pytest.raises(KeyError):
+        m.set_precision("int8")
+
+
+def test_create_rejects_bad_precision_and_oversized_chunk():
+    from fs_uae_image_enhancer_project_b200 import _lib, model_pix_shuffle
+    from fs_uae_image_enhancer_project_b200.descriptor import build_descriptor
+    from fs_uae_image_enhancer_project_b200.engine import Engine
+    m = model_pix_shuffle.get_model("lightweight")
+    desc, blob = build_descriptor(m._layer_specs(), m._head, m._tail)
+    with pytest.raises(ValueError, match="precision"):
+        Engine(desc, blob, 0, 7, 576, 752)
+    with pytest.raises(ValueError, match="max_chunk_frames"):
+        Engine(desc, blob, 0, _lib.PREC_FP32, 576, 752, _lib.MAX_CHUNK_FRAMES + 1)
+
+
 def test_conv3_conv5_state_dict_keys_and_param_counts():
     from fs_uae_image_enhancer_project_b200 import model_conv3, model_conv5
     for mod, chans, counts in ((model_conv3, O.conv3_channels, (21222, 455366)),
@@ -205,6 +257,14 @@ def test_engine_file_roundtrip_and_create_from_file_errors(tmp_path):
     assert b"malformed" in lib.fsuae_last_error(None)
     with pytest.raises(ValueError):
         export.read_engine_file(str(bad))
+    # a header whose float count disagrees with the file (truncated blob / absurd count) is refused before any allocation
+    good = open(path, "rb").read()
+    for name, data in (("trunc.fsuae", good[:-4000]),
+                       ("huge.fsuae", good[:12] + (0xFFFFFFF0).to_bytes(4, "little") + good[16:])):
+        q = tmp_path / name
+        q.write_bytes(data)
+        assert lib.fsuae_engine_create_from_file(str(q).encode(), 0, _lib.PREC_FP32, 576, 752, 4, C.byref(h)) == _lib.ERR_INVALID
+        assert b"malformed" in lib.fsuae_last_error(None)
 
 
 def test_raw_framebuffer_loader_validates_size(tmp_path):

@@ -17,6 +17,9 @@ FP32_TOL = 1e-5          # fp32 build vs fp32 oracle, float output in [0,~1.2]
 FP32_TOL_255 = 2e-3      # conv3 output scale 0..255
 BF16_TOL = 1e-2          # bf16 build max-abs
 BF16_PSNR = 55.0         # bf16 build PSNR (peak 1.0)
+FP16_TOL = 2e-3          # fp16 build max-abs (PyTorch's own fp16 run: 5.6e-4)
+FP16_PSNR = 68.0         # fp16 build PSNR (PyTorch's own: 78 dB)
+TC_GATES = {"bf16": (BF16_TOL, BF16_PSNR), "fp16": (FP16_TOL, FP16_PSNR)}
 
 
 def dev():
@@ -130,27 +133,52 @@ def test_fp32_framebuffer_contract_full_size(crop16):
     assert torch.equal(host, got)
 
 
-@pytest.mark.parametrize("i", [1, 5, 6])
-def test_fp32_trained_weights_reproduce_shipped_screenshots(i):
+# The reference's only result-pinning artefacts: its trained fp16 weights map model/samples/sample{0..7}.png onto
+# the shipped model/model_pix_shuffle/predicted/sample{0..7}.png.  Gates per build: (max LSB, PSNR dB, share within 1 LSB).
+# fp32 / fp16: the survey's golden-PNG bar (<= 4 LSB, >= 60 dB).  bf16: 8 mantissa bits on near-black linear values are
+# amplified by the 1/2.2 gamma (slope ~13 at L = 0.002), so its gate is wider and stated as measured -- `.half()` (what the
+# reference deploys) selects the fp16 build, which meets the golden bar.
+SCREENSHOT_GATES = {"fp32": (4, 60.0, 0.98), "fp16": (4, 60.0, 0.98), "bf16": (16, 48.0, 0.95)}
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp16", "bf16"])
+def test_trained_weights_reproduce_all_eight_shipped_screenshots(prec):
     sd = trained_pix_shuffle_sd()
     spec = O.pix_shuffle_preset("lightweight")
-    m = build_pkg_pix_shuffle(spec, sd).to(dev())
-    rgba = load_png_rgba(os.path.join(GOLD, "samples", f"sample{i}.png"))
-    want = load_png_rgb(os.path.join(GOLD, "predicted_pix_shuffle", f"sample{i}.png"))
-    got = m.forward_framebuffer(rgba.to(dev())).cpu()[..., :3].permute(0, 3, 1, 2)
-    assert O.psnr(got, want, 255.0) >= 60.0
-    assert (got.int() - want.int()).abs().max().item() <= 4
+    m = build_pkg_pix_shuffle(spec, sd).to(dev()).set_precision(prec)
+    max_lsb, min_psnr, min_within1 = SCREENSHOT_GATES[prec]
+    worst = []
+    for i in range(8):
+        rgba = load_png_rgba(os.path.join(GOLD, "samples", f"sample{i}.png"))
+        want = load_png_rgb(os.path.join(GOLD, "predicted_pix_shuffle", f"sample{i}.png"))
+        got = m.forward_framebuffer(rgba.to(dev())).cpu()[..., :3].permute(0, 3, 1, 2)
+        d = (got.int() - want.int()).abs()
+        stats = (d.max().item(), O.psnr(got, want, 255.0), (d <= 1).float().mean().item(), (d == 0).float().mean().item())
+        print(f"{prec} trained sample{i}: max {stats[0]} LSB, psnr {stats[1]:.1f} dB, <=1 LSB {stats[2]:.4f}, exact {stats[3]:.4f}")
+        worst.append(stats)
+    assert max(w[0] for w in worst) <= max_lsb
+    assert min(w[1] for w in worst) >= min_psnr
+    assert min(w[2] for w in worst) >= min_within1
 
 
-def test_fp32_trained_conv3_reproduces_shipped_screenshots():
+@pytest.mark.parametrize("preset,prec,max_lsb,min_psnr", [
+    ("lightweight", "fp32", 1, 60.0), ("lightweight", "fp16", 2, 58.0), ("lightweight", "bf16", 4, 48.0),
+    ("heavyweight", "fp32", 1, 60.0), ("heavyweight", "fp16", 2, 58.0), ("heavyweight", "bf16", 4, 46.0)])
+def test_trained_conv3_reproduces_shipped_screenshots(preset, prec, max_lsb, min_psnr):
+    """conv3.onnx / conv3_heavy.onnx weights on samples 5 and 6 against model_conv3*/predicted (clamp -> truncate)."""
     from fs_uae_image_enhancer_project_b200 import model_conv3
-    m = model_conv3.get_model("lightweight")
-    m.load_state_dict(trained_conv3_sd())
-    m = m.to(dev())
-    x = load_png_rgba(os.path.join(GOLD, "samples", "sample5.png")).permute(0, 3, 1, 2).contiguous()
-    want = load_png_rgba(os.path.join(GOLD, "predicted_conv3", "sample5.png")).permute(0, 3, 1, 2)
-    got = m(x.to(dev())).cpu().clamp(0, 255).to(torch.uint8)
-    assert (got.int() - want.int()).abs().max().item() <= 1
+    from tests.util import trained_conv3_heavy_sd
+    m = model_conv3.get_model(preset)
+    m.load_state_dict(trained_conv3_sd() if preset == "lightweight" else trained_conv3_heavy_sd())
+    m = m.to(dev()).set_precision(prec)
+    pred = "predicted_conv3" if preset == "lightweight" else "predicted_conv3_heavy"
+    for i in (5, 6):
+        x = load_png_rgba(os.path.join(GOLD, "samples", f"sample{i}.png")).permute(0, 3, 1, 2).contiguous()
+        want = load_png_rgba(os.path.join(GOLD, pred, f"sample{i}.png")).permute(0, 3, 1, 2)
+        got = m(x.to(dev())).float().cpu().clamp(0, 255).to(torch.uint8)
+        d = (got.int() - want.int()).abs()
+        print(f"conv3 {preset} {prec} sample{i}: max {d.max().item()} LSB, psnr {O.psnr(got, want, 255.0):.1f} dB")
+        assert d.max().item() <= max_lsb and O.psnr(got, want, 255.0) >= min_psnr
 
 
 def test_fp32_full_size_properties():
@@ -185,6 +213,48 @@ def _bf16_model(spec, sd):
     return build_pkg_pix_shuffle(spec, sd).to(dev()).set_precision("bf16")
 
 
+def _tc_model(spec, sd, prec):
+    return build_pkg_pix_shuffle(spec, sd).to(dev()).set_precision(prec)
+
+
+def test_half_selects_the_fp16_build_and_bfloat16_the_bf16_build():
+    """`.half()` is what the reference deploys (torch2onnx.py:58): fp16 operands on the tensor cores; `.bfloat16()` -> bf16."""
+    spec = O.pix_shuffle_preset("lightweight")
+    sd = O.make_pix_shuffle_state_dict(spec, 5)
+    x = torch.rand(2, 3, 32, 48, generator=torch.Generator().manual_seed(1))
+    want = O.pix_shuffle_forward(sd, spec, x)
+    mh = build_pkg_pix_shuffle(spec, sd).to(dev()).half()
+    yh = mh(x.to(dev()).half())
+    assert yh.dtype == torch.float16 and mh.engine_for(dev(), 32, 48).variant == "fp16_tcgen05"
+    assert (yh.float().cpu() - want).abs().max().item() <= FP16_TOL + 1e-3      # + fp16 rounding of the returned tensor
+    mb = build_pkg_pix_shuffle(spec, sd).to(dev()).bfloat16()
+    yb = mb(x.to(dev()).bfloat16())
+    assert yb.dtype == torch.bfloat16 and mb.engine_for(dev(), 32, 48).variant == "bf16_tcgen05"
+    with pytest.raises(TypeError, match="fp32, fp16 and bf16"):
+        build_pkg_pix_shuffle(spec, sd).to(dev()).double()(x.to(dev()).double())
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("name", ["vocab_a", "vocab_b", "proj_a", "heavyweight"])
+def test_tc_builds_run_the_whole_activation_registry(name, prec):
+    """Run-time tcgen05 epilogues on every registry name: vocab_a = gelu, leaky_relu(slope), silu/swish, per-channel
+    biased_relu(C) and prelu(C), sigmoid, elu, relu, softplus, scalar biased_prelu, scaled_tanh, relu6, telu, tanh;
+    vocab_b = mish, sinlu, softmax, log_softmax, elu(alpha), prelu(1), gelu; proj_a = 1x1 skip projections."""
+    g = load_gold(f"pix_shuffle_{name}")
+    spec = gold_spec(name)
+    sd = O.make_pix_shuffle_state_dict(spec, int(g["seed"]))
+    m = _tc_model(spec, sd, prec)
+    got = m(torch.from_numpy(g["x"]).to(dev())).cpu()
+    want = torch.from_numpy(g["y"])
+    tol, psnr = TC_GATES[prec]
+    if name == "vocab_b":                       # log_softmax amplifies operand rounding
+        tol, psnr = 2 * tol, psnr - 5.0
+    err, p = (got - want).abs().max().item(), O.psnr(got, want, 1.0)
+    print(f"{prec} {name}: max|d| {err:.2e}, psnr {p:.1f} dB")
+    assert m.engine_for(dev(), 44, 60).variant == f"{prec}_tcgen05"
+    assert err <= tol and p >= psnr
+
+
 @pytest.mark.parametrize("shape", [(1, 16, 16), (2, 64, 96), (1, 40, 300), (3, 34, 254), (1, 6, 508), (2, 2, 2)])
 def test_bf16_pix_shuffle_small_frames(shape):
     """Single strip, exactly-two-strips (W/2 = 127), three strips, 1-pixel-high maps."""
@@ -198,26 +268,20 @@ def test_bf16_pix_shuffle_small_frames(shape):
     assert m.engine_for(dev(), H, W).variant == "bf16_tcgen05"
     assert (got - want).abs().max().item() <= BF16_TOL
     assert O.psnr(got, want, 1.0) >= BF16_PSNR
+    mh = _tc_model(spec, sd, "fp16")
+    got = mh(x.to(dev())).cpu()
+    assert mh.engine_for(dev(), H, W).variant == "fp16_tcgen05"
+    assert (got - want).abs().max().item() <= FP16_TOL and O.psnr(got, want, 1.0) >= FP16_PSNR
 
 
-def test_bf16_matches_reference_vectors_and_trained_weights():
+def test_tc_builds_match_reference_vectors():
     g = load_gold("pix_shuffle_lightweight")
     spec = gold_spec("lightweight")
     sd = O.make_pix_shuffle_state_dict(spec, int(g["seed"]))
     got = _bf16_model(spec, sd)(torch.from_numpy(g["x"]).to(dev())).cpu().numpy()
     assert np.abs(got - g["y"]).max() <= BF16_TOL
-    # trained weights on a real Amiga screenshot vs the shipped prediction (u8, <= 6 LSB, PSNR >= 50 dB)
-    m = _bf16_model(spec, trained_pix_shuffle_sd())
-    rgba = load_png_rgba(os.path.join(GOLD, "samples", "sample5.png"))
-    want = load_png_rgb(os.path.join(GOLD, "predicted_pix_shuffle", "sample5.png"))
-    out = m.forward_framebuffer(rgba.to(dev())).cpu()[..., :3].permute(0, 3, 1, 2)
-    d = (out.int() - want.int()).abs()
-    print(f"bf16 trained sample5: max {d.max().item()} LSB, psnr {O.psnr(out, want, 255.0):.1f} dB, "
-          f"<=1 LSB {(d <= 1).float().mean().item():.4f}")
-    # bf16 rounding of near-black linear values is amplified by the 1/2.2 gamma (slope ~13 at L=0.002)
-    assert d.max().item() <= 16
-    assert O.psnr(out, want, 255.0) >= 48.0
-    assert (d <= 1).float().mean().item() >= 0.97
+    goth = _tc_model(spec, sd, "fp16")(torch.from_numpy(g["x"]).to(dev())).cpu().numpy()
+    assert np.abs(goth - g["y"]).max() <= FP16_TOL
 
 
 @pytest.mark.parametrize("crop16", [False, True])
@@ -315,7 +379,7 @@ def test_bf16_pix_shuffle_heavyweight_matches_reference_vectors():
     assert (got - want).abs().max().item() <= BF16_TOL and O.psnr(got, want, 1.0) >= BF16_PSNR
 
 
-def test_bf16_conv3_lightweight_matches_reference_vectors_and_screenshot():
+def test_bf16_conv3_lightweight_matches_reference_vectors():
     from fs_uae_image_enhancer_project_b200 import model_conv3
     g = load_gold("conv3_lightweight")
     m = model_conv3.get_model("lightweight")
@@ -325,14 +389,6 @@ def test_bf16_conv3_lightweight_matches_reference_vectors_and_screenshot():
     want = torch.from_numpy(g["y"])
     assert y.shape == want.shape and (y[:, 3] == 255.0).all()
     assert (y - want).abs().max().item() <= 255 * BF16_TOL and O.psnr(y, want, 255.0) >= 50.0
-    # trained weights on a real screenshot, full frame (6 strips at full resolution)
-    m = model_conv3.get_model("lightweight")
-    m.load_state_dict(trained_conv3_sd())
-    m = m.to(dev()).set_precision("bf16")
-    x = load_png_rgba(os.path.join(GOLD, "samples", "sample5.png")).permute(0, 3, 1, 2).contiguous()
-    want = load_png_rgba(os.path.join(GOLD, "predicted_conv3", "sample5.png")).permute(0, 3, 1, 2)
-    got = m(x.to(dev())).float().cpu().clamp(0, 255).to(torch.uint8)
-    assert (got.int() - want.int()).abs().max().item() <= 4 and O.psnr(got, want, 255.0) >= 48.0
 
 
 @pytest.mark.parametrize("preset", ["lightweight", "heavyweight"])
@@ -355,11 +411,12 @@ def test_bf16_partition_independence(grid, monkeypatch):
     spec = O.pix_shuffle_preset("lightweight")
     sd = O.make_pix_shuffle_state_dict(spec, 61)
     x = torch.rand(1, 3, 8, 752, generator=torch.Generator().manual_seed(5))
-    m = _bf16_model(spec, sd)
-    base = m(x.to(dev())).cpu()
+    base = _bf16_model(spec, sd)(x.to(dev())).cpu()
     assert (base - O.pix_shuffle_forward(sd, spec, x)).abs().max().item() <= BF16_TOL
-    monkeypatch.setenv("FSUAE_DEBUG_GRID", str(grid))
+    monkeypatch.setenv("FSUAE_DEBUG_GRID", str(grid))       # read once, when the engine is created
+    m = _bf16_model(spec, sd)
     assert torch.equal(m(x.to(dev())).cpu(), base)
+    assert f"FSUAE_DEBUG_GRID={grid}" in m.engine_for(dev(), 8, 752).variant
 
 
 def test_engine_file_and_raw_cli_match_the_module(tmp_path):
@@ -450,9 +507,10 @@ def test_bf16_three_rows_per_instruction_kernels(monkeypatch):
     m = _bf16_model(spec, sd)
     got = m(x.to(dev())).cpu()
     assert (got - want).abs().max().item() <= BF16_TOL and O.psnr(got, want, 1.0) >= BF16_PSNR
+    assert "FSUAE_R3=1" in m.engine_for(dev(), 50, 600).variant
     for grid in (1, 3, 7):
         monkeypatch.setenv("FSUAE_DEBUG_GRID", str(grid))
-        assert torch.equal(m(x.to(dev())).cpu(), got)
+        assert torch.equal(_bf16_model(spec, sd)(x.to(dev())).cpu(), got)
 
 
 def test_bf16_arbitrary_channel_plan_with_skip_projections():
@@ -530,3 +588,78 @@ def test_heavyweight_full_size_builds_agree_and_frames_are_independent(family):
     assert (y16[:1] - y32).abs().max().item() <= scale * BF16_TOL and O.psnr(y16[:1].cpu(), y32.cpu(), scale) >= 50.0
     assert torch.equal(y16.flip(0), m16(x.flip(0).contiguous()).float())            # frames are independent
     assert torch.equal(y16[2:3], m16(x[2:3].contiguous()).float())                  # chunking is invisible
+
+
+# ----------------------------------------------------------------------------------------------
+# BASELINE.json configs 2-4 at their own batch sizes, full 752x576 frames, against the ORACLE
+# (two or three frames of each batch are compared: the oracle needs 0.2-1.4 s per frame on the CPU)
+# ----------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_config2_batch64_framebuffers_against_the_oracle(prec):
+    """Config 2: 64 mixed pixel-mode RGB444 framebuffers, u8 in -> u8 out incl. gamma, one pass of 64 frames."""
+    spec = O.pix_shuffle_preset("lightweight")
+    sd = O.make_pix_shuffle_state_dict(spec, 31)
+    fb = O.synth_framebuffers(64, seed=18)
+    m = _tc_model(spec, sd, prec)
+    m.chunk_frames = 64
+    got = m.forward_framebuffer(fb.to(dev())).cpu()
+    assert (got[..., 3] == 255).all()
+    max_lsb, min_exact = (6, 0.85) if prec == "bf16" else (2, 0.97)
+    for i in (0, 29, 63):                       # lores, lores_laced and hires_laced frames
+        want = O.framebuffer_forward(sd, spec, fb[i:i + 1])
+        d = (got[i:i + 1].int() - want.int()).abs()
+        print(f"config2 {prec} frame {i}: max {d.max().item()} LSB, exact {(d == 0).float().mean().item():.4f}")
+        assert d.max().item() <= max_lsb and (d == 0).float().mean().item() >= min_exact
+    again = m.forward_framebuffer(fb.to(dev())).cpu()
+    assert torch.equal(again, got)              # run-to-run identical bits
+    m.chunk_frames = 16                         # a different pass partition gives the same bytes
+    m2 = _tc_model(spec, sd, prec)
+    m2.chunk_frames = 16
+    assert torch.equal(m2.forward_framebuffer(fb[:32].to(dev())).cpu(), got[:32])
+
+
+@pytest.mark.parametrize("preset", ["lightweight", "heavyweight"])
+def test_config3_conv3_batch16_against_the_oracle(preset):
+    """Config 3: model_conv3 / model_conv3_heavy, uint8 [16,4,576,752], fp32 vs bf16 vs fp16 builds vs the fp32 oracle."""
+    from fs_uae_image_enhancer_project_b200 import model_conv3
+    sd = O.make_bn_state_dict(O.conv3_channels(preset), 33)
+    x = torch.randint(0, 256, (16, 4, 576, 752), dtype=torch.uint8, generator=torch.Generator().manual_seed(3))
+    idx = [0, 15]
+    want = O.conv3_forward(sd, x[idx])
+    for prec, tol, psnr in (("fp32", FP32_TOL_255, 100.0), ("bf16", 255 * BF16_TOL, 50.0), ("fp16", 255 * FP16_TOL, 62.0)):
+        m = model_conv3.get_model(preset)
+        m.load_state_dict(sd)
+        m = m.to(dev()).set_precision(prec)
+        y = m(x.to(dev()))
+        assert y.shape == (16, 4, 576, 752) and (y[:, 3] == 255.0).all()
+        got = y[idx].float().cpu()
+        err, p = (got - want).abs().max().item(), O.psnr(got, want, 255.0)
+        print(f"config3 conv3 {preset} {prec}: max|d| {err:.3e} (0..255), psnr {p:.1f} dB")
+        assert err <= tol and p >= psnr
+        del y, m
+        torch.cuda.empty_cache()
+
+
+def test_config4_conv5_heavy_batch32_against_the_oracle():
+    """Config 4: model_conv5 heavyweight, float [32,3,576,752] sRGB in [0,1]."""
+    from fs_uae_image_enhancer_project_b200 import model_conv5
+    sd = O.make_bn_state_dict(O.conv5_channels("heavyweight"), 44)
+    x = torch.rand(32, 3, 576, 752, generator=torch.Generator().manual_seed(4))
+    idx = [0, 31]
+    want = O.conv5_forward(sd, x[idx])
+    for prec, tol, psnr in (("bf16", BF16_TOL, 50.0), ("fp16", FP16_TOL, 65.0)):
+        m = model_conv5.get_model("heavyweight")
+        m.load_state_dict(sd)
+        m = m.to(dev()).set_precision(prec)
+        y = m(x.to(dev()))
+        got = y[idx].float().cpu()
+        err, p = (got - want).abs().max().item(), O.psnr(got, want, 1.0)
+        print(f"config4 conv5 heavyweight {prec}: max|d| {err:.3e}, psnr {p:.1f} dB")
+        assert err <= tol and p >= psnr
+        del y, m
+        torch.cuda.empty_cache()
+    m = model_conv5.get_model("heavyweight")
+    m.load_state_dict(sd)
+    got = m.to(dev())(x[idx].to(dev())).cpu()          # fp32 build on the two compared frames
+    assert (got - want).abs().max().item() <= FP32_TOL

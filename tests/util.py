@@ -31,6 +31,11 @@ def trained_conv3_sd():
     return {k: torch.from_numpy(z[k].astype(np.float32) if z[k].dtype == np.float16 else z[k]) for k in z.files}
 
 
+def trained_conv3_heavy_sd():
+    z = np.load(os.path.join(GOLD, "conv3_heavy_trained_fp16.npz"))
+    return {k: torch.from_numpy(z[k].astype(np.float32) if z[k].dtype == np.float16 else z[k]) for k in z.files}
+
+
 def load_png_rgb(path):
     from PIL import Image
     a = np.asarray(Image.open(path).convert("RGB"))
