@@ -207,8 +207,8 @@ __device__ __forceinline__ void act_rt8(int op, float (&t)[8], const float (&p0)
 }
 
 // OP >= 0: compile-time op (the switch folds away); OP < 0: op-code read from the layer parameters
-template <int OP>
-__device__ __forceinline__ float act_slot(const LayerK& P, int slot, int ch, float x) {
+template <int OP, class PK>
+__device__ __forceinline__ float act_slot(const PK& P, int slot, int ch, float x) {
   if constexpr (OP == FSUAE_ACT_IDENTITY) return x;
   else if constexpr (OP >= 0) return act_rt(OP, x, P.p0[slot][ch], P.p1[slot][ch]);
   else return act_rt(P.op[slot], x, P.p0[slot][ch], P.p1[slot][ch]);
@@ -221,11 +221,13 @@ struct Epi {
   static constexpr bool kSkip = SKIP;
   static constexpr bool kRuntime = PRE0 < 0;      // op-codes come from the layer parameters
   static constexpr int kOp0 = PRE0, kOp1 = PRE1, kOp2 = POST0, kOp3 = POST1;
-  __device__ static __forceinline__ float pre(const LayerK& P, int ch, float v) {
+  template <class PK>      // PK: LayerK, or the fused pass's slimmer per-layer parameter block
+  __device__ static __forceinline__ float pre(const PK& P, int ch, float v) {
     v = act_slot<PRE0>(P, 0, ch, v);
     return act_slot<PRE1>(P, 1, ch, v);
   }
-  __device__ static __forceinline__ float post(const LayerK& P, int ch, float v) {
+  template <class PK>
+  __device__ static __forceinline__ float post(const PK& P, int ch, float v) {
     v = act_slot<POST0>(P, 2, ch, v);
     return act_slot<POST1>(P, 3, ch, v);
   }

@@ -1,0 +1,678 @@
+// The single fused pass of the flagship network (included by bf16_tc.cu inside its anonymous namespace).
+//
+// Reference semantics: model/model_pix_shuffle.py:227-298 executed as ONE persistent kernel -- input normalisation (gamma LUT,
+// PixelUnshuffle), conv1..conv7 with their activation chains / residual adds / the long-skip concat, PixelShuffle, global
+// residual, ReLU, gamma, uint8 pack.  HBM is touched for the input frame and the output frame only: every inter-layer feature
+// map lives in a small ring of image rows that is overwritten in place every few microseconds and therefore never leaves L2.
+//
+// Organisation ("stage pipeline through L2 rings"):
+//   * The layer kernels of bf16_tc.cu stay what they are -- a strip-marching implicit GEMM on a CTA pair (cta_group::2,
+//     two frames in lockstep) with a shared-memory ring of input rows, resident weights and TMEM accumulator stages -- but
+//     here each one is an ENGINE: a set of warps (producer, MMA issuer / peer relay, two or four epilogue warpgroups) with
+//     its own barriers, ring, weights and TMEM columns.  A CTA hosts one or two engines side by side; the hardware warp
+//     scheduler interleaves them, so an MMA-bound layer runs under an activation-bound one:
+//         stage A = conv2 (TeLU, SinLU, BiasedPReLU: SFU-bound)  + conv3 (no activation: tensor-bound)
+//         stage B = conv4 (Mish, BiasedPReLU, Tanh: both)
+//         stage C = conv5 (no activation)                        + conv7 (PixelShuffle tail: store / pow-bound)
+//         stage D = conv6 (Mish)                                 + conv1 (SinLU; its producer warp is also the network head)
+//     MMA instructions per strip row: A 24+24, B 42, C 42+24, D 45+9 -- balanced to within 15 % at N = 48/80.
+//   * 4 stage pairs = 1 group = one 126-column strip of a frame pair; S groups (S strips) = 1 team = whole rows of a frame
+//     pair; the rows of all frame pairs are cut into equal contiguous ranges, one per team.  Where a range starts or ends
+//     inside a frame, layer i recomputes 7-i halo rows (1.3 % extra MMAs at 64 frames) -- teams never talk to each other.
+//   * Engines talk through CHANNELS in global memory: the producer layer's epilogue stores row q of its output into slot
+//     q % D of a D-row ring (chunk-planar, full image width, zero borders baked in exactly as in the per-layer buffers) and
+//     then bumps a per-slot counter (red.release.gpu); the consumer layer's producer warp polls those counters
+//     (ld.acquire.gpu, one coalesced load covers the whole ring) before its TMA bulk copies, and publishes how far it has
+//     read so the ring slot can be overwritten.  All S strips of a row must be complete before any strip of the next layer
+//     reads it (the 3x3 taps reach one column into the neighbouring strips).
+//   * Rings: 12 rows per channel, 32 for conv1 -> conv6 (the long skip spans the whole pipeline): 3.4 MB per frame in flight,
+//     12 frames in flight -> 41 MB, well inside the 126 MB L2.
+#pragma once
+
+constexpr int MG_MAXC = 80;          // widest layer of the flagship (72 -> N = 80)
+constexpr int MG_NCH = 6;            // channels: output of conv1..conv6
+constexpr int MG_DMAX = 32;          // deepest ring (power of two: one warp polls a whole ring)
+constexpr int MG_SMAX = 8;           // strips per row the flag block is laid out for
+constexpr int MG_THREADS = 640;      // 4 service warps + 16 epilogue warps
+constexpr int MG_FLAG_WORDS = MG_NCH * MG_DMAX + MG_NCH * 2 * MG_SMAX;      // per (team, rank): prod[ch][slot], cons[ch][consumer][strip]
+__host__ __device__ constexpr int mg_depth(int ch) { return ch == 0 ? 32 : 12; }
+
+struct MegaLayerP {
+  float bias[MG_MAXC];
+  float p0[4][MG_MAXC];
+  float p1[4][MG_MAXC];
+  const unsigned char* wpack;        // CTA-pair packing of pack_weights(..., ctas = 2)
+};
+
+struct MegaK {
+  int Hw, Ww, PW, S, n_frames, n_fp, teams;
+  int H, W, xoff, in_fmt, out_fmt, gamma_in, gamma_out;
+  const void* frame_in;
+  void* frame_out;
+  unsigned char* scratch;                       // [team][rank]{channel rings}
+  unsigned long long rank_stride;               // bytes of one (team, rank) block; team stride = 2 * rank_stride
+  unsigned long long ch_off[MG_NCH];            // channel c inside the block; plane stride = depth * PW * 16
+  unsigned int* flags;                          // [team][rank][MG_FLAG_WORDS]
+  const unsigned char* zero_row;                // one plane row of zeros (rows above / below the frame)
+  MegaLayerP L[7];
+};
+
+// ---- flags ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const unsigned int* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned int* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned int* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int* mg_prod(unsigned int* fl, int ch) { return fl + ch * MG_DMAX; }
+__device__ __forceinline__ unsigned int* mg_cons(unsigned int* fl, int ch, int consumer) {
+  return fl + MG_NCH * MG_DMAX + (ch * 2 + consumer) * MG_SMAX;
+}
+
+// ---- work partition ---------------------------------------------------------------------------------------------------
+// The n_fp * Hw image rows (frame pair major) are cut into `teams` equal contiguous ranges; a range is walked as segments
+// that stay inside one frame pair.  Layer i (halo h = 7 - i) computes rows [max(0, y0 - h), min(Hw, y0 + rows + h)).
+struct MSeg { int fp, y0, rows; };
+struct MSegIter {
+  int cur, end, Hw;
+  __device__ MSegIter(const MegaK& M, int team) : Hw(M.Hw) {
+    const long long tot = (long long)M.n_fp * M.Hw;
+    cur = (int)(tot * team / M.teams);
+    end = (int)(tot * (team + 1) / M.teams);
+  }
+  __device__ bool next(MSeg& g) {
+    if (cur >= end) return false;
+    g.fp = cur / Hw;
+    g.y0 = cur - g.fp * Hw;
+    g.rows = min(Hw - g.y0, end - cur);
+    cur += g.rows;
+    return true;
+  }
+};
+__device__ __forceinline__ int mg_lo(const MSeg& g, int halo) { return max(0, g.y0 - halo); }
+__device__ __forceinline__ int mg_hi(const MSeg& g, int halo, int Hw) { return min(Hw, g.y0 + g.rows + halo); }
+
+// ---- one engine = one layer ---------------------------------------------------------------------------------------------
+// LAYER 1..7.  Sources: conv1 <- the frame (head), conv{2,3,4,5} <- channel LAYER-2, conv6 <- channels 0 (conv1, long skip)
+// and 4 (conv5), conv7 <- channel 5.  Consumer index inside a channel: conv6 is consumer 1 of channel 0, everything else 0.
+template <int LAYER, int PT_, int NPAD_, int COUT_, int KIND_, class EPI_, int RING_, int STAGES_, int NWG_>
+struct MEng {
+  using EPI = EPI_;
+  static constexpr int L = LAYER, PT = PT_, NPAD = NPAD_, COUT = COUT_, KIND = KIND_, RING = RING_, STAGES = STAGES_, NWG = NWG_;
+  static constexpr int HALO = 7 - LAYER;
+  static constexpr int STEPS_ROW = (3 * PT + 1) / 2, STEPS = 3 * STEPS_ROW, NB = NPAD / 2;
+  static constexpr int WBYTES = STEPS * NB * 32, ROWBYTES = PT * PLANE_ROW;
+  static constexpr int SMEM = WBYTES + RING * ROWBYTES + 128;       // + the 64-byte overrun pad behind the ring (descriptors of the last units reach past it)
+  static constexpr int TCOLS = STAGES * NPAD;
+  static constexpr int NBARS = 3 * RING + 2 * STAGES + 1;           // full, empty, pfull; tfull, tempty; wbar
+  static constexpr int IN0 = LAYER == 1 ? -1 : (LAYER == 6 ? 0 : LAYER - 2);
+  static constexpr int IN1 = LAYER == 6 ? 4 : -1;
+  static constexpr int P0 = LAYER == 6 ? 5 : PT, P1 = LAYER == 6 ? 5 : 0;
+  static constexpr int HALO0 = LAYER == 6 ? 6 : HALO + 1;           // halo of the layer that produced source 0 / 1
+  static constexpr int HALO1 = HALO + 1;
+  static constexpr int CONS0 = LAYER == 6 ? 1 : 0;                  // my consumer index in source channel 0 (source 1: always 0)
+  static constexpr int OUT = LAYER <= 6 ? LAYER - 1 : -1;
+  static constexpr int OUT_PLANES = (COUT + 7) / 8;
+  static constexpr int OUT_NCONS = LAYER == 1 ? 2 : 1;              // conv1's output is read by conv2 and conv6
+  static_assert(STAGES >= NWG && STAGES <= 2 * NWG + 2, "accumulator stages vs epilogue warpgroups");
+  static_assert(RING >= 4 && RING <= 16, "ring depth (one relay lane per slot)");
+  static_assert(NB % 8 == 0, "each CTA of the pair holds whole core matrices of B");
+};
+
+struct MEngSmem {      // shared-memory carve-up of one engine
+  uint8_t* w;
+  uint8_t* ring;
+  uint64_t *full, *empty, *pfull, *tfull, *tempty, *wbar;
+};
+template <class E>
+__device__ __forceinline__ MEngSmem mg_carve(uint8_t* data, uint64_t* bars) {
+  MEngSmem s;
+  s.w = data;
+  s.ring = data + E::WBYTES;
+  s.full = bars;
+  s.empty = bars + E::RING;
+  s.pfull = bars + 2 * E::RING;
+  s.tfull = bars + 3 * E::RING;
+  s.tempty = s.tfull + E::STAGES;
+  s.wbar = s.tempty + E::STAGES;
+  return s;
+}
+template <class E>
+__device__ __forceinline__ void mg_init_bars(const MEngSmem& s) {     // one thread
+  // a ring row is released by the MMA commit and, when the residual is read from it, by the 4 epilogue warps of its block
+  for (int i = 0; i < E::RING; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], E::EPI::kSkip ? 5 : 1); mbar_init(&s.pfull[i], 1); }
+  for (int i = 0; i < E::STAGES; ++i) { mbar_init(&s.tfull[i], 1); mbar_init(&s.tempty[i], 8); }      // 4 epilogue warps in each CTA of the pair
+  mbar_init(s.wbar, 1);
+}
+
+struct MCtx {          // where this CTA sits
+  int team, strip, rank, f;       // f: the frame this CTA works on inside the current segment is 2 * fp + rank (clamped)
+  unsigned char* scratch;         // this (team, rank)'s channel block
+  unsigned int* flags;            // this (team, rank)'s flag block
+};
+
+// Wait until rows [q, q + 1) of channel `ch` are complete in every strip.  Whole warp; caches how far the ring is known to be
+// complete (`upto`, exclusive) so that one coalesced poll releases several rows.
+__device__ __forceinline__ void mg_wait_rows(const MegaK& M, const MCtx& c, int ch, uint32_t q, uint32_t& upto, int lane) {
+  if (q < upto) return;
+  const uint32_t D = (uint32_t)mg_depth(ch), need_per_use = 4u * (uint32_t)M.S;     // 4 epilogue warps per strip bump the counter
+  const unsigned int* prod = mg_prod(c.flags, ch);
+  const long long t0 = clock64();
+  for (;;) {
+    bool ok = false;
+    if ((uint32_t)lane < D) {
+      const uint32_t qq = q + (uint32_t)lane;
+      ok = ld_acquire_gpu(prod + qq % D) >= need_per_use * (qq / D + 1u);
+    }
+    const uint32_t mask = __ballot_sync(0xffffffffu, ok);
+    const uint32_t cnt = (uint32_t)__ffs((int)~mask) - 1u;      // consecutive complete rows from q on (mask is never all ones: D <= 32 and lanes >= D vote 0 ... D == 32: ffs(0) = 0 -> handled below)
+    const uint32_t n = mask == 0xffffffffu ? 32u : cnt;
+    if (n > 0) { upto = q + n; break; }
+    if (clock64() - t0 > (1ll << 31)) __trap();
+    __nanosleep(64);
+  }
+  __syncwarp();
+}
+
+// ---- producer warp: channel rows -> shared-memory ring (TMA) -----------------------------------------------------------
+template <class E>
+__device__ void mg_producer(const MegaK& M, const MCtx& c, const MEngSmem& s, int lane) {
+  static_assert(E::L != 1, "conv1 has its own producer (the head)");
+  const MegaLayerP& LP = M.L[E::L - 1];
+  if (lane == 0) {
+    mbar_arrive_expect_tx(s.wbar, E::WBYTES);
+    tma_load_1d(s.w, LP.wpack + (size_t)c.rank * E::WBYTES, E::WBYTES, s.wbar);
+  }
+  const size_t row_pitch = (size_t)M.PW * 16;
+  const size_t xoff_b = (size_t)(c.strip * STRIP - 1 + BORDER) * 16;       // first slot of this strip's 128-slot window
+  const unsigned char* ch0 = c.scratch + M.ch_off[E::IN0];
+  const size_t pp0 = (size_t)mg_depth(E::IN0) * row_pitch;
+  const unsigned char* ch1 = E::IN1 >= 0 ? c.scratch + M.ch_off[E::IN1 >= 0 ? E::IN1 : 0] : nullptr;
+  const size_t pp1 = (size_t)mg_depth(E::IN1 >= 0 ? E::IN1 : 0) * row_pitch;
+  uint32_t fill = 0;                 // ring fills so far
+  uint32_t qb0 = 0, qb1 = 0;         // sequence number of the first row the source layers produce in this segment
+  uint32_t upto0 = 0, upto1 = 0;
+  MSegIter it(M, c.team);
+  MSeg g;
+  while (it.next(g)) {
+    const int lo = mg_lo(g, E::HALO), hi = mg_hi(g, E::HALO, M.Hw);
+    const int lo0 = mg_lo(g, E::HALO0), lo1 = mg_lo(g, E::HALO1);
+    for (int y = lo - 1; y <= hi; ++y) {       // input rows of output rows lo .. hi-1
+      const uint32_t slot = fill % E::RING, par = ((fill / E::RING) & 1u) ^ 1u;
+      const bool inframe = y >= 0 && y < M.Hw;
+      const uint32_t q0 = qb0 + (uint32_t)(y - lo0), q1 = qb1 + (uint32_t)(y - lo1);
+      if (lane == 0) {
+        mbar_wait(&s.empty[slot], par);
+        // the row that lived in this slot has been consumed by the MMAs, so every row more than RING fills back has been
+        // read: tell the producing layer(s) that everything below q - RING may be overwritten
+        if (fill >= (uint32_t)E::RING) {
+          const uint32_t qq0 = inframe ? q0 : (y < 0 ? qb0 : qb0 + (uint32_t)(mg_hi(g, E::HALO0, M.Hw) - lo0));
+          if (qq0 > (uint32_t)E::RING) st_release_gpu(mg_cons(c.flags, E::IN0, E::CONS0) + c.strip, qq0 - (uint32_t)E::RING);
+          if constexpr (E::IN1 >= 0) {
+            const uint32_t qq1 = inframe ? q1 : (y < 0 ? qb1 : qb1 + (uint32_t)(mg_hi(g, E::HALO1, M.Hw) - lo1));
+            if (qq1 > (uint32_t)E::RING) st_release_gpu(mg_cons(c.flags, E::IN1 >= 0 ? E::IN1 : 0, 0) + c.strip, qq1 - (uint32_t)E::RING);
+          }
+        }
+      }
+      __syncwarp();
+      if (inframe) {
+        mg_wait_rows(M, c, E::IN0, q0, upto0, lane);
+        if constexpr (E::IN1 >= 0) mg_wait_rows(M, c, E::IN1 >= 0 ? E::IN1 : 0, q1, upto1, lane);
+      }
+      if (lane == 0) {
+        fence_proxy_async_all();               // the rows were written through the generic proxy (other SMs' epilogues)
+        uint8_t* d = s.ring + slot * E::ROWBYTES;
+        mbar_arrive_expect_tx(&s.full[slot], E::ROWBYTES);
+        if (inframe) {
+          const unsigned char* g0 = ch0 + (size_t)(q0 % (uint32_t)mg_depth(E::IN0)) * row_pitch + xoff_b;
+#pragma unroll 1
+          for (int j = 0; j < E::P0; ++j) tma_load_1d(d + j * PLANE_ROW, g0 + (size_t)j * pp0, PLANE_ROW, &s.full[slot]);
+          if constexpr (E::IN1 >= 0) {
+            const unsigned char* g1 = ch1 + (size_t)(q1 % (uint32_t)mg_depth(E::IN1 >= 0 ? E::IN1 : 0)) * row_pitch + xoff_b;
+#pragma unroll 1
+            for (int j = 0; j < E::P1; ++j) tma_load_1d(d + (E::P0 + j) * PLANE_ROW, g1 + (size_t)j * pp1, PLANE_ROW, &s.full[slot]);
+          }
+        } else {
+#pragma unroll 1
+          for (int j = 0; j < E::PT; ++j) tma_load_1d(d + j * PLANE_ROW, M.zero_row, PLANE_ROW, &s.full[slot]);
+        }
+      }
+      ++fill;
+    }
+    qb0 += (uint32_t)(mg_hi(g, E::HALO0, M.Hw) - lo0);
+    qb1 += (uint32_t)(mg_hi(g, E::HALO1, M.Hw) - lo1);
+  }
+}
+
+// ---- producer warp of conv1 = the network head: frame -> gamma LUT -> PixelUnshuffle(2) -> ring rows, no TMA -------------
+// 128 slots per strip row, 4 per lane; a slot is one half-resolution pixel = 2x2 full-resolution pixels x RGB = 12 channels
+// = plane 0 (8 channels) + plane 1 (4 channels, 4 zeros).  Out-of-frame slots are zero (the conv's zero padding).
+template <class E>
+__device__ void mg_producer_head(const MegaK& M, const MCtx& c, const MEngSmem& s, const float* s_lut, int lane) {
+  static_assert(E::L == 1 && E::PT == 2, "head feeds conv1");
+  const MegaLayerP& LP = M.L[0];
+  if (lane == 0) {
+    mbar_arrive_expect_tx(s.wbar, E::WBYTES);
+    tma_load_1d(s.w, LP.wpack + (size_t)c.rank * E::WBYTES, E::WBYTES, s.wbar);
+  }
+  const size_t fpl = (size_t)M.H * M.W;
+  uint32_t fill = 0;
+  MSegIter it(M, c.team);
+  MSeg g;
+  while (it.next(g)) {
+    const int f = min(2 * g.fp + c.rank, M.n_frames - 1);
+    const int lo = mg_lo(g, E::HALO), hi = mg_hi(g, E::HALO, M.Hw);
+    for (int y = lo - 1; y <= hi; ++y) {
+      const uint32_t slot = fill % E::RING, par = ((fill / E::RING) & 1u) ^ 1u;
+      // issue this row's global loads first, wait for the ring slot afterwards
+      uint32_t raw[4][2][6];          // [slot of this lane][dy][2 pixels x 3 channels: f32 bits, or one u8x4 word per pixel in [0], [1]]
+      bool ok[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = lane + 32 * i;
+        const int x = c.strip * STRIP - 1 + m;
+        ok[i] = y >= 0 && y < M.Hw && x >= 0 && x < M.Ww;
+        if (ok[i]) {
+#pragma unroll
+          for (int dy = 0; dy < 2; ++dy) {
+            const size_t p0 = (size_t)(2 * y + dy) * M.W + 2 * x + M.xoff;
+            if (M.in_fmt == FSUAE_FMT_F32_NCHW3) {
+              const float* ip = (const float*)M.frame_in + (size_t)f * 3 * fpl + p0;
+#pragma unroll
+              for (int ch = 0; ch < 3; ++ch) {
+                const float2 t2 = __ldg(reinterpret_cast<const float2*>(ip + ch * fpl));
+                raw[i][dy][2 * ch] = __float_as_uint(t2.x); raw[i][dy][2 * ch + 1] = __float_as_uint(t2.y);
+              }
+            } else if (M.in_fmt == FSUAE_FMT_U8_NHWC4) {
+              const uint2 t2 = __ldg(reinterpret_cast<const uint2*>((const unsigned char*)M.frame_in + ((size_t)f * fpl + p0) * 4));
+              raw[i][dy][0] = t2.x; raw[i][dy][1] = t2.y;
+            } else {
+              const unsigned char* ip = (const unsigned char*)M.frame_in + (size_t)f * 4 * fpl + p0;
+#pragma unroll
+              for (int ch = 0; ch < 3; ++ch) { raw[i][dy][2 * ch] = __ldg(ip + ch * fpl); raw[i][dy][2 * ch + 1] = __ldg(ip + ch * fpl + 1); }
+            }
+          }
+        }
+      }
+      if (lane == 0) mbar_wait(&s.empty[slot], par);
+      __syncwarp();
+      uint8_t* d = s.ring + slot * E::ROWBYTES;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = lane + 32 * i;
+        float v[12];
+        if (ok[i]) {
+#pragma unroll
+          for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+              float a, b;
+              if (M.in_fmt == FSUAE_FMT_F32_NCHW3) { a = __uint_as_float(raw[i][dy][2 * ch]); b = __uint_as_float(raw[i][dy][2 * ch + 1]); }
+              else if (M.in_fmt == FSUAE_FMT_U8_NHWC4) { a = s_lut[(raw[i][dy][0] >> (8 * ch)) & 0xFF]; b = s_lut[(raw[i][dy][1] >> (8 * ch)) & 0xFF]; }
+              else { a = s_lut[raw[i][dy][2 * ch] & 0xFF]; b = s_lut[raw[i][dy][2 * ch + 1] & 0xFF]; }
+              v[ch * 4 + dy * 2] = a; v[ch * 4 + dy * 2 + 1] = b;
+            }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 12; ++k) v[k] = 0.f;
+        }
+        *reinterpret_cast<uint4*>(d + m * 16) = make_uint4(pack_op2(v[0], v[1]), pack_op2(v[2], v[3]), pack_op2(v[4], v[5]), pack_op2(v[6], v[7]));
+        *reinterpret_cast<uint4*>(d + PLANE_ROW + m * 16) = make_uint4(pack_op2(v[8], v[9]), pack_op2(v[10], v[11]), 0u, 0u);
+      }
+      fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.full[slot]);
+      ++fill;
+    }
+  }
+}
+
+// ---- peer CTA of the pair: relay "my ring row has landed" to the leader (one lane per ring slot) -------------------------
+template <class E>
+__device__ void mg_relay(const MegaK& M, const MCtx& c, const MEngSmem& s, int lane) {
+  uint32_t total = 0;
+  MSegIter it(M, c.team);
+  MSeg g;
+  while (it.next(g)) total += (uint32_t)(mg_hi(g, E::HALO, M.Hw) - mg_lo(g, E::HALO)) + 2u;
+  if (lane == 0) mbar_wait(s.wbar, 0);          // my half of the weights is part of every MMA the leader issues
+  __syncwarp();
+  const bool active = lane < E::RING;
+  const uint32_t fills = active && total > (uint32_t)lane ? (total - (uint32_t)lane + E::RING - 1) / E::RING : 0u;
+  uint32_t done = 0, par = 0;
+  long long t0 = clock64();
+  while (__any_sync(0xffffffffu, done < fills)) {
+    if (done < fills && mbar_try_wait(&s.full[active ? lane : 0], par)) {
+      mbar_arrive_cluster(&s.pfull[lane], 0);
+      par ^= 1u;
+      ++done;
+      t0 = clock64();
+    }
+    if (clock64() - t0 > (1ll << 33)) __trap();
+  }
+}
+
+// ---- MMA issuer (leader CTA): block-major, one accumulator per strip row -------------------------------------------------
+template <class E>
+__device__ void mg_issuer(const MegaK& M, const MCtx& c, const MEngSmem& s, uint32_t tmem_cols) {
+  constexpr uint32_t IDESC = umma_idesc_op(2 * MROWS, E::NPAD);
+  const uint32_t ring_lo = (smem_u32(s.ring) & 0x3FFFFu) >> 4;
+  const uint32_t w_lo = ((smem_u32(s.w) & 0x3FFFFu) >> 4) | ((uint32_t)((E::NB * 16) >> 4) << 16);
+  mbar_wait(s.wbar, 0);
+  uint32_t wslot = 0, wpar = 0, stage = 0, spar = 1;
+  auto wait_row = [&]() {
+    mbar_wait(&s.full[wslot], wpar);
+    mbar_wait(&s.pfull[wslot], wpar);
+    if (++wslot == E::RING) { wslot = 0; wpar ^= 1u; }
+  };
+  MSegIter it(M, c.team);
+  MSeg g;
+  while (it.next(g)) {
+    const int rows = mg_hi(g, E::HALO, M.Hw) - mg_lo(g, E::HALO);
+    uint32_t s0 = wslot;
+    wait_row();
+    wait_row();
+    for (int b = 0; b < rows; ++b) {
+      wait_row();
+      mbar_wait(&s.tempty[stage], spar);
+      tc_fence_after();
+      issue_block_2cta<E::PT, PLANE_ROW / 16, E::NB>(tmem_cols + stage * E::NPAD, ring_lo, E::ROWBYTES >> 4, s0, E::RING, w_lo, IDESC);
+      umma_commit_2cta(&s.tfull[stage]);
+      umma_commit_2cta(&s.empty[s0]);
+      if (b == rows - 1) {
+        const uint32_t s1 = s0 + 1 == E::RING ? 0 : s0 + 1, s2 = s1 + 1 == E::RING ? 0 : s1 + 1;
+        umma_commit_2cta(&s.empty[s1]);
+        umma_commit_2cta(&s.empty[s2]);
+      }
+      if (++s0 == E::RING) s0 = 0;
+      if (++stage == E::STAGES) { stage = 0; spar ^= 1u; }
+    }
+  }
+}
+
+// ---- epilogue warpgroup `wg` of the engine's NWG --------------------------------------------------------------------------
+template <class E>
+__device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, uint32_t tmem_cols, const float* s_lut, int wg, int warp, int lane) {
+  using EPI = typename E::EPI;
+  const MegaLayerP& P = M.L[E::L - 1];
+  const int q4 = warp & 3;                       // TMEM lane quadrant
+  const int m = q4 * 32 + lane;                  // pixel inside the strip row
+  const int x = c.strip * STRIP + m;
+  const bool valid = m < STRIP && x < M.Ww;
+  const size_t row_pitch = (size_t)M.PW * 16;
+  constexpr int D = E::OUT >= 0 ? mg_depth(E::OUT >= 0 ? E::OUT : 0) : 1;
+  const size_t plane_pitch = (size_t)D * row_pitch;
+  unsigned char* och = E::OUT >= 0 ? c.scratch + M.ch_off[E::OUT >= 0 ? E::OUT : 0] : nullptr;
+  unsigned int* prod = mg_prod(c.flags, E::OUT >= 0 ? E::OUT : 0);
+  uint32_t blk = 0, qrow = 0, qout = 0;          // blocks / ring rows / output rows before this segment
+  uint32_t cons_seen = 0;                        // every row below this has been read by all my consumers
+  MSegIter it(M, c.team);
+  MSeg g;
+  while (it.next(g)) {
+    const int f = min(2 * g.fp + c.rank, M.n_frames - 1);
+    const int lo = mg_lo(g, E::HALO), rows = mg_hi(g, E::HALO, M.Hw) - lo;
+    for (int b = 0; b < rows; ++b, ++blk) {
+      if ((int)(blk % E::NWG) != wg) continue;
+      const uint32_t stage = blk % E::STAGES, spar = (blk / E::STAGES) & 1u;
+      const int y = lo + b;
+      const uint32_t q = qout + (uint32_t)b;     // sequence number of this output row in my channel
+
+      uint32_t raw[E::KIND == EPI_TAIL_SHUFFLE ? 2 : 1][6];
+      if constexpr (E::KIND == EPI_TAIL_SHUFFLE) {
+        if (valid) {
+          const size_t fpl = (size_t)M.H * M.W;
+#pragma unroll
+          for (int dy = 0; dy < 2; ++dy) {
+            const size_t p0 = (size_t)(2 * y + dy) * M.W + 2 * x + M.xoff;
+            if (M.in_fmt == FSUAE_FMT_F32_NCHW3) {
+              const float* ip = (const float*)M.frame_in + (size_t)f * 3 * fpl + p0;
+#pragma unroll
+              for (int ch = 0; ch < 3; ++ch) {
+                const float2 t2 = __ldg(reinterpret_cast<const float2*>(ip + ch * fpl));
+                raw[dy][2 * ch] = __float_as_uint(t2.x); raw[dy][2 * ch + 1] = __float_as_uint(t2.y);
+              }
+            } else if (M.in_fmt == FSUAE_FMT_U8_NHWC4) {
+              const uint2 t2 = __ldg(reinterpret_cast<const uint2*>((const unsigned char*)M.frame_in + ((size_t)f * fpl + p0) * 4));
+              raw[dy][0] = t2.x; raw[dy][1] = t2.y;
+            } else {
+              const unsigned char* ip = (const unsigned char*)M.frame_in + (size_t)f * 4 * fpl + p0;
+#pragma unroll
+              for (int ch = 0; ch < 3; ++ch) { raw[dy][2 * ch] = __ldg(ip + ch * fpl); raw[dy][2 * ch + 1] = __ldg(ip + ch * fpl + 1); }
+            }
+          }
+        }
+      } else {
+        // back-pressure: slot q % D still holds row q - D until every consumer strip that reads my columns (s-1, s, s+1)
+        // has loaded it.  Checked before the accumulator wait, so the poll hides behind the MMAs.
+        if (q >= (uint32_t)D && cons_seen < q - (uint32_t)D + 1u) {
+          const uint32_t need = q - (uint32_t)D + 1u;
+          const long long t0 = clock64();
+          for (;;) {
+            uint32_t v = 0xFFFFFFFFu;
+            if (lane < 3 * E::OUT_NCONS) {
+              const int k = lane / 3, sn = c.strip - 1 + lane % 3;
+              if (sn >= 0 && sn < M.S) v = ld_acquire_gpu(mg_cons(c.flags, E::OUT >= 0 ? E::OUT : 0, k) + sn);
+            }
+            v = __reduce_min_sync(0xffffffffu, v);
+            if (v >= need) { cons_seen = v; break; }
+            if (clock64() - t0 > (1ll << 31)) __trap();
+            __nanosleep(64);
+          }
+        }
+      }
+
+      mbar_wait(&s.tfull[stage], spar);
+      tc_fence_after();
+      const uint32_t taddr = tmem_cols + ((uint32_t)(q4 * 32) << 16) + stage * E::NPAD;
+      // residual = this layer's input at the same pixel = centre row of the block, still in the ring (see conv3x3_tc_kernel)
+      const uint32_t kc = qrow + (uint32_t)b + 1;
+      const uint32_t cslot = kc % E::RING;
+      const uint8_t* sp = s.ring + cslot * E::ROWBYTES + (m + 1) * 16;
+      if constexpr (EPI::kSkip) mbar_wait(&s.full[cslot], (kc / E::RING) & 1);
+
+      if constexpr (E::KIND == EPI_STORE) {
+        uint4 sk[EPI::kSkip ? E::OUT_PLANES : 1];
+        if constexpr (EPI::kSkip) {
+#pragma unroll
+          for (int cc = 0; cc < E::OUT_PLANES; ++cc)
+            sk[cc] = valid ? *reinterpret_cast<const uint4*>(sp + cc * PLANE_ROW) : make_uint4(0, 0, 0, 0);
+        }
+        unsigned char* dp = och + (size_t)(q % (uint32_t)D) * row_pitch + (size_t)(x + BORDER) * 16;
+#pragma unroll
+        for (int cc = 0; cc < E::OUT_PLANES; ++cc) {
+          uint32_t v[8];
+          tmem_ld_x8(taddr + cc * 8, v);
+          tmem_ld_wait();
+          float o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int ch = cc * 8 + i;
+            if (ch >= E::COUT) { o[i] = 0.f; continue; }
+            float t = EPI::pre(P, ch, __uint_as_float(v[i]) + P.bias[ch]);
+            if constexpr (EPI::kSkip) {
+              const uint32_t w = (&sk[cc].x)[i >> 1];
+              t += (i & 1) ? op_hi(w) : op_lo(w);
+            }
+            o[i] = EPI::post(P, ch, t);
+          }
+          if (valid)
+            *reinterpret_cast<uint4*>(dp + (size_t)cc * plane_pitch) =
+                make_uint4(pack_op2(o[0], o[1]), pack_op2(o[2], o[3]), pack_op2(o[4], o[5]), pack_op2(o[6], o[7]));
+        }
+        // publish: my quarter of this strip row is in place (generic stores -> other SMs' TMA reads)
+        fence_proxy_async_all();
+        __syncwarp();
+        if (lane == 0) {
+          red_release_gpu_add(prod + q % (uint32_t)D, 1u);
+          if constexpr (EPI::kSkip) {            // residual values consumed: release the ring rows
+            mbar_arrive(&s.empty[cslot]);
+            if (b == 0) mbar_arrive(&s.empty[(kc - 1) % E::RING]);
+            if (b == rows - 1) mbar_arrive(&s.empty[(kc + 1) % E::RING]);
+          }
+        }
+      } else {
+        // PixelShuffle(2) + input residual + ReLU (+ gamma, uint8 pack), straight to the output frame
+        uint32_t v[16];
+        tmem_ld_x16(taddr, v);
+        tmem_ld_wait();
+        float o[12];
+#pragma unroll
+        for (int ch = 0; ch < 12; ++ch) o[ch] = EPI::post(P, ch, EPI::pre(P, ch, __uint_as_float(v[ch]) + P.bias[ch]));
+        if (valid) {
+          const size_t fpl = (size_t)M.H * M.W;
+          float idv[2][3][2];
+#pragma unroll
+          for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) {
+              if (M.in_fmt == FSUAE_FMT_F32_NCHW3) {
+                idv[dy][cc][0] = __uint_as_float(raw[dy][2 * cc]); idv[dy][cc][1] = __uint_as_float(raw[dy][2 * cc + 1]);
+              } else if (M.in_fmt == FSUAE_FMT_U8_NHWC4) {
+                idv[dy][cc][0] = s_lut[(raw[dy][0] >> (8 * cc)) & 0xFF]; idv[dy][cc][1] = s_lut[(raw[dy][1] >> (8 * cc)) & 0xFF];
+              } else {
+                idv[dy][cc][0] = s_lut[raw[dy][2 * cc] & 0xFF]; idv[dy][cc][1] = s_lut[raw[dy][2 * cc + 1] & 0xFF];
+              }
+            }
+#pragma unroll
+          for (int dy = 0; dy < 2; ++dy) {
+            const size_t p0 = (size_t)(2 * y + dy) * M.W + 2 * x + M.xoff;
+            float res[3][2];
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc)
+#pragma unroll
+              for (int dx = 0; dx < 2; ++dx) res[cc][dx] = fmaxf(o[cc * 4 + dy * 2 + dx] + idv[dy][cc][dx], 0.f);
+            if (M.out_fmt == FSUAE_FMT_F32_NCHW3) {
+              float* op = (float*)M.frame_out + (size_t)f * 3 * fpl + p0;
+#pragma unroll
+              for (int cc = 0; cc < 3; ++cc) *reinterpret_cast<float2*>(op + cc * fpl) = make_float2(res[cc][0], res[cc][1]);
+            } else {
+              uint32_t px[2];
+#pragma unroll
+              for (int dx = 0; dx < 2; ++dx)
+                px[dx] = (uint32_t)to_u8_fast(res[0][dx], M.gamma_out) | ((uint32_t)to_u8_fast(res[1][dx], M.gamma_out) << 8) |
+                         ((uint32_t)to_u8_fast(res[2][dx], M.gamma_out) << 16) | 0xFF000000u;
+              *reinterpret_cast<uint2*>((unsigned char*)M.frame_out + ((size_t)f * fpl + p0) * 4) = make_uint2(px[0], px[1]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&s.tempty[stage], 0);
+    }
+    qrow += (uint32_t)rows + 2u;
+    qout += (uint32_t)rows;
+  }
+}
+
+// ---- the engines of the flagship preset (model_pix_shuffle.py:306-311) ---------------------------------------------------
+#define MG_A(x) FSUAE_ACT_##x
+using MgConv1 = MEng<1, 2, 48, 36, EPI_STORE, Epi<MG_A(SINLU), MG_A(RELU6), 0, 0, false>, 8, 4, 2>;
+using MgConv2 = MEng<2, 5, 48, 36, EPI_STORE, Epi<MG_A(TELU), 0, MG_A(SINLU), MG_A(BIASED_PRELU), true>, 8, 4, 2>;
+using MgConv3 = MEng<3, 5, 80, 72, EPI_STORE, Epi<0, 0, 0, 0, false>, 8, 4, 2>;
+using MgConv4 = MEng<4, 9, 80, 72, EPI_STORE, Epi<MG_A(MISH), MG_A(BIASED_PRELU), MG_A(TANH), MG_A(RELU), true>, 9, 6, 4>;
+using MgConv5 = MEng<5, 9, 48, 36, EPI_STORE, Epi<0, 0, 0, 0, false>, 6, 6, 2>;
+using MgConv6 = MEng<6, 10, 48, 36, EPI_STORE, Epi<MG_A(MISH), MG_A(RELU6), 0, 0, false>, 6, 6, 2>;
+using MgConv7 = MEng<7, 5, 16, 12, EPI_TAIL_SHUFFLE, Epi<MG_A(BIASED_PRELU), 0, 0, 0, false>, 6, 6, 2>;
+#undef MG_A
+struct MgNone { static constexpr int SMEM = 0, TCOLS = 0, NBARS = 0, NWG = 0; };
+
+template <class E0, class E1>
+struct MStage {
+  static constexpr bool kTwo = E1::NWG > 0;
+  static constexpr int SMEM = E0::SMEM + E1::SMEM;
+  static_assert(E0::NWG + E1::NWG == 4, "16 epilogue warps per CTA");
+  static_assert(E0::TCOLS + E1::TCOLS <= 512, "TMEM columns");
+  static_assert((E0::SMEM % 128) == 0, "operand alignment of the second engine");
+};
+using MgStageA = MStage<MgConv2, MgConv3>;
+using MgStageB = MStage<MgConv4, MgNone>;
+using MgStageC = MStage<MgConv5, MgConv7>;
+using MgStageD = MStage<MgConv6, MgConv1>;
+constexpr int mg_max(int a, int b) { return a > b ? a : b; }
+constexpr int MG_BAR_BYTES = 1024;
+constexpr int MG_SMEM = mg_max(mg_max(MgStageA::SMEM, MgStageB::SMEM), mg_max(MgStageC::SMEM, MgStageD::SMEM)) + MG_BAR_BYTES;
+static_assert(MG_SMEM <= SMEM_LIMIT, "fused pass does not fit in shared memory");
+
+template <class E, bool HEAD>
+__device__ __forceinline__ void mg_run_service(const MegaK& M, const MCtx& c, const MEngSmem& s, uint32_t tmem_cols, const float* s_lut,
+                                               int role, int lane) {
+  if (role == 0) {           // producer warp
+    if constexpr (HEAD) mg_producer_head<E>(M, c, s, s_lut, lane);
+    else mg_producer<E>(M, c, s, lane);
+  } else if (c.rank != 0) {  // peer CTA: relay
+    mg_relay<E>(M, c, s, lane);
+  } else if (elect_one()) {  // leader CTA: MMA issue
+    mg_issuer<E>(M, c, s, tmem_cols);
+  }
+}
+
+template <class ST, class E0, class E1>
+__device__ __forceinline__ void mg_run_stage(const MegaK& M, MCtx& c, uint8_t* smem, float* s_lut, int warp, int lane) {
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MG_SMEM - MG_BAR_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 120);
+  const MEngSmem s0 = mg_carve<E0>(smem, bars);
+  MEngSmem s1 = s0;
+  if constexpr (ST::kTwo) s1 = mg_carve<E1>(smem + E0::SMEM, bars + E0::NBARS);
+  static_assert(E0::NBARS + E1::NBARS <= 120, "barrier block");
+  if (threadIdx.x == 0) {
+    mg_init_bars<E0>(s0);
+    if constexpr (ST::kTwo) mg_init_bars<E1>(s1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2cta(tmem_slot, 512);
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + 32) {   // zero the pads behind the rings
+    reinterpret_cast<uint32_t*>(s0.ring + E0::RING * E0::ROWBYTES)[threadIdx.x - 64] = 0u;
+    if constexpr (ST::kTwo) reinterpret_cast<uint32_t*>(s1.ring + E1::RING * E1::ROWBYTES)[threadIdx.x - 64] = 0u;
+  }
+  for (int i = threadIdx.x; i < 256; i += MG_THREADS) {
+    const float t = (float)i * (1.0f / 255.0f);
+    s_lut[i] = M.gamma_in ? powf(t, 2.2f) : t;
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 2) {
+    mg_run_service<E0, E0::L == 1>(M, c, s0, tmem_base, s_lut, warp, lane);
+  } else if (warp < 4) {
+    if constexpr (ST::kTwo) mg_run_service<E1, E1::L == 1>(M, c, s1, tmem_base + E0::TCOLS, s_lut, warp - 2, lane);
+  } else {
+    const int wg = (warp - 4) >> 2;
+    if (wg < E0::NWG) mg_epilogue<E0>(M, c, s0, tmem_base, s_lut, wg, warp, lane);
+    else if constexpr (ST::kTwo) mg_epilogue<E1>(M, c, s1, tmem_base + E0::TCOLS, s_lut, wg - E0::NWG, warp, lane);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2cta(tmem_base, 512);
+}
+
+__global__ void __launch_bounds__(MG_THREADS, 1) fused_pass_kernel(const __grid_constant__ MegaK M) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ float s_lut[256];
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int pair = blockIdx.x >> 1, group = pair >> 2, stage = pair & 3;
+  MCtx c;
+  c.team = group / M.S;
+  c.strip = group - c.team * M.S;
+  c.rank = (int)cluster_ctarank();
+  c.f = 0;
+  if (c.team >= M.teams) return;                 // both CTAs of a pair leave together
+  c.scratch = M.scratch + ((size_t)c.team * 2 + c.rank) * M.rank_stride;
+  c.flags = M.flags + ((size_t)c.team * 2 + c.rank) * MG_FLAG_WORDS;
+  switch (stage) {
+    case 0: mg_run_stage<MgStageA, MgConv2, MgConv3>(M, c, smem, s_lut, warp, lane); break;
+    case 1: mg_run_stage<MgStageB, MgConv4, MgNone>(M, c, smem, s_lut, warp, lane); break;
+    case 2: mg_run_stage<MgStageC, MgConv5, MgConv7>(M, c, smem, s_lut, warp, lane); break;
+    default: mg_run_stage<MgStageD, MgConv6, MgConv1>(M, c, smem, s_lut, warp, lane); break;
+  }
+}
