@@ -32,11 +32,20 @@ WORKLOAD = "pix_shuffle-lightweight, 64 synthetic RGB444 752x576 RGBA framebuffe
 
 
 def measured_peaks():
+    """(burst TFLOP/s, sustained TFLOP/s, HBM GB/s, source).  MEASURED_PEAKS.json is driver-written: the burst figure is
+    cuBLAS bf16 timed alone at full clocks, the sustained one back to back for 4 s (power-capped clocks)."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get("bf16_tflops_sustained", 1379.1), d.get("hbm_gbs", 6549.1), "measured"
-    return 1400.0, 6650.0, "fallback"
+        return d.get("bf16_tflops", 1631.8), d.get("bf16_tflops_sustained", 1379.1), d.get("hbm_gbs", 6549.1), "measured"
+    return 1650.0, 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def committed_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this round
+    (profiles/r02_dram_traffic.json, written by tools/ncu_summary.py from the .ncu-rep): {kernel label: bytes}."""
+    p = os.path.join(ROOT, "profiles", "r02_dram_traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
 
 
 class ClockSampler:
@@ -150,6 +159,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunk", type=int, default=64, help="frames per internal engine pass")
     ap.add_argument("--quick", action="store_true", help="skip latency / e2e legs (tuning runs)")
+    ap.add_argument("--stream-frames", type=int, default=4096, help="BASELINE config 5: host frames in the sharded stream (0: skip)")
+    ap.add_argument("--sustain", type=float, default=2.5, help="seconds of the sustained device-resident leg (0: skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -251,6 +262,10 @@ def main():
             print(json.dumps({"chunk": args.chunk, "fps": BATCH * world * args.steps / (ms / 1000.0),
                               "us_per_frame": 1e3 * ms / args.steps / BATCH}), flush=True)
         return
+    def pctl(v, q):
+        v = sorted(v)
+        return v[min(len(v) - 1, int(len(v) * q))]
+
     # single-frame latency, device resident (p50 over 200 launches)
     lat = []
     one_in, one_out = d_in[0][:1].contiguous(), d_out[0][:1].contiguous()
@@ -264,12 +279,18 @@ def main():
         b.record()
         b.synchronize()
         lat.append(a.elapsed_time(b))
-    lat.sort()
 
     # end to end through the host-buffer C-ABI call (pinned host memory; H2D and D2H inside)
     h_out = [torch.empty_like(h).pin_memory() for h in host]
     for i in range(2):
         eng.run_host(host[i & 1], h_out[i & 1], BATCH, _lib.FMT_U8_NHWC4, _lib.FMT_U8_NHWC4, flags)
+    # the emulator's own call: ONE host frame in, one host frame out, blocking (README.md:21-24)
+    lat1 = []
+    for i in range(120):
+        t0 = time.perf_counter()
+        eng.run_host(host[0][i % BATCH:i % BATCH + 1], h_out[0][i % BATCH:i % BATCH + 1], 1, _lib.FMT_U8_NHWC4, _lib.FMT_U8_NHWC4, flags)
+        if i >= 20:
+            lat1.append(1e3 * (time.perf_counter() - t0))
     barrier()
     e2e_steps = max(3, min(args.steps, 10))
     # (a) one synchronous fsuae_engine_run_host call per step (pipeline fill and drain paid on every call)
@@ -287,63 +308,160 @@ def main():
     eng.wait_host()
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
+    barrier()
+    # (c) what the box's host<->device path can carry at this rank count: the same bytes, same 16-frame pieces, H2D and D2H
+    # on two streams at once, all ranks concurrently, no kernel in between -- the ceiling of any end-to-end number here
+    s_up, s_dn = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    piece = 16
+    def copy_pass(steps):
+        for i in range(steps):
+            for f0 in range(0, BATCH, piece):
+                with torch.cuda.stream(s_up):
+                    d_in[i & 1][f0:f0 + piece].copy_(host[i & 1][f0:f0 + piece], non_blocking=True)
+                with torch.cuda.stream(s_dn):
+                    h_out[i & 1][f0:f0 + piece].copy_(d_out[i & 1][f0:f0 + piece], non_blocking=True)
+    copy_pass(1)
+    barrier()
+    t0 = time.perf_counter()
+    copy_pass(e2e_steps)
+    torch.cuda.synchronize(dev)
+    copy_s = time.perf_counter() - t0
+    barrier()
 
-    from fs_uae_image_enhancer_project_b200.sharding import max_over_ranks
-    ms, e2e_s, e2e_sync_s = max_over_ranks(ms, dev), max_over_ranks(e2e_s, dev), max_over_ranks(e2e_sync_s, dev)   # slowest rank
+    # BASELINE config 5, literally: a stream of 4096 synthetic host frames cut into contiguous per-GPU ranges
+    # (sharding.frame_range), submitted in 64-frame pieces through the host-buffer call, one wait at the end
+    from fs_uae_image_enhancer_project_b200.sharding import frame_range, max_over_ranks
+    stream5 = None
+    if args.stream_frames > 0:
+        lo, hi = frame_range(args.stream_frames, world, rank)
+        n5 = hi - lo
+        s_host = s_out = None
+        err = ""
+        try:
+            s_host = torch.empty((n5, FRAME_H, FRAME_W, 4), dtype=torch.uint8, pin_memory=True)
+            s_out = torch.empty((n5, FRAME_H, FRAME_W, 4), dtype=torch.uint8, pin_memory=True)
+        except RuntimeError as exc:                               # not enough pinnable host memory on this box: say so
+            err = str(exc)[:200]
+        if max_over_ranks(1.0 if err else 0.0, dev) > 0:          # every rank takes the same branch (collectives below)
+            stream5 = {"frames": args.stream_frames, "unavailable": err or "another rank could not pin its range"}
+        else:
+            for f0 in range(0, n5, 256):                         # the stream is born on the device, frame g = lo + i
+                k = min(256, n5 - f0)
+                s_host[f0:f0 + k].copy_(synth.synth_rgb444_frames(k, FRAME_H, FRAME_W, seed=5000, first_frame=lo + f0, device=dev))
+            torch.cuda.synchronize(dev)
+            barrier()
+            t0 = time.perf_counter()
+            for f0 in range(0, n5, BATCH):
+                k = min(BATCH, n5 - f0)
+                eng.submit_host(s_host[f0:f0 + k], s_out[f0:f0 + k], k, _lib.FMT_U8_NHWC4, _lib.FMT_U8_NHWC4, flags)
+            eng.wait_host()
+            stream_s = time.perf_counter() - t0
+            barrier()
+            # latency of a piece in the stream: blocking 64-frame calls, submit -> all 64 frames back in host memory
+            piece_ms = []
+            for f0 in range(0, min(n5, 16 * BATCH), BATCH):
+                k = min(BATCH, n5 - f0)
+                t1 = time.perf_counter()
+                eng.run_host(s_host[f0:f0 + k], s_out[f0:f0 + k], k, _lib.FMT_U8_NHWC4, _lib.FMT_U8_NHWC4, flags)
+                piece_ms.append(1e3 * (time.perf_counter() - t1))
+            stream_s = max_over_ranks(stream_s, dev)
+            stream5 = {"frames": args.stream_frames, "frames_per_gpu": n5, "sharding": "contiguous ranges (sharding.frame_range)",
+                       "value": args.stream_frames / stream_s, "unit": "frames/s", "seconds": stream_s,
+                       "piece_frames": BATCH, "piece_latency_p50_ms": pctl(piece_ms, 0.5), "piece_latency_p99_ms": pctl(piece_ms, 0.99),
+                       "api": "fsuae_engine_submit_host per 64-frame piece of the rank's range + one fsuae_engine_wait_host"}
+        del s_host, s_out
+
+    # sustained leg: the same device-resident step back to back for >= args.sustain seconds (the burst number above is
+    # 20 steps = 50 ms; a long run meets the software power cap), clocks sampled throughout
+    sustained = None
+    if args.sustain > 0:
+        n_sus = max(args.steps, int(args.sustain * 1000.0 / (ms / args.steps)) + 1)
+        sampler2 = ClockSampler(local)
+        if rank == 0:
+            sampler2.start()
+        barrier()
+        ev0.record()
+        for i in range(n_sus):
+            step(i)
+        ev1.record()
+        barrier()
+        sus_ms = max_over_ranks(ev0.elapsed_time(ev1), dev)
+        sustained = {"steps": n_sus, "seconds": sus_ms / 1000.0, "value": BATCH * world * n_sus / (sus_ms / 1000.0),
+                     "unit": "frames/s", "clocks": sampler2.stop() if rank == 0 else None}
+
+    ms, e2e_s, e2e_sync_s, copy_s = (max_over_ranks(v, dev) for v in (ms, e2e_s, e2e_sync_s, copy_s))   # slowest rank
 
     if rank == 0:
         frames = BATCH * world * args.steps
         fps = frames / (ms / 1000.0)
-        tf_peak, hbm_peak, how = measured_peaks()
+        tf_burst, tf_sus, hbm_peak, how = measured_peaks()
+        # which peak applies: a run at (nearly) maximum SM clock without a power cap is measured against the burst figure
+        at_full_clock = bool(clocks and clocks.get("sm_mhz") and clocks["sm_mhz"] >= 0.97 * (clocks.get("sm_max_mhz") or 1e9)
+                             and "sw_power_cap" not in clocks.get("reasons", []))
+        tf_peak, peak_kind = (tf_burst, "burst") if at_full_clock else (tf_sus, "sustained")
         per_gpu_step_s = ms / 1000.0 / args.steps
         achieved_tf = GFLOP_PER_FRAME * BATCH / per_gpu_step_s / 1000.0
         # dominant kernel: algorithmic FLOPs of the layers it runs / its own event-timed duration
         mac = {"conv1": 3888, "conv2": 11664, "conv3": 23328, "conv4": 46656, "conv5": 23328, "conv6": 23328, "conv7": 3888}
         dom = max(per_kernel, key=per_kernel.get) if per_kernel else None
+        traffic = committed_traffic()
+        algo_bytes = BYTES_PER_FRAME_U8 * BATCH
         dom_line = None
         if dom:
-            layers = [l for l in mac if l in dom.replace("+", " ").replace("_", " ").split()]
+            layers = list(mac) if dom == "fused_pass" else [l for l in mac if l in dom.replace("+", " ").replace("_", " ").split()]
             gflop = sum(2 * mac[l] * (FRAME_H // 2) * (FRAME_W // 2) for l in layers) * BATCH / 1e9
             dom_tf = gflop / per_kernel[dom]                    # GFLOP / ms = TFLOP/s
             dom_line = {"kernel": dom, "ms": per_kernel[dom], "share_of_step": per_kernel[dom] / sum(per_kernel.values()),
-                        "achieved": dom_tf, "frac": dom_tf / tf_peak,
-                        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, ncu --set full, per launch of 64 frames
-                        # (profiles/r01_layers_ncu_full_summary.csv); algorithmic bytes of the fused kernel: 5 planes in +
-                        # 9 planes out of bf16 = 64 x 14 x 1.77 MB = 1.59 GB
-                        "traffic": 1.566e9 if "conv3+conv4" in dom else None}
+                        "achieved": dom_tf, "traffic": traffic.get(dom)}
+        pass_traffic = sum(v for k, v in traffic.items() if k in per_kernel) if traffic and all(k in traffic for k in per_kernel) else None
         line = {
             "metric": "752x576 frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[precision], "data": "synthetic",
             "config": {"workload": WORKLOAD, "variant": eng.variant, "frames_per_gpu_per_step": BATCH,
+                       "launches_per_step": int(launches_per_step),
                        "l2": "inputs rotate over 2 batches (443 MB in+out) > 126 MB L2",
                        "sharding": "frame-wise, one replica per GPU, no collective",
                        "host_numa_binding": f"{len(numa_cpus)} CPUs next to GPU 0" if numa_cpus else "none"},
-            "latency_p50_ms": lat[len(lat) // 2], "latency_p99_ms": lat[int(len(lat) * 0.99) - 1],
+            "latency_p50_ms": pctl(lat, 0.5), "latency_p99_ms": pctl(lat, 0.99),
+            "latency_host_1frame_p50_ms": pctl(lat1, 0.5), "latency_host_1frame_p99_ms": pctl(lat1, 0.99),
             "us_per_frame": 1e6 * per_gpu_step_s / BATCH,
             "e2e": {"value": BATCH * world * e2e_steps / e2e_s, "unit": "frames/s",
                     "h2d_bytes_per_step": BATCH * FRAME_H * FRAME_W * 4, "d2h_bytes_per_step": BATCH * FRAME_H * FRAME_W * 4,
                     "steps": e2e_steps, "api": "fsuae_engine_submit_host per step + one fsuae_engine_wait_host (pinned host buffers)",
                     "sync_call_value": BATCH * world * e2e_steps / e2e_sync_s,
-                    "sync_call_api": "one blocking fsuae_engine_run_host per step"},
+                    "sync_call_api": "one blocking fsuae_engine_run_host per step",
+                    "copy_ceiling_fps": BATCH * world * e2e_steps / copy_s,
+                    "frac_of_copy_ceiling": (BATCH * world * e2e_steps / e2e_s) / (BATCH * world * e2e_steps / copy_s),
+                    "copy_ceiling_note": "the same H2D + D2H bytes in the same 16-frame pieces on two streams, all ranks at once, no kernel"},
             "gpu_launches": int(launches_per_step * args.steps),
             "roofline": {"bound": "tensor", "achieved": dom_line["achieved"] if dom_line else achieved_tf, "peak": tf_peak,
                          "unit": "TFLOP/s", "frac": (dom_line["achieved"] if dom_line else achieved_tf) / tf_peak,
+                         "frac_burst": (dom_line["achieved"] if dom_line else achieved_tf) / tf_burst,
+                         "frac_sustained": (dom_line["achieved"] if dom_line else achieved_tf) / tf_sus,
+                         "peak_kind": peak_kind,
                          "traffic": dom_line["traffic"] if dom_line else None,
+                         "algorithmic_bytes": algo_bytes if dom == "fused_pass" else None,
                          "kernel": dom_line["kernel"] if dom_line else None,
                          "kernel_ms": dom_line["ms"] if dom_line else None,
                          "share_of_step": dom_line["share_of_step"] if dom_line else None,
-                         "note": f"dominant kernel, CUDA events on its stream; peak = {how} sustained bf16 (kernel timed inside a long step)"},
+                         "note": f"dominant kernel, CUDA events on its stream; peak = {how} {peak_kind} bf16 (chosen by the clocks record: "
+                                 f"burst when the SM clock stayed >= 97 % of max without a power cap); traffic = dram bytes per launch from "
+                                 f"the committed ncu --set full capture (profiles/r02_dram_traffic.json)"},
             "roofline_whole_pass": {"bound": "tensor", "achieved": achieved_tf, "peak": tf_peak, "unit": "TFLOP/s",
-                                    "frac": achieved_tf / tf_peak,
+                                    "frac": achieved_tf / tf_peak, "frac_burst": achieved_tf / tf_burst, "frac_sustained": achieved_tf / tf_sus,
+                                    "traffic": pass_traffic, "algorithmic_bytes": algo_bytes,
+                                    "traffic_over_algorithmic": (pass_traffic / algo_bytes) if pass_traffic else None,
                                     "note": f"algorithmic 29.472 GFLOP/frame x {BATCH} frames / step device time (all kernels of the "
-                                            f"pass); HBM floor: {BYTES_PER_FRAME_U8 * BATCH / 1e9 / (hbm_peak) * 1e3:.3f} ms/step"},
+                                            f"pass); HBM floor: {algo_bytes / 1e9 / (hbm_peak) * 1e3:.3f} ms/step"},
             "kernel_ms": per_kernel,
             "parity_check": parity,
+            "stream_config5": stream5,
+            "sustained": sustained,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            cfps, threads = cpu_forward_fps(16, 4, sd={k: v.detach().cpu() for k, v in model.state_dict().items()}, frames=host[0][:16])
+            cfps, threads = cpu_forward_fps(16, 4, sd={k: v.detach().float().cpu() for k, v in model.state_dict().items()}, frames=host[0][:16])
             line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": threads, "kind": "port",
                                     "sample": "16 of the 64 frames, batch 4, oracle port of the PyTorch fp32 eval forward"}
         print(json.dumps(line), flush=True)

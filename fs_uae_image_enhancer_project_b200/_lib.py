@@ -10,7 +10,7 @@ import os
 
 from .build import LIB_PATH
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_LAYERS = 16
 MAX_ACTS = 4
 
@@ -22,11 +22,11 @@ ACT = {name: i for i, name in enumerate([
     "log_softmax"])}
 ACT["swish"] = ACT["silu"]
 
-HEAD_PLAIN, HEAD_UNSHUFFLE2 = 0, 1
-TAIL_PLAIN, TAIL_SHUFFLE2_RESIDUAL_RELU, TAIL_SCALE255_ALPHA = 0, 1, 2
+HEAD_PLAIN, HEAD_UNSHUFFLE2, HEAD_FEATURES = 0, 1, 2
+TAIL_PLAIN, TAIL_SHUFFLE2_RESIDUAL_RELU, TAIL_SCALE255_ALPHA, TAIL_FEATURES = 0, 1, 2, 3
 PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2
 MAX_CHUNK_FRAMES = 1024
-FMT_F32_NCHW3, FMT_U8_NHWC4, FMT_U8_NCHW4, FMT_F32_NCHW4 = 0, 1, 2, 3
+FMT_F32_NCHW3, FMT_U8_NHWC4, FMT_U8_NCHW4, FMT_F32_NCHW4, FMT_F32_NCHW = 0, 1, 2, 3, 4
 FLAG_GAMMA_IN, FLAG_GAMMA_OUT, FLAG_CROP16 = 1, 2, 4
 
 
@@ -40,12 +40,13 @@ class LayerDesc(C.Structure):
                 ("src0", C.c_int32), ("src1", C.c_int32), ("skip_src", C.c_int32),
                 ("w_off", C.c_int32), ("b_off", C.c_int32),
                 ("n_pre", C.c_int32), ("n_post", C.c_int32),
-                ("pre", ActDesc * MAX_ACTS), ("post", ActDesc * MAX_ACTS)]
+                ("pre", ActDesc * MAX_ACTS), ("post", ActDesc * MAX_ACTS),
+                ("ksize", C.c_int32), ("reserved", C.c_int32)]
 
 
 class NetDesc(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("n_layers", C.c_int32),
-                ("head", C.c_int32), ("tail", C.c_int32),
+                ("head", C.c_int32), ("tail", C.c_int32), ("in_channels", C.c_int32), ("reserved", C.c_int32),
                 ("layers", LayerDesc * MAX_LAYERS)]
 
 
@@ -66,6 +67,8 @@ EXPORTS = {
     "fsuae_engine_wait_host": (C.c_int, [C.c_void_p]),
     "fsuae_quantize_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_void_p]),
+    "fsuae_dither_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                      C.c_void_p]),
     "fsuae_synth_rgb444_frames": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_int, C.c_void_p]),
     "fsuae_engine_device_bytes": (C.c_size_t, [C.c_void_p]),
     "fsuae_engine_last_launch_count": (C.c_int64, [C.c_void_p]),

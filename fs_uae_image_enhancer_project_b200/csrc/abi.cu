@@ -69,22 +69,26 @@ static int validate(const fsuae_net_desc* d, size_t blob_floats, int H, int W, s
   auto bad = [&](const std::string& s) { *why = s; return FSUAE_ERR_INVALID; };
   if (d->abi_version != FSUAE_ABI_VERSION) return bad("descriptor abi_version mismatch");
   if (d->n_layers < 1 || d->n_layers > FSUAE_MAX_LAYERS) return bad("n_layers out of range");
-  if (d->head != FSUAE_HEAD_PLAIN && d->head != FSUAE_HEAD_UNSHUFFLE2) return bad("unknown head");
-  if (d->tail < FSUAE_TAIL_PLAIN || d->tail > FSUAE_TAIL_SCALE255_ALPHA) return bad("unknown tail");
+  if (d->head < FSUAE_HEAD_PLAIN || d->head > FSUAE_HEAD_FEATURES) return bad("unknown head");
+  if (d->tail < FSUAE_TAIL_PLAIN || d->tail > FSUAE_TAIL_FEATURES) return bad("unknown tail");
+  if ((d->head == FSUAE_HEAD_FEATURES) != (d->tail == FSUAE_TAIL_FEATURES))
+    return bad("the feature-map head and tail come together");
+  if (d->head == FSUAE_HEAD_FEATURES && (d->in_channels < 1 || d->in_channels > 4096)) return bad("in_channels out of range");
   if (H < 2 || W < 2) return bad("frame too small");
   if (d->head == FSUAE_HEAD_UNSHUFFLE2 && ((H | W) & 1))
     return bad("PixelUnshuffle(2) needs even height and width");
   std::vector<int> ch(d->n_layers + 1);
-  ch[0] = d->head == FSUAE_HEAD_UNSHUFFLE2 ? 12 : 3;
+  ch[0] = d->head == FSUAE_HEAD_UNSHUFFLE2 ? 12 : (d->head == FSUAE_HEAD_FEATURES ? d->in_channels : 3);
   for (int i = 0; i < d->n_layers; ++i) {
     const fsuae_layer_desc& L = d->layers[i];
     const std::string tag = "layer " + std::to_string(i + 1) + ": ";
     if (L.cout < 1 || L.cin0 < 1 || L.cin1 < 0) return bad(tag + "bad channel count");
+    if (L.ksize != 3 && L.ksize != 5 && L.ksize != 7) return bad(tag + "kernel size must be 3, 5 or 7 (1x1: centre tap of 3x3)");
     if (L.src0 < 0 || L.src0 > i || ch[L.src0] != L.cin0) return bad(tag + "src0 mismatch");
     if (L.cin1 > 0 && (L.src1 < 0 || L.src1 > i || ch[L.src1] != L.cin1)) return bad(tag + "src1 mismatch");
     if (L.skip_src >= 0 && (L.skip_src > i || ch[L.skip_src] != L.cout))
       return bad(tag + "skip source channel mismatch (a 1x1 skip projection is described as a layer of its own)");
-    size_t wn = (size_t)L.cout * (L.cin0 + L.cin1) * 9;
+    size_t wn = (size_t)L.cout * (L.cin0 + L.cin1) * L.ksize * L.ksize;
     if (L.w_off < 0 || (size_t)L.w_off + wn > blob_floats) return bad(tag + "weights outside blob");
     if (L.b_off >= 0 && (size_t)L.b_off + L.cout > blob_floats) return bad(tag + "bias outside blob");
     if (L.n_pre < 0 || L.n_pre > FSUAE_MAX_ACTS || L.n_post < 0 || L.n_post > FSUAE_MAX_ACTS)
@@ -108,12 +112,17 @@ static int validate(const fsuae_net_desc* d, size_t blob_floats, int H, int W, s
   int last = ch[d->n_layers];
   if (d->tail == FSUAE_TAIL_SHUFFLE2_RESIDUAL_RELU && (last != 12 || d->head != FSUAE_HEAD_UNSHUFFLE2))
     return bad("shuffle tail needs 12 output channels and the unshuffle head");
-  if (d->tail != FSUAE_TAIL_SHUFFLE2_RESIDUAL_RELU && (last != 3 || d->head != FSUAE_HEAD_PLAIN))
+  if ((d->tail == FSUAE_TAIL_PLAIN || d->tail == FSUAE_TAIL_SCALE255_ALPHA) && (last != 3 || d->head != FSUAE_HEAD_PLAIN))
     return bad("plain / scale255 tail needs 3 output channels and the plain head");
   return FSUAE_OK;
 }
 
 static int check_formats(fsuae_engine* e, int in_fmt, int out_fmt, uint32_t flags) {
+  if (e->desc.head == FSUAE_HEAD_FEATURES) {      // feature-map networks: float [B,C,H,W] in and out, nothing else
+    if (in_fmt != FSUAE_FMT_F32_NCHW || out_fmt != FSUAE_FMT_F32_NCHW || flags != 0)
+      return set_error(e, FSUAE_ERR_INVALID, "a feature-map network takes FSUAE_FMT_F32_NCHW in and out, no flags");
+    return FSUAE_OK;
+  }
   if (in_fmt != FSUAE_FMT_F32_NCHW3 && in_fmt != FSUAE_FMT_U8_NHWC4 && in_fmt != FSUAE_FMT_U8_NCHW4)
     return set_error(e, FSUAE_ERR_INVALID, "invalid input format");
   if (out_fmt != FSUAE_FMT_F32_NCHW3 && out_fmt != FSUAE_FMT_U8_NHWC4 && out_fmt != FSUAE_FMT_F32_NCHW4)
@@ -130,6 +139,12 @@ static int check_formats(fsuae_engine* e, int in_fmt, int out_fmt, uint32_t flag
   if ((flags & FSUAE_FLAG_CROP16) && (e->W <= 16 + 2))
     return set_error(e, FSUAE_ERR_INVALID, "CROP16 needs width > 18");
   return FSUAE_OK;
+}
+
+static size_t frame_bytes(const fsuae_engine* e, int fmt, bool input) {
+  if (fmt == FSUAE_FMT_F32_NCHW)
+    return (size_t)(input ? e->desc.in_channels : e->desc.layers[e->desc.n_layers - 1].cout) * e->H * e->W * 4;
+  return fmt_frame_bytes(fmt, e->H, e->W);
 }
 
 }  // namespace fsuae
@@ -201,7 +216,8 @@ int fsuae_engine_create(const fsuae_net_desc* desc, const float* blob, size_t bl
 
   // host-pipeline staging: sized for the widest formats
   e->host_chunk = std::min(e->chunk, 16);  // largest stage of the host-buffer pipeline (H2D / compute / D2H overlap)
-  size_t in_b = (size_t)e->host_chunk * 12 * height * width, out_b = (size_t)e->host_chunk * 16 * height * width;
+  size_t in_b = (size_t)e->host_chunk * std::max<size_t>(12, frame_bytes(e, FSUAE_FMT_F32_NCHW, true) / ((size_t)height * width)) * height * width;
+  size_t out_b = (size_t)e->host_chunk * std::max<size_t>(16, frame_bytes(e, FSUAE_FMT_F32_NCHW, false) / ((size_t)height * width)) * height * width;
   for (int i = 0; i < FSUAE_STAGE_BUFS && ce == cudaSuccess; ++i) {
     ce = cudaMalloc(&e->d_stage_in[i], in_b);
     if (ce == cudaSuccess) ce = cudaMalloc(&e->d_stage_out[i], out_b);
@@ -281,7 +297,7 @@ int fsuae_engine_destroy(fsuae_engine* e) {
 
 static int enqueue_impl(fsuae_engine* e, const void* in_dev, void* out_dev, int n_frames, int in_fmt,
                         int out_fmt, uint32_t flags, cudaStream_t st) {
-  size_t in_fb = fmt_frame_bytes(in_fmt, e->H, e->W), out_fb = fmt_frame_bytes(out_fmt, e->H, e->W);
+  size_t in_fb = frame_bytes(e, in_fmt, true), out_fb = frame_bytes(e, out_fmt, false);
   for (int f0 = 0; f0 < n_frames; f0 += e->chunk) {
     int n = std::min(e->chunk, n_frames - f0);
     const char* ip = (const char*)in_dev + (size_t)f0 * in_fb;
@@ -321,7 +337,7 @@ int fsuae_engine_submit_host(fsuae_engine* e, const void* in_host, void* out_hos
   int prev = 0;
   cudaGetDevice(&prev);
   if (prev != e->device) cudaSetDevice(e->device);
-  size_t in_fb = fmt_frame_bytes(in_fmt, e->H, e->W), out_fb = fmt_frame_bytes(out_fmt, e->H, e->W);
+  size_t in_fb = frame_bytes(e, in_fmt, true), out_fb = frame_bytes(e, out_fmt, false);
   rc = FSUAE_OK;
   // Stage sizes (measured on a B200 / PCIe 5 x16 box, 64-frame calls, tools/e2e_stage_sweep.sh): when earlier
   // submissions are still in flight the stream is full and uniform large stages are best (22.8 k frames/s); when the

@@ -65,7 +65,7 @@ constexpr int MAXC = 128;           // widest N of one launch
 constexpr int STRIP = 126;            // valid output columns per strip row
 constexpr int MROWS = 128;            // MMA M = slots per strip row
 constexpr int PLANE_ROW = MROWS * 16; // bytes of one plane of one strip row
-constexpr int BORDER = 2;             // zero pixels baked in on every side of a plane (1 for a layer, 2 for a fused pair)
+constexpr int BORDER = 3;             // zero pixels baked in on every side of a plane (1 for a 3x3 layer, 2 for a fused pair / 5x5, 3 for 7x7)
 __host__ __device__ constexpr int plane_width(int S) { return STRIP * S + 2 * BORDER; }   // slots per padded row (PW)
 constexpr int SMEM_LIMIT = 232448 - 2048;
 constexpr int EPI_WG = 4;                       // epilogue warpgroups; group g owns accumulator stage g
@@ -1493,6 +1493,45 @@ __global__ void head_plain_bf16_kernel(const void* __restrict__ in, unsigned cha
   }
 }
 
+// feature-map networks (FSUAE_HEAD_FEATURES / FSUAE_TAIL_FEATURES): float [B,C,H,W] <-> chunk-planar operands; thread = (pixel, plane)
+__global__ void head_features_kernel(const float* __restrict__ in, unsigned char* __restrict__ dst, int n_frames, int C, int Hw, int Ww,
+                                     int PW, unsigned long long fs_dst) {
+  const int planes = (C + 7) / 8;
+  const size_t plane = (size_t)Hw * Ww, total = (size_t)n_frames * planes * plane;
+  const size_t row_pitch = (size_t)PW * 16, plane_pitch = (size_t)(Hw + 2 * BORDER) * row_pitch;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = idx % plane;
+    const size_t t = idx / plane;
+    const int j = (int)(t % planes), f = (int)(t / planes);
+    const int h = (int)(r / Ww), w = (int)(r - (size_t)h * Ww);
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = j * 8 + k < C ? in[((size_t)f * C + j * 8 + k) * plane + r] : 0.f;
+    unsigned char* dp = dst + (size_t)f * fs_dst + (size_t)j * plane_pitch + (size_t)(h + BORDER) * row_pitch + (size_t)(w + BORDER) * 16;
+    *reinterpret_cast<uint4*>(dp) = make_uint4(pack_op2(v[0], v[1]), pack_op2(v[2], v[3]), pack_op2(v[4], v[5]), pack_op2(v[6], v[7]));
+  }
+}
+__global__ void tail_features_kernel(const unsigned char* __restrict__ src, float* __restrict__ out, int n_frames, int C, int Hw, int Ww,
+                                     int PW, unsigned long long fs_src) {
+  const int planes = (C + 7) / 8;
+  const size_t plane = (size_t)Hw * Ww, total = (size_t)n_frames * planes * plane;
+  const size_t row_pitch = (size_t)PW * 16, plane_pitch = (size_t)(Hw + 2 * BORDER) * row_pitch;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = idx % plane;
+    const size_t t = idx / plane;
+    const int j = (int)(t % planes), f = (int)(t / planes);
+    const int h = (int)(r / Ww), w = (int)(r - (size_t)h * Ww);
+    const uint4 q = *reinterpret_cast<const uint4*>(src + (size_t)f * fs_src + (size_t)j * plane_pitch + (size_t)(h + BORDER) * row_pitch +
+                                                    (size_t)(w + BORDER) * 16);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (j * 8 + k < C) {
+        const uint32_t wd = (&q.x)[k >> 1];
+        out[((size_t)f * C + j * 8 + k) * plane + r] = (k & 1) ? op_hi(wd) : op_lo(wd);
+      }
+  }
+}
+
 __global__ void black_columns_bf16_kernel(void* __restrict__ out, int n_frames, int out_fmt, int H, int W, int ncols) {
   const size_t total = (size_t)n_frames * H * ncols;
   const size_t fplane = (size_t)H * W;
@@ -1573,6 +1612,7 @@ std::vector<uint16_t> pack_weights(const float* w, int cout, int cin0, int cin1,
 }
 
 #include "bf16_wide.cuh"
+#include "mega.cuh"
 
 // R3 mode: B operand of step st of an input row = [2 halves][3 NPAD rows][8 k]; row block b holds kernel row dy = 2 - b
 // (the input row is the bottom / middle / top row of output rows k-2 / k-1 / k).
@@ -1727,7 +1767,28 @@ struct TcPlan {
   int fused_at = -1;
   void (*fused_fn)(const LayerK, const LayerK) = nullptr;
   int fused_smem = 0;
+  // the single fused pass (mega.cuh): the whole flagship network as one persistent kernel, feature maps in L2-resident rings
+  bool mega_ok = false;
+  int mega_groups = 0;                 // groups of 4 stage pairs the GPU holds
+  unsigned char* mega_scratch = nullptr;
+  size_t mega_scratch_bytes = 0;
+  unsigned int* mega_flags = nullptr;
+  size_t mega_flag_words = 0;
+  unsigned char* mega_zero = nullptr;
+  int mega_zero_Ww = -1;               // geometry the scratch rows' zero borders are valid for
+  MegaK mega_k{};                      // per-layer parameters prefilled
 };
+
+// bytes of one (team, rank) channel block for rows of PW slots
+static size_t mega_block_bytes(int PW, unsigned long long* ch_off = nullptr) {
+  const int planes[MG_NCH] = {5, 5, 9, 9, 5, 5};
+  size_t off = 0;
+  for (int c = 0; c < MG_NCH; ++c) {
+    if (ch_off) ch_off[c] = off;
+    off += (size_t)planes[c] * mg_depth(c) * PW * 16;
+  }
+  return (off + 255) / 256 * 256;
+}
 
 static int planes_of(int c) { return (c + 7) / 8; }
 
@@ -1757,8 +1818,9 @@ int TC_FN(create)(fsuae_engine* e) {
   const bool unshuffle = d.head == FSUAE_HEAD_UNSHUFFLE2;
   TcPlan* plan = new TcPlan();
   e->TC_FIELD = plan;
+  const bool features = d.head == FSUAE_HEAD_FEATURES;      // float feature maps in and out (residual-UNet building blocks)
   std::vector<int> ch(d.n_layers + 1);
-  ch[0] = unshuffle ? 12 : 3;
+  ch[0] = unshuffle ? 12 : (features ? d.in_channels : 3);
   for (int i = 0; i < d.n_layers; ++i) ch[i + 1] = d.layers[i].cout;
 
   plan->layers.resize(d.n_layers);
@@ -1782,7 +1844,7 @@ int TC_FN(create)(fsuae_engine* e) {
         softmax_log = ops[k] == FSUAE_ACT_LOG_SOFTMAX;
         ops[k] = FSUAE_ACT_IDENTITY;
       }
-    const int kind = !last ? EPI_STORE : (d.tail == FSUAE_TAIL_SHUFFLE2_RESIDUAL_RELU ? EPI_TAIL_SHUFFLE : EPI_TAIL_PLAIN);
+    const int kind = (!last || features) ? EPI_STORE : (d.tail == FSUAE_TAIL_SHUFFLE2_RESIDUAL_RELU ? EPI_TAIL_SHUFFLE : EPI_TAIL_PLAIN);
     // The residual is normally the layer's own input and is then read from the centre row of the shared-memory ring;
     // a residual from another buffer (the 1x1 skip projections of model_pix_shuffle.py:126-128, 143-145) is read from
     // global memory by the run-time epilogues.
@@ -1812,12 +1874,14 @@ int TC_FN(create)(fsuae_engine* e) {
       }
     }
     if (global_skip || softmax_slot >= 0) exact = fit_ops = widest_ops = nullptr;   // only the run-time epilogue knows about a residual in global memory / a softmax slot
+    const bool big_kernel = L.ksize > 3;       // 5x5 / 7x7: window decomposition on the K-streamed wide kernel
+    if (big_kernel) exact = fit_ops = widest_ops = fit = widest = nullptr;
     if (softmax_slot >= 0 && fit == nullptr && widest != nullptr) widest = nullptr;      // the softmax needs every channel in one launch: wide kernel, one group
     const Variant* var = exact ? exact : fit_ops ? fit_ops : fit ? fit : widest_ops ? widest_ops : widest;
     // Layers whose weights / full-depth input rows do not fit beside each other in shared memory stream K through the
     // wide tile kernel (thin-input layers are cheap to split over output-channel groups instead).
     const bool too_wide = !var || var->NPAD < need;
-    const bool use_wide = !exact && !e->tuning.no_wide && ((too_wide && (PT >= 4 || !var)) || e->tuning.force_wide);
+    const bool use_wide = big_kernel || (!exact && !e->tuning.no_wide && ((too_wide && (PT >= 4 || !var)) || e->tuning.force_wide));
     if (use_wide) {
       const int ngroups = kind == EPI_STORE ? (need + 127) / 128 : 1;
       if (softmax_slot >= 0 && ngroups > 1)
@@ -1833,13 +1897,23 @@ int TC_FN(create)(fsuae_engine* e) {
       if (!wv) return set_error(e, FSUAE_ERR_UNSUPPORTED, tag + "no wide tensor-core kernel for " + std::to_string(L.cout) + " output channels");
       Launch ln;
       ln.wide = wv;
-      std::vector<uint16_t> wp = pack_weights_wide(e->h_blob.data() + L.w_off, L.cout, L.cin0, L.cin1, P0, P1, wv->NT, ngroups);
+      const KWindows kw = k_windows(L.ksize);
+      const int nwin = kw.n1 * kw.n1;
+      std::vector<uint16_t> wp;
+      if (nwin == 1) {
+        wp = pack_weights_wide(e->h_blob.data() + L.w_off, L.cout, L.cin0, L.cin1, P0, P1, wv->NT, ngroups);
+      } else {
+        const std::vector<float> wexp = expand_weights_windows(e->h_blob.data() + L.w_off, L.cout, L.cin0, L.cin1, P0, P1, L.ksize);
+        wp = pack_weights_wide(wexp.data(), L.cout, nwin * PT * 8, 0, nwin * PT, 0, wv->NT, ngroups);
+      }
       FSUAE_CUDA_CHECK(e, cudaMalloc(&ln.d_w, wp.size() * 2));
       FSUAE_CUDA_CHECK(e, cudaMemcpy(ln.d_w, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
       e->device_bytes += wp.size() * 2;
       WideK& k = ln.wk;
       std::memset(&k, 0, sizeof(k));
-      k.P0 = P0; k.pin = PT; k.kchunks = (PT + 1) / 2;
+      k.P0 = P0; k.pin_real = PT; k.nwin = nwin; k.pin = nwin * PT; k.kchunks = (nwin * PT + 1) / 2;
+      for (int wy = 0; wy < kw.n1; ++wy)
+        for (int wx = 0; wx < kw.n1; ++wx) { k.win_dy[wy * kw.n1 + wx] = (signed char)kw.centre[wy]; k.win_dx[wy * kw.n1 + wx] = (signed char)kw.centre[wx]; }
       k.ngroups = ngroups; k.cout = L.cout; k.cpad = ngroups * wv->NT;
       k.has_skip = any_skip;
       k.softmax_slot = softmax_slot; k.softmax_log = softmax_log;
@@ -1979,14 +2053,73 @@ int TC_FN(create)(fsuae_engine* e) {
       }
     }
   }
+  // The whole flagship network as ONE persistent kernel (mega.cuh).  Needs exactly the lightweight preset's seven layers
+  // (its engines are compile-time specialised), wired conv1 -> ... -> conv7 with the residuals on conv2 / conv4 and the
+  // long skip into conv6 (model_pix_shuffle.py:227-298).
+  if (!e->tuning.no_mega && d.n_layers == 7 && unshuffle && d.tail == FSUAE_TAIL_SHUFFLE2_RESIDUAL_RELU) {
+    struct Sig { int PT, NPAD, COUT, pre0, pre1, post0, post1, skip, src0, src1, skip_src; };
+    const Sig want[7] = {
+        {2, 48, 36, FSUAE_ACT_SINLU, FSUAE_ACT_RELU6, 0, 0, 0, 0, -1, -1},
+        {5, 48, 36, FSUAE_ACT_TELU, 0, FSUAE_ACT_SINLU, FSUAE_ACT_BIASED_PRELU, 1, 1, -1, 1},
+        {5, 80, 72, 0, 0, 0, 0, 0, 2, -1, -1},
+        {9, 80, 72, FSUAE_ACT_MISH, FSUAE_ACT_BIASED_PRELU, FSUAE_ACT_TANH, FSUAE_ACT_RELU, 1, 3, -1, 3},
+        {9, 48, 36, 0, 0, 0, 0, 0, 4, -1, -1},
+        {10, 48, 36, FSUAE_ACT_MISH, FSUAE_ACT_RELU6, 0, 0, 0, 1, 5, -1},
+        {5, 16, 12, FSUAE_ACT_BIASED_PRELU, 0, 0, 0, 0, 6, -1, -1}};
+    bool ok = true;
+    for (int i = 0; i < 7 && ok; ++i) {
+      const LayerPlan& lp = plan->layers[i];
+      const fsuae_layer_desc& L = d.layers[i];
+      ok = lp.launches.size() == 1 && lp.launches[0].var2 != nullptr;
+      if (!ok) break;
+      const Variant* v = lp.launches[0].var2;
+      const Sig& w = want[i];
+      ok = v->PT == w.PT && v->NPAD == w.NPAD && v->COUT == w.COUT && v->pre0 == w.pre0 && v->pre1 == w.pre1 && v->post0 == w.post0 &&
+           v->post1 == w.post1 && v->skip == w.skip && L.src0 == w.src0 && (w.src1 < 0 ? L.cin1 == 0 : (L.cin1 > 0 && L.src1 == w.src1)) &&
+           L.skip_src == w.skip_src;
+    }
+    plan->mega_groups = e->sm_count / 8;
+    const int Hw0 = e->H / 2;
+    (void)Hw0;
+    size_t need = 0, flag_words = 0;
+    for (int crop = 0; crop < 2 && ok; ++crop) {            // both geometries an enqueue may ask for (FSUAE_FLAG_CROP16)
+      const int We = e->W - (crop ? 16 : 0);
+      if (We < 2) continue;
+      const int Ww = We / 2, S = (Ww + STRIP - 1) / STRIP, teams = plan->mega_groups / std::max(S, 1);
+      if (S > MG_SMAX || teams < 1) { if (!crop) ok = false; continue; }
+      need = std::max(need, (size_t)teams * 2 * mega_block_bytes(plane_width(S)));
+      flag_words = std::max(flag_words, (size_t)teams * 2 * MG_FLAG_WORDS);
+    }
+    if (ok) {
+      FSUAE_CUDA_CHECK(e, cudaMalloc(&plan->mega_scratch, need));
+      FSUAE_CUDA_CHECK(e, cudaMalloc(&plan->mega_flags, flag_words * sizeof(unsigned int)));
+      FSUAE_CUDA_CHECK(e, cudaMalloc(&plan->mega_zero, PLANE_ROW + 256));
+      FSUAE_CUDA_CHECK(e, cudaMemset(plan->mega_zero, 0, PLANE_ROW + 256));
+      plan->mega_scratch_bytes = need;
+      plan->mega_flag_words = flag_words;
+      e->device_bytes += need + flag_words * sizeof(unsigned int) + PLANE_ROW + 256;
+      for (int i = 0; i < 7; ++i) {
+        const Launch& ln = plan->layers[i].launches[0];
+        MegaLayerP& lp = plan->mega_k.L[i];
+        for (int c = 0; c < MG_MAXC; ++c) {
+          lp.bias[c] = ln.k.bias[c];
+          for (int sl = 0; sl < 4; ++sl) { lp.p0[sl][c] = ln.k.p0[sl][c]; lp.p1[sl][c] = ln.k.p1[sl][c]; }
+        }
+        lp.wpack = ln.d_w2;
+      }
+      FSUAE_CUDA_CHECK(e, cudaFuncSetAttribute((const void*)fused_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM));
+      plan->mega_ok = true;
+    }
+  }
   // activation buffers at the largest geometry (no crop)
   const int Hw = unshuffle ? e->H / 2 : e->H, Ww = unshuffle ? e->W / 2 : e->W;
   const int S = (Ww + STRIP - 1) / STRIP, PW = plane_width(S);
-  plan->buf.assign(d.n_layers, nullptr);
-  plan->planes.assign(d.n_layers, 0);
-  plan->buf_bytes.assign(d.n_layers, 0);
-  for (int i = 0; i < d.n_layers; ++i) {
-    plan->planes[i] = i == 0 ? (unshuffle ? 2 : 1) : planes_of(ch[i]);
+  const int n_bufs = d.n_layers + (features ? 1 : 0);       // a feature-map network also keeps its last layer's output chunk-planar
+  plan->buf.assign(n_bufs, nullptr);
+  plan->planes.assign(n_bufs, 0);
+  plan->buf_bytes.assign(n_bufs, 0);
+  for (int i = 0; i < n_bufs; ++i) {
+    plan->planes[i] = planes_of(ch[i]);
     size_t bytes = (size_t)e->chunk * plan->planes[i] * (Hw + 2 * BORDER) * PW * 16 + 256;
     FSUAE_CUDA_CHECK(e, cudaMalloc(&plan->buf[i], bytes));
     plan->buf_bytes[i] = bytes;
@@ -2003,6 +2136,9 @@ void TC_FN(destroy)(fsuae_engine* e) {
       { if (ln.d_w) cudaFree(ln.d_w); if (ln.d_w2) cudaFree(ln.d_w2); if (ln.d_w3) cudaFree(ln.d_w3); if (ln.d_params) cudaFree(ln.d_params); }
   for (unsigned char* p : e->TC_FIELD->buf)
     if (p) cudaFree(p);
+  if (e->TC_FIELD->mega_scratch) cudaFree(e->TC_FIELD->mega_scratch);
+  if (e->TC_FIELD->mega_flags) cudaFree(e->TC_FIELD->mega_flags);
+  if (e->TC_FIELD->mega_zero) cudaFree(e->TC_FIELD->mega_zero);
   delete e->TC_FIELD;
   e->TC_FIELD = nullptr;
 }
@@ -2013,6 +2149,48 @@ int TC_FN(enqueue_chunk)(fsuae_engine* e, const void* in, void* out, int n, int 
   const fsuae_net_desc& d = e->desc;
   const Geom g = make_geom(e, flags);
   const int S = (g.Ww + STRIP - 1) / STRIP, PW = plane_width(S);
+  // ---- the single fused pass: one persistent kernel, feature maps in L2-resident rings (mega.cuh) ----
+  {
+    const int teams = plan->mega_ok ? plan->mega_groups / S : 0;
+    const int min_frames = e->tuning.mega_min_frames >= 0 ? e->tuning.mega_min_frames : 8;
+    if (teams >= 1 && S <= MG_SMAX && n >= std::max(2, min_frames) &&
+        (size_t)teams * 2 * mega_block_bytes(PW) <= plan->mega_scratch_bytes) {
+      if (plan->mega_zero_Ww != g.Ww) {      // zero borders / unused tail slots of the ring rows for this geometry
+        FSUAE_CUDA_CHECK(e, cudaMemsetAsync(plan->mega_scratch, 0, plan->mega_scratch_bytes, st));
+        plan->mega_zero_Ww = g.Ww;
+      }
+      FSUAE_CUDA_CHECK(e, cudaMemsetAsync(plan->mega_flags, 0, (size_t)teams * 2 * MG_FLAG_WORDS * sizeof(unsigned int), st));
+      MegaK& k = plan->mega_k;
+      k.Hw = g.Hw; k.Ww = g.Ww; k.PW = PW; k.S = S; k.n_frames = n; k.n_fp = (n + 1) / 2; k.teams = teams;
+      k.H = g.H; k.W = g.W; k.xoff = g.xoff; k.in_fmt = in_fmt; k.out_fmt = out_fmt;
+      k.gamma_in = (flags & FSUAE_FLAG_GAMMA_IN) ? 1 : 0;
+      k.gamma_out = (flags & FSUAE_FLAG_GAMMA_OUT) ? 1 : 0;
+      k.frame_in = in; k.frame_out = out;
+      k.scratch = plan->mega_scratch;
+      k.rank_stride = mega_block_bytes(PW, k.ch_off);
+      k.flags = plan->mega_flags;
+      k.zero_row = plan->mega_zero;
+      cudaLaunchConfig_t cfg = cudaLaunchConfig_t{};
+      cudaLaunchAttribute attr[1];
+      cfg.gridDim = dim3(8 * teams * S);
+      cfg.blockDim = dim3(MG_THREADS);
+      cfg.dynamicSmemBytes = MG_SMEM;
+      cfg.stream = st;
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      { ProfScope ps(e, st, "fused_pass");
+        FSUAE_CUDA_CHECK(e, cudaLaunchKernelEx(&cfg, fused_pass_kernel, k)); }
+      e->launches++;
+      if (g.xoff > 0) {
+        black_columns_bf16_kernel<<<64, 256, 0, st>>>(out, n, out_fmt, g.H, g.W, g.xoff);
+        e->launches++;
+      }
+      FSUAE_CUDA_CHECK(e, cudaGetLastError());
+      return FSUAE_OK;
+    }
+  }
   if (plan->zero_Hw != g.Hw || plan->zero_Ww != g.Ww) {   // (re)establish the zero borders for this geometry
     for (size_t i = 0; i < plan->buf.size(); ++i) FSUAE_CUDA_CHECK(e, cudaMemsetAsync(plan->buf[i], 0, plan->buf_bytes[i], st));
     plan->zero_Hw = g.Hw;
@@ -2032,6 +2210,8 @@ int TC_FN(enqueue_chunk)(fsuae_engine* e, const void* in, void* out, int n, int 
   if (d.head == FSUAE_HEAD_UNSHUFFLE2)
     head_unshuffle_bf16_kernel<<<e->sm_count * 8, 256, 0, st>>>(in, plan->buf[0], n, in_fmt, g.H, g.W, g.xoff, g.Hw, g.Ww, PW,
                                                                 fstride(0), gin);
+  else if (d.head == FSUAE_HEAD_FEATURES)
+    head_features_kernel<<<e->sm_count * 8, 256, 0, st>>>((const float*)in, plan->buf[0], n, d.in_channels, g.Hw, g.Ww, PW, fstride(0));
   else
     head_plain_bf16_kernel<<<e->sm_count * 8, 256, 0, st>>>(in, plan->buf[0], n, in_fmt, g.H, g.W, g.xoff, g.Hw, g.Ww, PW,
                                                             fstride(0), gin);
@@ -2047,7 +2227,7 @@ int TC_FN(enqueue_chunk)(fsuae_engine* e, const void* in, void* out, int n, int 
     k.src0 = plan->buf[L.src0]; k.fs0 = fstride(L.src0);
     if (L.cin1 > 0) { k.src1 = plan->buf[L.src1]; k.fs1 = fstride(L.src1); }
     if (L.skip_src >= 0) { k.skip = plan->buf[L.skip_src]; k.fs_skip = fstride(L.skip_src); }
-    if (i < d.n_layers - 1) { k.dst = plan->buf[i + 1]; k.fs_dst = fstride(i + 1); }
+    if (i + 1 < (int)plan->buf.size()) { k.dst = plan->buf[i + 1]; k.fs_dst = fstride(i + 1); }
     k.frame_in = in; k.frame_out = out; k.in_fmt = in_fmt; k.out_fmt = out_fmt;
     k.H = g.H; k.W = g.W; k.xoff = g.xoff;
     k.gamma_in = gin;
@@ -2098,7 +2278,7 @@ int TC_FN(enqueue_chunk)(fsuae_engine* e, const void* in, void* out, int n, int 
         k.src0 = plan->buf[L.src0]; k.fs0 = fstride(L.src0);
         if (L.cin1 > 0) { k.src1 = plan->buf[L.src1]; k.fs1 = fstride(L.src1); }
         if (L.skip_src >= 0) { k.skip = plan->buf[L.skip_src]; k.fs_skip = fstride(L.skip_src); }
-        if (i < d.n_layers - 1) { k.dst = plan->buf[i + 1]; k.fs_dst = fstride(i + 1); }
+        if (i + 1 < (int)plan->buf.size()) { k.dst = plan->buf[i + 1]; k.fs_dst = fstride(i + 1); }
         k.frame_in = in; k.frame_out = out; k.in_fmt = in_fmt; k.out_fmt = out_fmt; k.H = g.H; k.W = g.W; k.xoff = g.xoff;
         k.gamma_in = gin;
         k.gamma_out = (flags & FSUAE_FLAG_GAMMA_OUT) ? 1 : 0;
@@ -2118,6 +2298,11 @@ int TC_FN(enqueue_chunk)(fsuae_engine* e, const void* in, void* out, int n, int 
         FSUAE_CUDA_CHECK(e, cudaLaunchKernelEx(&cfg, var->fn, k)); }
       e->launches++;
     }
+  }
+  if (d.tail == FSUAE_TAIL_FEATURES) {
+    tail_features_kernel<<<e->sm_count * 8, 256, 0, st>>>(plan->buf[d.n_layers], (float*)out, n, d.layers[d.n_layers - 1].cout, g.Hw, g.Ww, PW,
+                                                          fstride(d.n_layers));
+    e->launches++;
   }
   if (g.xoff > 0) {
     black_columns_bf16_kernel<<<64, 256, 0, st>>>(out, n, out_fmt, g.H, g.W, g.xoff);

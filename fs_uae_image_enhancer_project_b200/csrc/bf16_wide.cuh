@@ -20,6 +20,13 @@
 struct WideK {
   int Hw, Ww, PW, S, n_frames;
   int P0, pin, kchunks;          // planes of the first source, total input planes, K slices of 16 channels
+  // Kernels larger than 3x3 (model_pix_shuffle.py:108-115 `layer{i}_kernel_size`; residual_feature_block.py:6): a k x k
+  // convolution is the sum of nwin 3x3 convolutions of the same input shifted by (win_dy, win_dx) pixels -- 4 windows for
+  // 5x5, 9 for 7x7 -- i.e. one 3x3 convolution over nwin * pin_real "virtual" planes whose weights hold each real tap once
+  // and zeros elsewhere.  A shifted window is only a different TMA source address: the planes' baked-in zero border of
+  // BORDER = 3 pixels covers the widest reach (7x7: 2 + 1).
+  int pin_real, nwin;            // planes of the real input (pin = nwin * pin_real); 3x3: nwin = 1
+  signed char win_dy[9], win_dx[9];
   int ngroups, cout, cpad;       // output-channel groups of NT, channels of the layer, stride of the dparams rows
   int rowblocks, n_units;        // 8-row blocks per strip; n_frames * S * rowblocks * ngroups
   int has_skip;
@@ -122,17 +129,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_wide_kernel(const __gr
           mbar_arrive_expect_tx(&full[stage], C::STAGE);
           tma_load_1d(sa + C::A_BYTES, wsrc + (size_t)kc * 2 * C::B_BYTES, C::B_BYTES, &full[stage]);
           const unsigned char* gp[2];
+          int wdy[2];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const int p = min(2 * kc + h, P.pin - 1);      // odd plane count: the last slice re-reads a landed plane against zero weights
+            const int pv = min(2 * kc + h, P.pin - 1);     // odd plane count: the last slice re-reads a landed plane against zero weights
+            const int win = pv / P.pin_real, p = pv - win * P.pin_real;
+            wdy[h] = P.win_dy[win];
             gp[h] = (p < P.P0 ? P.src0 + (size_t)w.f * P.fs0 + (size_t)p * plane_pitch
-                              : P.src1 + (size_t)w.f * P.fs1 + (size_t)(p - P.P0) * plane_pitch) + col;
+                              : P.src1 + (size_t)w.f * P.fs1 + (size_t)(p - P.P0) * plane_pitch) + col + (ptrdiff_t)P.win_dx[win] * 16;
           }
 #pragma unroll
           for (int k = 0; k < C::ROWS + 2; ++k) {
-            const int py = min(w.y0 + k - 1 + BORDER, P.Hw + 2 * BORDER - 1);   // rows below the frame: stay inside the buffer (results discarded)
-            tma_load_1d(sa + (k * 2 + 0) * PLANE_ROW, gp[0] + (size_t)py * row_pitch, PLANE_ROW, &full[stage]);
-            tma_load_1d(sa + (k * 2 + 1) * PLANE_ROW, gp[1] + (size_t)py * row_pitch, PLANE_ROW, &full[stage]);
+            // rows below the frame (results discarded) stay inside the buffer
+            const int py0 = max(0, min(w.y0 + k - 1 + BORDER + wdy[0], P.Hw + 2 * BORDER - 1));
+            const int py1 = max(0, min(w.y0 + k - 1 + BORDER + wdy[1], P.Hw + 2 * BORDER - 1));
+            tma_load_1d(sa + (k * 2 + 0) * PLANE_ROW, gp[0] + (size_t)py0 * row_pitch, PLANE_ROW, &full[stage]);
+            tma_load_1d(sa + (k * 2 + 1) * PLANE_ROW, gp[1] + (size_t)py1 * row_pitch, PLANE_ROW, &full[stage]);
           }
           if (++stage == C::NSTAGE) { stage = 0; par ^= 1; }
         }
@@ -383,6 +395,46 @@ std::vector<uint16_t> pack_weights_wide(const float* w, int cout, int cin0, int 
               }
             }
           }
+  return out;
+}
+
+// Window decomposition of a k x k kernel (k = 5, 7) into 3x3 windows: window centres along one axis and the window that owns
+// each tap offset (the first one that reaches it).
+struct KWindows {
+  int n1;                 // windows per axis
+  int centre[3];
+  int owner[7];           // tap offset o + R -> window index along the axis
+};
+inline KWindows k_windows(int ksize) {
+  KWindows kw{};
+  const int R = ksize / 2;
+  if (ksize == 3) { kw.n1 = 1; kw.centre[0] = 0; }
+  else if (ksize == 5) { kw.n1 = 2; kw.centre[0] = -1; kw.centre[1] = 1; }
+  else { kw.n1 = 3; kw.centre[0] = -2; kw.centre[1] = 0; kw.centre[2] = 2; }
+  for (int o = -R; o <= R; ++o)
+    for (int w = kw.n1 - 1; w >= 0; --w)
+      if (std::abs(o - kw.centre[w]) <= 1) kw.owner[o + R] = w;
+  return kw;
+}
+// [cout][nwin * pin_real * 8][3][3]: the k x k weights spread over the windows' virtual channels (plane-padded channel space)
+inline std::vector<float> expand_weights_windows(const float* w, int cout, int cin0, int cin1, int P0, int P1, int ksize) {
+  const KWindows kw = k_windows(ksize);
+  const int R = ksize / 2, pin = P0 + P1, cin = cin0 + cin1, nwin = kw.n1 * kw.n1, cv = nwin * pin * 8;
+  std::vector<float> out((size_t)cout * cv * 9, 0.f);
+  for (int n = 0; n < cout; ++n)
+    for (int pr = 0; pr < pin; ++pr)
+      for (int k = 0; k < 8; ++k) {
+        int ci;
+        if (pr < P0) { ci = pr * 8 + k; if (ci >= cin0) continue; }
+        else { ci = (pr - P0) * 8 + k; if (ci >= cin1) continue; ci += cin0; }
+        for (int oy = -R; oy <= R; ++oy)
+          for (int ox = -R; ox <= R; ++ox) {
+            const int wy = kw.owner[oy + R], wx = kw.owner[ox + R], win = wy * kw.n1 + wx;
+            const int dy = oy - kw.centre[wy] + 1, dx = ox - kw.centre[wx] + 1;      // tap inside the window's 3x3
+            out[((size_t)n * cv + (size_t)(win * pin + pr) * 8 + k) * 9 + dy * 3 + dx] =
+                w[(((size_t)n * cin + ci) * ksize + (oy + R)) * ksize + (ox + R)];
+          }
+      }
   return out;
 }
 

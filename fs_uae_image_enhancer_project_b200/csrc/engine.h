@@ -90,6 +90,7 @@ inline Geom make_geom(const fsuae_engine* e, uint32_t flags) {
   g.W = e->W;
   g.xoff = (flags & FSUAE_FLAG_CROP16) ? 16 : 0;
   g.We = e->W - g.xoff;
+  if (e->desc.head == FSUAE_HEAD_FEATURES) g.xoff = 0, g.We = e->W;
   if (e->desc.head == FSUAE_HEAD_UNSHUFFLE2) {
     g.Hw = e->H / 2;
     g.Ww = g.We / 2;

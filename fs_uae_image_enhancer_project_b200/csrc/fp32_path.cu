@@ -77,12 +77,15 @@ struct ConvArgs {
   EpiDev epi;
 };
 
-constexpr int TX = 32, TYT = 8, PY = 2, CK = 8;  // tile 32 x 16 pixels, 256 threads, 8 input channels per stage
+constexpr int TX = 32, TYT = 8, PY = 2;  // tile 32 x 16 pixels, 256 threads
 
-template <int CO_T>
+// KS x KS taps (3, 5, 7: model_pix_shuffle.py:108-115 padding = (k - 1) / 2); CK input channels per stage (8; 4 for 7x7 so the
+// patch + weight stage stays inside the 48 KB of static shared memory)
+template <int CO_T, int KS>
 __global__ void __launch_bounds__(TX * TYT) conv3x3_fp32_kernel(ConvArgs a) {
-  __shared__ float patch[CK][TYT * PY + 2][TX + 2];
-  __shared__ __align__(16) float wsm[CK][9][CO_T];
+  constexpr int R = KS / 2, CK = KS == 7 ? 4 : 8, KK = KS * KS;
+  __shared__ float patch[CK][TYT * PY + 2 * R][TX + 2 * R];
+  __shared__ __align__(16) float wsm[CK][KK][CO_T];
 
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const int x0 = blockIdx.x * TX, y0 = blockIdx.y * (TYT * PY);
@@ -101,11 +104,11 @@ __global__ void __launch_bounds__(TX * TYT) conv3x3_fp32_kernel(ConvArgs a) {
 
   for (int c0 = 0; c0 < cin; c0 += CK) {
     // stage the input patch with zero padding outside the frame
-    for (int i = threadIdx.x; i < CK * (TYT * PY + 2) * (TX + 2); i += TX * TYT) {
-      int ci = i / ((TYT * PY + 2) * (TX + 2));
-      int r = i - ci * ((TYT * PY + 2) * (TX + 2));
-      int py = r / (TX + 2), px = r - py * (TX + 2);
-      int y = y0 + py - 1, x = x0 + px - 1, c = c0 + ci;
+    for (int i = threadIdx.x; i < CK * (TYT * PY + 2 * R) * (TX + 2 * R); i += TX * TYT) {
+      int ci = i / ((TYT * PY + 2 * R) * (TX + 2 * R));
+      int r = i - ci * ((TYT * PY + 2 * R) * (TX + 2 * R));
+      int py = r / (TX + 2 * R), px = r - py * (TX + 2 * R);
+      int y = y0 + py - R, x = x0 + px - R, c = c0 + ci;
       float v = 0.f;
       if (c < cin && y >= 0 && y < a.Hw && x >= 0 && x < a.Ww) {
         const float* p = c < a.cin0 ? s0 + (size_t)c * plane : s1 + (size_t)(c - a.cin0) * plane;
@@ -114,27 +117,27 @@ __global__ void __launch_bounds__(TX * TYT) conv3x3_fp32_kernel(ConvArgs a) {
       patch[ci][py][px] = v;
     }
     // stage weights [ci][tap][co]
-    for (int i = threadIdx.x; i < CO_T * CK * 9; i += TX * TYT) {
-      int co = i / (CK * 9);
-      int r = i - co * (CK * 9);
-      int ci = r / 9, tap = r - ci * 9;
+    for (int i = threadIdx.x; i < CO_T * CK * KK; i += TX * TYT) {
+      int co = i / (CK * KK);
+      int r = i - co * (CK * KK);
+      int ci = r / KK, tap = r - ci * KK;
       float v = 0.f;
-      if (co0 + co < a.cout && c0 + ci < cin) v = __ldg(a.w + ((size_t)(co0 + co) * cin + (c0 + ci)) * 9 + tap);
+      if (co0 + co < a.cout && c0 + ci < cin) v = __ldg(a.w + ((size_t)(co0 + co) * cin + (c0 + ci)) * KK + tap);
       wsm[ci][tap][co] = v;
     }
     __syncthreads();
 #pragma unroll
     for (int ci = 0; ci < CK; ++ci) {
 #pragma unroll
-      for (int dy = 0; dy < 3; ++dy) {
+      for (int dy = 0; dy < KS; ++dy) {
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
+        for (int dx = 0; dx < KS; ++dx) {
           float v[PY];
 #pragma unroll
           for (int j = 0; j < PY; ++j) v[j] = patch[ci][ty + j * TYT + dy][tx + dx];
 #pragma unroll
           for (int c4 = 0; c4 < CO_T / 4; ++c4) {
-            float4 w4 = *reinterpret_cast<const float4*>(&wsm[ci][dy * 3 + dx][c4 * 4]);
+            float4 w4 = *reinterpret_cast<const float4*>(&wsm[ci][dy * KS + dx][c4 * 4]);
 #pragma unroll
             for (int j = 0; j < PY; ++j) {
               acc[j][c4 * 4 + 0] = fmaf(v[j], w4.x, acc[j][c4 * 4 + 0]);
@@ -297,7 +300,7 @@ int fp32_create(fsuae_engine* e) {
   const size_t plane = unshuffle ? (size_t)(e->H / 2) * (e->W / 2) : (size_t)e->H * e->W;
   e->buf_channels.assign(d.n_layers + 1, 0);
   e->f32_buf.assign(d.n_layers + 1, nullptr);
-  e->buf_channels[0] = unshuffle ? 12 : 3;
+  e->buf_channels[0] = unshuffle ? 12 : (d.head == FSUAE_HEAD_FEATURES ? 1 : 3);   // a feature-map input is used in place
   for (int i = 0; i < d.n_layers; ++i) e->buf_channels[i + 1] = d.layers[i].cout;
   for (int i = 0; i <= d.n_layers; ++i) {
     size_t bytes = (size_t)e->chunk * e->buf_channels[i] * plane * sizeof(float);
@@ -315,11 +318,13 @@ void fp32_destroy(fsuae_engine* e) {
 }
 
 template <int CO_T>
-static void launch_conv(const ConvArgs& a, int n, cudaStream_t st) {
+static void launch_conv(const ConvArgs& a, int ksize, int n, cudaStream_t st) {
   ConvArgs b = a;
   b.co_groups = (a.cout + CO_T - 1) / CO_T;
   dim3 grid((a.Ww + TX - 1) / TX, (a.Hw + TYT * PY - 1) / (TYT * PY), n * b.co_groups);
-  conv3x3_fp32_kernel<CO_T><<<grid, TX * TYT, 0, st>>>(b);
+  if (ksize == 3) conv3x3_fp32_kernel<CO_T, 3><<<grid, TX * TYT, 0, st>>>(b);
+  else if (ksize == 5) conv3x3_fp32_kernel<CO_T, 5><<<grid, TX * TYT, 0, st>>>(b);
+  else conv3x3_fp32_kernel<CO_T, 7><<<grid, TX * TYT, 0, st>>>(b);
 }
 
 int fp32_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in_fmt, int out_fmt,
@@ -331,7 +336,7 @@ int fp32_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in
 
   // head
   const float* buf0 = e->f32_buf[0];
-  if (d.head == FSUAE_HEAD_PLAIN && in_fmt == FSUAE_FMT_F32_NCHW3 && g.xoff == 0) {
+  if ((d.head == FSUAE_HEAD_PLAIN && in_fmt == FSUAE_FMT_F32_NCHW3 && g.xoff == 0) || d.head == FSUAE_HEAD_FEATURES) {
     buf0 = (const float*)in;  // already planar fp32 at working resolution
   } else if (d.head == FSUAE_HEAD_UNSHUFFLE2) {
     head_kernel<true><<<ew_blocks, 256, 0, st>>>(in, e->f32_buf[0], n, in_fmt, g.H, g.W, g.xoff, g.Hw, g.Ww,
@@ -351,7 +356,8 @@ int fp32_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in
     a.src0 = buf(L.src0);
     a.src1 = L.cin1 > 0 ? buf(L.src1) : nullptr;
     a.skip = L.skip_src >= 0 ? buf(L.skip_src) : nullptr;
-    a.out = e->f32_buf[i + 1];
+    // a feature-map network's last layer writes the caller's output (same planar fp32 layout)
+    a.out = (i == d.n_layers - 1 && d.tail == FSUAE_TAIL_FEATURES) ? (float*)out : e->f32_buf[i + 1];
     a.w = e->d_blob + L.w_off;
     a.bias = L.b_off >= 0 ? e->d_blob + L.b_off : nullptr;
     a.cin0 = L.cin0; a.cin1 = L.cin1; a.cout = L.cout;
@@ -363,15 +369,15 @@ int fp32_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in
     a.epi.n_pre = L.n_pre; a.epi.n_post = L.n_post;
     for (int k = 0; k < L.n_pre; ++k) a.epi.pre[k] = make_act_dev(L.pre[k], e->d_blob);
     for (int k = 0; k < L.n_post; ++k) a.epi.post[k] = make_act_dev(L.post[k], e->d_blob);
-    if (L.cout % 16 == 0) launch_conv<16>(a, n, st);
-    else if (L.cout % 12 == 0) launch_conv<12>(a, n, st);
-    else if (L.cout <= 4) launch_conv<4>(a, n, st);
-    else launch_conv<16>(a, n, st);
+    if (L.cout % 16 == 0) launch_conv<16>(a, L.ksize, n, st);
+    else if (L.cout % 12 == 0) launch_conv<12>(a, L.ksize, n, st);
+    else if (L.cout <= 4) launch_conv<4>(a, L.ksize, n, st);
+    else launch_conv<16>(a, L.ksize, n, st);
     e->launches++;
 
     if (has_softmax) {
       // run the chain as segments split at the softmax slots; the skip add sits between pre and post
-      float* b = e->f32_buf[i + 1];
+      float* b = a.out;
       auto run_ops = [&](const fsuae_act_desc* acts, int cnt, const float* skip_first) {
         ActDev seg[4] = {};
         int ns = 0;
@@ -400,9 +406,11 @@ int fp32_enqueue_chunk(fsuae_engine* e, const void* in, void* out, int n, int in
     }
   }
 
-  tail_kernel<<<ew_blocks, 256, 0, st>>>(e->f32_buf[d.n_layers], buf0, out, n, d.tail, out_fmt, g.H, g.W, g.xoff,
-                                         g.Hw, g.Ww, (flags & FSUAE_FLAG_GAMMA_OUT) ? 1 : 0);
-  e->launches++;
+  if (d.tail != FSUAE_TAIL_FEATURES) {
+    tail_kernel<<<ew_blocks, 256, 0, st>>>(e->f32_buf[d.n_layers], buf0, out, n, d.tail, out_fmt, g.H, g.W, g.xoff,
+                                           g.Hw, g.Ww, (flags & FSUAE_FLAG_GAMMA_OUT) ? 1 : 0);
+    e->launches++;
+  }
   if (g.xoff > 0) {
     black_columns_kernel<<<64, 256, 0, st>>>(out, n, out_fmt, g.H, g.W, g.xoff);
     e->launches++;

@@ -18,7 +18,7 @@ from . import _lib as L
 
 @dataclass
 class LayerSpec:
-    weight: torch.Tensor                    # [Cout, Cin0+Cin1, 3, 3] (BN folded)
+    weight: torch.Tensor                    # [Cout, Cin0+Cin1, k, k], k in {1, 3, 5, 7} (BN folded); 1x1 runs as the centre tap of 3x3
     bias: Optional[torch.Tensor]            # [Cout] or None
     src0: int
     cin0: int
@@ -76,7 +76,7 @@ def _fill_act(dst: L.ActDesc, module, channels: int, blob: BlobBuilder):
             dst.n1, dst.p1_off = n, off
 
 
-def build_descriptor(layers: Sequence[LayerSpec], head: int, tail: int):
+def build_descriptor(layers: Sequence[LayerSpec], head: int, tail: int, in_channels: int = 0):
     """-> (NetDesc, float32 blob).  Identity slots are dropped."""
     if not 1 <= len(layers) <= L.MAX_LAYERS:
         raise ValueError(f"between 1 and {L.MAX_LAYERS} conv layers supported")
@@ -84,12 +84,16 @@ def build_descriptor(layers: Sequence[LayerSpec], head: int, tail: int):
     desc.abi_version = L.ABI_VERSION
     desc.n_layers = len(layers)
     desc.head, desc.tail = head, tail
+    desc.in_channels = in_channels
     blob = BlobBuilder()
     for i, spec in enumerate(layers):
         d = desc.layers[i]
         w = spec.weight
-        if w.dim() != 4 or w.shape[2] != 3 or w.shape[3] != 3:
-            raise ValueError(f"layer {i + 1}: only 3x3 kernels are implemented by the engine, got {tuple(w.shape)}")
+        if w.dim() != 4 or w.shape[2] != w.shape[3] or int(w.shape[2]) not in (1, 3, 5, 7):
+            raise ValueError(f"layer {i + 1}: square kernels of size 1, 3, 5 or 7 are implemented by the engine, got {tuple(w.shape)}")
+        if w.shape[2] == 1:                              # 1x1: centre tap of a 3x3 kernel
+            w = torch.nn.functional.pad(w, (1, 1, 1, 1))
+        d.ksize = int(w.shape[2])
         if w.shape[1] != spec.cin0 + spec.cin1:
             raise ValueError(f"layer {i + 1}: weight has {w.shape[1]} input channels, sources give {spec.cin0 + spec.cin1}")
         d.cin0, d.cin1, d.cout = spec.cin0, spec.cin1, int(w.shape[0])

@@ -21,7 +21,7 @@ MAGIC = b"FSUAEENG"
 
 def export_engine_file(model, path: str) -> int:
     """Serialise a drop-in model (``model_pix_shuffle`` / ``model_conv3`` / ``model_conv5`` instance)."""
-    desc, blob = build_descriptor(model._layer_specs(), model._head, model._tail)
+    desc, blob = build_descriptor(model._layer_specs(), model._head, model._tail, getattr(model, "_in_channels", 0))
     blob = np.ascontiguousarray(blob, dtype=np.float32)
     with open(path, "wb") as f:
         f.write(MAGIC)

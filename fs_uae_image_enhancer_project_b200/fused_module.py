@@ -26,6 +26,7 @@ class FusedEnhancer(nn.Module):
     """
     _head = L.HEAD_PLAIN
     _tail = L.TAIL_PLAIN
+    _in_channels = 0          # HEAD_FEATURES only
     chunk_frames = 8
 
     def __init__(self):
@@ -77,7 +78,7 @@ class FusedEnhancer(nn.Module):
                self._precision(), self.chunk_frames)
         eng = self._engines.get(key)
         if eng is None:
-            desc, blob = build_descriptor(self._layer_specs(), self._head, self._tail)
+            desc, blob = build_descriptor(self._layer_specs(), self._head, self._tail, self._in_channels)
             eng = Engine(desc, blob, key[0], key[3], height, width, self.chunk_frames)
             self._engines[key] = eng
         return eng
@@ -104,6 +105,19 @@ class FusedEnhancer(nn.Module):
         if B == 0:
             return out.to(in_dtype)
         self.engine_for(x.device, H, W).enqueue(xf, out, B, L.FMT_F32_NCHW3, out_fmt)
+        return out if in_dtype == torch.float32 else out.to(in_dtype)
+
+    def _forward_features(self, x: torch.Tensor, out_channels: int) -> torch.Tensor:
+        """Feature-map networks (HEAD_FEATURES / TAIL_FEATURES): float ``[B,C,H,W]`` in, float ``[B,out_channels,H,W]`` out."""
+        self._require_cuda(x)
+        if x.dim() != 4 or x.shape[1] != self._in_channels:
+            raise ValueError(f"expected a [B,{self._in_channels},H,W] tensor, got {tuple(x.shape)}")
+        in_dtype = x.dtype
+        xf = x.contiguous() if x.dtype == torch.float32 else x.float().contiguous()
+        B, _, H, W = xf.shape
+        out = torch.empty((B, out_channels, H, W), dtype=torch.float32, device=x.device)
+        if B:
+            self.engine_for(x.device, H, W).enqueue(xf, out, B, L.FMT_F32_NCHW, L.FMT_F32_NCHW)
         return out if in_dtype == torch.float32 else out.to(in_dtype)
 
     def forward_framebuffer(self, rgba: torch.Tensor, gamma: bool = True, crop16: bool = False) -> torch.Tensor:

@@ -34,22 +34,23 @@ class Model(FusedEnhancer):
 
     def __init__(self, verbose: bool = False, **kwargs):
         """Accepts the reference's keyword arguments: ``layer{1..6}_out_channels`` (default 36),
-        ``layer{1..7}_kernel_size`` (default 3), ``layer{L}_act{K}`` and ``layer{L}_act{K}_params``."""
+        ``layer{1..7}_kernel_size`` (default 3; 1, 3, 5 or 7 here), ``layer{L}_act{K}`` and ``layer{L}_act{K}_params``."""
         super().__init__()
         self.verbose = verbose
         ch = [int(kwargs.pop(f"layer{i}_out_channels", 36)) for i in range(1, 7)]
         ks = [int(kwargs.pop(f"layer{i}_kernel_size", 3)) for i in range(1, 8)]
         for k in ks:
             if k % 2 == 0:
-                raise ValueError("kernel_size must be odd for symmetric padding")
-        if any(k != 3 for k in ks):
-            raise ValueError("the fused engine implements 3x3 convolutions only (both reference presets use 3)")
+                raise ValueError("kernel_size must be odd for symmetric padding")      # reference :81-83
+        if any(k > 7 for k in ks):
+            raise ValueError("the fused engine implements kernel sizes 1, 3, 5 and 7")
         self.channels = tuple(ch)
+        self.kernel_sizes = tuple(ks)
         cin = [12, ch[0], ch[1], ch[2], ch[3], ch[0] + ch[4], ch[5]]
         cout = ch + [12]
         self.pixel_unshuffle = nn.PixelUnshuffle(2)   # structure marker only (no parameters)
         for i in range(7):
-            setattr(self, f"conv{i + 1}", nn.Conv2d(cin[i], cout[i], 3, stride=1, padding=1, bias=True))
+            setattr(self, f"conv{i + 1}", nn.Conv2d(cin[i], cout[i], ks[i], stride=1, padding=(ks[i] - 1) // 2, bias=True))
         for (layer, idx), default in _DEFAULT_ACTS.items():
             name = kwargs.pop(f"layer{layer}_act{idx}", default)
             params = kwargs.pop(f"layer{layer}_act{idx}_params", None)

@@ -42,6 +42,31 @@ def quantize_frames(img: torch.Tensor, color_space: str = "RGB444", style: str =
     return out
 
 
+DITHER_METHODS = {"none": 0, "checkerboard": 1, "bayer2x2": 2, "bayer4x4": 3, "bayer8x8": 4}
+
+
+def dither_frames(img: torch.Tensor, palette: torch.Tensor, method: str = "checkerboard") -> torch.Tensor:
+    """Palette dithers of the reference's dataset generator (quantize.py:137-331; 'none' = nearest palette colour, :529-537).
+    ``img``: CUDA uint8 ``[B,h,w,3|4]``; ``palette``: uint8 ``[N,3]`` (N <= 4096, any device) -> uint8 RGBA ``[B,h,w,4]``.
+    Error-diffusion methods are sequential CPU algorithms and stay in the reference's offline generator."""
+    if method not in DITHER_METHODS:
+        raise ValueError(f"dithering_method must be one of {sorted(DITHER_METHODS)}")       # quantize.py:434-436
+    if not img.is_cuda or img.dtype != torch.uint8 or img.dim() != 4 or img.shape[3] not in (3, 4):
+        raise ValueError("dither_frames needs a CUDA uint8 [B,h,w,3|4] tensor")
+    if palette.dtype != torch.uint8 or palette.dim() != 2 or palette.shape[1] != 3 or palette.shape[0] > 4096:
+        raise ValueError("palette must be uint8 [N,3] with N <= 4096")
+    img = img.contiguous()
+    pal = palette.to(img.device).contiguous()
+    B, h, w, c = img.shape
+    out = torch.empty((B, h, w, 4), dtype=torch.uint8, device=img.device)
+    if B:
+        with torch.cuda.device(img.device):
+            _check(L.load().fsuae_dither_frames(img.data_ptr(), out.data_ptr(), B, h, w, c, pal.data_ptr() if pal.numel() else None,
+                                                pal.shape[0], DITHER_METHODS[method],
+                                                torch.cuda.current_stream(img.device).cuda_stream), "fsuae_dither_frames")
+    return out
+
+
 def synth_rgb444_frames(n_frames: int, height: int = 576, width: int = 752, seed: int = 0, first_frame: int = 0,
                         expand17: bool = True, device=None, out: torch.Tensor | None = None) -> torch.Tensor:
     """``n_frames`` synthetic RGB444 framebuffers ``[n,H,W,4]`` uint8 on the GPU; frame ``first_frame + i`` uses pixel mode

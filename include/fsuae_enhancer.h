@@ -26,6 +26,8 @@
  *   fsuae_engine_destroy     Python GC of the module / OrtReleaseSession
  *   fsuae_quantize_frames    dataset_generator/quantize.py:464-473, 512-521 (grid quantisation, no dithering) +
  *                            dataset_generator/util.py:318-350 (pixel-mode replication)
+ *   fsuae_dither_frames      dataset_generator/quantize.py:137-331 (checkerboard and ordered/Bayer palette dithers, numba) and
+ *                            :529-537 (nearest palette colour)
  *   fsuae_synth_rgb444_frames  the synthetic benchmark stream of SURVEY 8d (README.md:7-10 pixel modes,
  *                            rgb444_flat_image_generator.py:28-30 expansion), generated on the device
  *   fsuae_last_error         Python exception text (ValueError at model_conv3.py:109-110,
@@ -52,7 +54,7 @@ extern "C" {
 #define FSUAE_API
 #endif
 
-#define FSUAE_ABI_VERSION 1
+#define FSUAE_ABI_VERSION 2
 #define FSUAE_MAX_LAYERS 16
 #define FSUAE_MAX_ACTS 4 /* activation slots before / after the skip add (reference uses <= 2) */
 #define FSUAE_MAX_CHUNK_FRAMES 1024 /* upper bound of fsuae_engine_create's max_chunk_frames */
@@ -96,7 +98,9 @@ typedef struct fsuae_act_desc {
   int32_t n1, p1_off; /* count and float offset of parameter 1 */
 } fsuae_act_desc;
 
-/* One 3x3 / stride 1 / zero-pad 1 convolution with its fused epilogue:
+/* One k x k / stride 1 / zero-pad (k-1)/2 convolution (k = 3, 5 or 7: the `layer{i}_kernel_size` constructor arguments of
+ * model/model_pix_shuffle.py:21-64, 108-115 and the `kernel_size` of residual_feature_block.py:6; a 1x1 convolution is
+ * handed over as the centre tap of a 3x3 one) with its fused epilogue:
  *   y = post( skip + pre( conv(cat[src0, src1]) + bias ) )
  * Buffer ids: 0 = the network input after the head stage, i = output of layers[i-1]. */
 typedef struct fsuae_layer_desc {
@@ -104,29 +108,36 @@ typedef struct fsuae_layer_desc {
   int32_t cout;
   int32_t src0, src1;
   int32_t skip_src;   /* -1: no skip add */
-  int32_t w_off;      /* float offset: weights [cout][cin0+cin1][3][3] */
+  int32_t w_off;      /* float offset: weights [cout][cin0+cin1][ksize][ksize] */
   int32_t b_off;      /* float offset: bias [cout]; -1: none */
   int32_t n_pre, n_post;
   fsuae_act_desc pre[FSUAE_MAX_ACTS];
   fsuae_act_desc post[FSUAE_MAX_ACTS];
+  int32_t ksize;      /* 3, 5 or 7 */
+  int32_t reserved;   /* 0 */
 } fsuae_layer_desc;
 
 /* head: how buffer 0 is derived from the frame */
 enum {
   FSUAE_HEAD_PLAIN = 0,      /* 3 channels at full resolution (conv3, conv5) */
-  FSUAE_HEAD_UNSHUFFLE2 = 1  /* PixelUnshuffle(2): 12 channels at half resolution, channel c*4+dy*2+dx */
+  FSUAE_HEAD_UNSHUFFLE2 = 1, /* PixelUnshuffle(2): 12 channels at half resolution, channel c*4+dy*2+dx */
+  FSUAE_HEAD_FEATURES = 2    /* buffer 0 is the input as it is: a float feature map [B,in_channels,H,W] (the building blocks
+                                of model/model_residual_unet.py, e.g. residual_feature_block.py:44-55) */
 };
 /* tail: how the last layer's output becomes the frame */
 enum {
   FSUAE_TAIL_PLAIN = 0,                 /* 3 channels as they are (conv5) */
   FSUAE_TAIL_SHUFFLE2_RESIDUAL_RELU = 1,/* PixelShuffle(2), + input, ReLU (model_pix_shuffle.py:293-296) */
-  FSUAE_TAIL_SCALE255_ALPHA = 2         /* x255 and alpha=255.0 appended (model_conv3.py:145-153) */
+  FSUAE_TAIL_SCALE255_ALPHA = 2,        /* x255 and alpha=255.0 appended (model_conv3.py:145-153) */
+  FSUAE_TAIL_FEATURES = 3               /* the last layer's output as it is: a float feature map [B,cout,H,W] */
 };
 
 typedef struct fsuae_net_desc {
   int32_t abi_version; /* FSUAE_ABI_VERSION */
   int32_t n_layers;
   int32_t head, tail;
+  int32_t in_channels; /* FSUAE_HEAD_FEATURES: channels of the input feature map; otherwise 0 */
+  int32_t reserved;    /* 0 */
   fsuae_layer_desc layers[FSUAE_MAX_LAYERS];
 } fsuae_net_desc;
 
@@ -143,7 +154,9 @@ enum {
   FSUAE_FMT_F32_NCHW3 = 0, /* float [B,3,H,W] in [0,1]; pix_shuffle: linear light (train.py:61) */
   FSUAE_FMT_U8_NHWC4 = 1,  /* uint8 [B,H,W,4] RGBA framebuffer (torch2onnx.py:225-232, 717-756) */
   FSUAE_FMT_U8_NCHW4 = 2,  /* uint8 [B,4,H,W] planar RGBA, input only (model_conv3.py:109-113) */
-  FSUAE_FMT_F32_NCHW4 = 3  /* float [B,4,H,W], output only, with FSUAE_TAIL_SCALE255_ALPHA */
+  FSUAE_FMT_F32_NCHW4 = 3, /* float [B,4,H,W], output only, with FSUAE_TAIL_SCALE255_ALPHA */
+  FSUAE_FMT_F32_NCHW = 4   /* float [B,C,H,W] feature map: C = in_channels on the input side (FSUAE_HEAD_FEATURES), the last
+                              layer's cout on the output side (FSUAE_TAIL_FEATURES) */
 };
 
 /* flags */
@@ -211,6 +224,20 @@ enum {
  * 4 -> 8 bit expansion a real framebuffer holds (rgb444_flat_image_generator.py:28-30), instead of floor(v/16)*16. */
 FSUAE_API int fsuae_quantize_frames(const void* in_dev, void* out_dev_rgba, int n_frames, int in_height, int in_width,
                           int in_channels, int color_space, int sy, int sx, int expand17, void* cuda_stream);
+/* Palette dithers of the dataset generator (dataset_generator/quantize.py:137-331, the numba kernels
+ * _apply_checkerboard_dithering_numba_optimized / _apply_ordered_dithering_numba_optimized, and the palette mapping of
+ * :529-537): every pixel is replaced by a colour of `palette_dev` (uint8 [n_colors][3], device memory, n_colors <= 4096;
+ * how the palette is chosen -- k-means / median cut / octree -- stays on the host, it is offline data preparation).
+ * in: uint8 [n][h][w][in_channels] (3 or 4), out: uint8 RGBA [n][h][w][4], alpha 255.  Bit-exact against the reference. */
+enum {
+  FSUAE_DITHER_NONE = 0,         /* nearest palette colour (first index of the minimum squared distance) */
+  FSUAE_DITHER_CHECKERBOARD = 1, /* closest / second closest colour alternate on (x + y) parity; exact matches stay */
+  FSUAE_DITHER_BAYER2 = 2,       /* ordered dither between the two closest colours by Rec.709 luminance, 2x2 Bayer matrix */
+  FSUAE_DITHER_BAYER4 = 3,
+  FSUAE_DITHER_BAYER8 = 4
+};
+FSUAE_API int fsuae_dither_frames(const void* in_dev, void* out_dev_rgba, int n_frames, int height, int width, int in_channels,
+                        const void* palette_dev, int n_colors, int method, void* cuda_stream);
 /* Synthetic RGB444 framebuffers generated on the device (SURVEY 8d workload): frame g = first_frame + i uses pixel mode
  * g & 3 (lores, lores_laced, hires, hires_laced); every sy x sx cell holds one counter-hashed 12-bit colour
  * (splitmix64 of seed, g, cell), stored as q * 17 (expand17) or q * 16; alpha = 255.  Deterministic in (seed, g). */

@@ -143,12 +143,16 @@ class PixShuffleSpec:
         "l6_act1": ("mish", None), "l6_act2": ("prelu", None),
         "l7_act1": ("sinlu", None), "l7_act2": ("prelu", None),
     })
+    kernel_sizes: Tuple[int, int, int, int, int, int, int] = (3, 3, 3, 3, 3, 3, 3)    # layer{i}_kernel_size (:21-64), padding (k-1)//2 (:108-115)
 
     def with_acts(self, **kw) -> "PixShuffleSpec":
         acts = dict(self.acts)
         for k, v in kw.items():
             acts[k] = v if isinstance(v, tuple) else (v, None)
-        return PixShuffleSpec(self.channels, acts)
+        return PixShuffleSpec(self.channels, acts, self.kernel_sizes)
+
+    def with_kernels(self, *ks) -> "PixShuffleSpec":
+        return PixShuffleSpec(self.channels, dict(self.acts), tuple(ks))
 
 
 def pix_shuffle_preset(name: str) -> PixShuffleSpec:
@@ -188,7 +192,8 @@ def pix_shuffle_forward(sd: Dict[str, torch.Tensor], spec: PixShuffleSpec, x: to
         return apply_activation(name, t, sd, slot, params)
 
     def conv(i, t):
-        return F.conv2d(t, w(f"conv{i}.weight"), w(f"conv{i}.bias"), stride=1, padding=1)
+        k = w(f"conv{i}.weight")
+        return F.conv2d(t, k, w(f"conv{i}.bias"), stride=1, padding=(k.shape[-1] - 1) // 2)        # :108-115
 
     x = x.to(dtype)
     identity = x                                             # :232
@@ -210,6 +215,46 @@ def pix_shuffle_forward(sd: Dict[str, torch.Tensor], spec: PixShuffleSpec, x: to
     x = act("l7_act2", act("l7_act1", conv(7, x)))           # :288-290
     x = F.pixel_shuffle(x, 2)                                # :293
     return torch.relu(identity + x)                          # :295-296
+
+
+# --------------------------------------------------------------------------------------
+# residual feature block (residual_feature_block.py:5-55), the bottleneck of model_residual_unet.py
+# --------------------------------------------------------------------------------------
+
+def residual_block_forward(sd: Dict[str, torch.Tensor], acts: Dict[str, object], x: torch.Tensor,
+                           dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """residual_feature_block.py:44-55: conv1 (1x1) -> conv2 (k x k) -> act1, act2 -> conv3 (1x1) -> act3 -> + identity
+    (proj_conv when present) -> act4.  ``acts``: the block's `acts` dict with 'global' / 'channel' already resolved."""
+    w = lambda k: sd[k].to(dtype)
+    act = lambda key, t: apply_activation(acts[key], t, sd, key, acts.get(key + "_params"))
+    x = x.to(dtype)
+    identity = x
+    t = F.conv2d(x, w("conv1.weight"), w("conv1.bias"))
+    k2 = w("conv2.weight")
+    t = F.conv2d(t, k2, w("conv2.bias"), padding=(k2.shape[-1] - 1) // 2)
+    t = act("act2", act("act1", t))
+    t = act("act3", F.conv2d(t, w("conv3.weight"), w("conv3.bias")))
+    if "proj_conv.weight" in sd:
+        identity = F.conv2d(identity, w("proj_conv.weight"), w("proj_conv.bias"))
+    return act("act4", identity + t)
+
+
+def make_residual_block_state_dict(cin: int, cmid: int, cout: int, ksize: int, acts: Dict[str, object], seed: int):
+    rs = np.random.RandomState(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    for name, (ci, co, k) in (("conv1", (cin, cmid, 1)), ("conv2", (cmid, cmid, ksize)), ("conv3", (cmid, cout, 1))):
+        b = 1.0 / math.sqrt(ci * k * k)
+        sd[f"{name}.weight"] = _u(rs, (co, ci, k, k), -b, b)
+        sd[f"{name}.bias"] = _u(rs, (co,), -b, b)
+    for key in ("act1", "act2", "act3", "act4"):
+        for suffix, shape in activation_param_shapes(acts[key], acts.get(key + "_params")).items():
+            lo, hi = (0.6, 1.7) if suffix in (".a", ".b") else ((-0.1, 0.1) if suffix == ".bias" else (0.05, 0.45))
+            sd[key + suffix] = _u(rs, shape, lo, hi)
+    if cin != cout:
+        b = 1.0 / math.sqrt(cin)
+        sd["proj_conv.weight"] = _u(rs, (cout, cin, 1, 1), -b, b)
+        sd["proj_conv.bias"] = _u(rs, (cout,), -b, b)
+    return sd
 
 
 # --------------------------------------------------------------------------------------
@@ -311,8 +356,9 @@ def make_pix_shuffle_state_dict(spec: PixShuffleSpec, seed: int) -> Dict[str, to
     rs = np.random.RandomState(seed)
     sd: Dict[str, torch.Tensor] = {}
     for i, (ci, co) in enumerate(pix_shuffle_conv_shapes(spec), start=1):
-        k = 1.0 / math.sqrt(ci * 9)
-        sd[f"conv{i}.weight"] = _u(rs, (co, ci, 3, 3), -k, k)
+        ks = spec.kernel_sizes[i - 1]
+        k = 1.0 / math.sqrt(ci * ks * ks)
+        sd[f"conv{i}.weight"] = _u(rs, (co, ci, ks, ks), -k, k)
         sd[f"conv{i}.bias"] = _u(rs, (co,), -k, k)
     for slot in sorted(spec.acts):
         name, params = spec.acts[slot]
@@ -427,6 +473,54 @@ def quantize_frames(img: np.ndarray, color_space: str, style: str, expand17: boo
         np.zeros((0, img.shape[1] * PIXEL_MODES[style][0], img.shape[2] * PIXEL_MODES[style][1], 3), np.uint8)
     alpha = np.full(out.shape[:3] + (1,), 255, np.uint8)
     return np.concatenate([out.astype(np.uint8), alpha], axis=3)
+
+
+BAYER_MATRICES = {      # quantize.py:336-357
+    "bayer2x2": np.array([[0, 2], [3, 1]], dtype=np.int32),
+    "bayer4x4": np.array([[0, 8, 2, 10], [12, 4, 14, 6], [3, 11, 1, 9], [15, 7, 13, 5]], dtype=np.int32),
+    "bayer8x8": np.array([[0, 32, 8, 40, 2, 34, 10, 42], [48, 16, 56, 24, 50, 18, 58, 26], [12, 44, 4, 36, 14, 46, 6, 38],
+                          [60, 28, 52, 20, 62, 30, 54, 22], [3, 35, 11, 43, 1, 33, 9, 41], [51, 19, 59, 27, 49, 17, 57, 25],
+                          [15, 47, 7, 39, 13, 45, 5, 37], [63, 31, 55, 23, 61, 29, 53, 21]], dtype=np.int32),
+}
+
+
+def dither_palette(img: np.ndarray, palette: np.ndarray, method: str) -> np.ndarray:
+    """quantize.py:137-331 + :529-537 restated in vectorised numpy (float64 like the reference): img uint8 [h,w,3],
+    palette uint8 [N,3] -> uint8 [h,w,3].  'none' = nearest palette colour (np.argmin: first minimum), 'checkerboard'
+    (:137-229), 'bayer2x2|4x4|8x8' (:232-331)."""
+    h, w, _ = img.shape
+    n = palette.shape[0]
+    if n == 0:
+        return np.zeros_like(img)
+    if n == 1:
+        return np.broadcast_to(palette[0], img.shape).copy()
+    px = img.astype(np.float64).reshape(-1, 1, 3)
+    pal = palette.astype(np.float64)
+    d = ((px[:, :, 0] - pal[None, :, 0]) ** 2 + (px[:, :, 1] - pal[None, :, 1]) ** 2) + (px[:, :, 2] - pal[None, :, 2]) ** 2
+    i1 = np.argmin(d, axis=1)                                   # first index of the minimum, as the strict '<' loop
+    d1 = d[np.arange(len(d)), i1]
+    if method == "none":
+        return palette[i1].reshape(img.shape)
+    d_rest = d.copy()
+    d_rest[np.arange(len(d)), i1] = np.inf
+    i2 = np.argmin(d_rest, axis=1)
+    yy, xx = np.divmod(np.arange(h * w), w)
+    if method == "checkerboard":
+        chosen = np.where(d1 == 0.0, i1, np.where((xx + yy) % 2 == 0, i1, i2))
+        return palette[chosen].reshape(img.shape)
+    mat = BAYER_MATRICES[method]
+    msz = mat.shape[0]
+    thr = (mat.astype(np.float64) / (msz * msz))[yy % msz, xx % msz]
+    lum = lambda c: (c[:, 0] * 0.2126 + c[:, 1] * 0.7152) + c[:, 2] * 0.0722
+    lp, l1, l2 = lum(px[:, 0, :]), lum(pal[i1]), lum(pal[i2])
+    swap = l1 > l2
+    dark, light = np.where(swap, i2, i1), np.where(swap, i1, i2)
+    la, lb = np.where(swap, l2, l1), np.where(swap, l1, l2)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        frac = np.where(np.abs(lb - la) < 1e-6, 0.0, (lp - la) / (lb - la))
+    frac = np.maximum(0.0, np.minimum(1.0, frac))
+    chosen = np.where(d1 == 0.0, i1, np.where(frac > thr, light, dark))
+    return palette[chosen].reshape(img.shape)
 
 
 def _mix64(z: np.ndarray) -> np.ndarray:

@@ -45,6 +45,7 @@ def import_reference():
 def ref_pix_shuffle(mps, spec: O.PixShuffleSpec):
     c = spec.channels
     kw = {f"layer{i + 1}_out_channels": c[i] for i in range(6)}
+    kw.update({f"layer{i + 1}_kernel_size": k for i, k in enumerate(spec.kernel_sizes)})
     for slot, (name, params) in spec.acts.items():
         layer, idx = slot[1], slot[-1]
         kw[f"layer{layer}_act{idx}"] = name
@@ -127,6 +128,85 @@ def gen_quantize_cases():
     os.chmod(os.path.join(GOLD, "quantize.npz"), 0o644)
 
 
+# kernel sizes other than 3 (model_pix_shuffle.py:21-64, 108-115) and the residual-UNet building block (residual_feature_block.py)
+KSIZE_SPECS = {
+    "ksize_a": O.pix_shuffle_preset("lightweight").with_kernels(5, 3, 5, 3, 7, 5, 3),
+    "ksize_b": O.PixShuffleSpec((16, 16, 24, 24, 16, 16)).with_acts(l1_act1="mish", l2_act2=("biased_relu", {"num_parameters": 16}),
+                                                                    l6_act2=("prelu", None), l7_act1="tanh",
+                                                                    l7_act2="identity").with_kernels(7, 1, 3, 5, 1, 3, 5),
+}
+RESBLOCK_CASES = {   # name: (in, mid, out, kernel_size, acts)
+    "resblock_a": (24, 16, 24, 3, {"act1": "identity", "act1_params": None, "act2": "relu", "act2_params": None,
+                                   "act3": "identity", "act3_params": None, "act4": "relu", "act4_params": None}),
+    "resblock_b": (20, 32, 40, 5, {"act1": "mish", "act1_params": None, "act2": "biased_prelu", "act2_params": {"num_parameters": 32},
+                                   "act3": "sinlu", "act3_params": None, "act4": "prelu", "act4_params": {"num_parameters": 40}}),
+    "resblock_c": (16, 16, 16, 7, {"act1": "telu", "act1_params": None, "act2": "relu6", "act2_params": None,
+                                   "act3": "tanh", "act3_params": None, "act4": "leaky_relu", "act4_params": {"negative_slope": 0.1}}),
+}
+
+
+def gen_ksize_and_block_cases():
+    mps, _, _, _ = import_reference()
+    import residual_feature_block as ref_rfb   # noqa: E402  (imports only `activations`)
+    g = torch.Generator().manual_seed(777)
+    for seed, (name, spec) in enumerate(KSIZE_SPECS.items(), start=71):
+        sd = O.make_pix_shuffle_state_dict(spec, seed)
+        model = ref_pix_shuffle(mps, spec)
+        model.load_state_dict(sd, strict=True)
+        x = torch.rand((2, 3, 44, 60), generator=g) * 1.1
+        with torch.no_grad():
+            y = model(x)
+        np.savez_compressed(os.path.join(GOLD, f"pix_shuffle_{name}.npz"), seed=seed, x=x.numpy(), y=y.numpy())
+        print(f"pix_shuffle {name}: oracle-vs-reference max|d| = {(y - O.pix_shuffle_forward(sd, spec, x)).abs().max().item():.3e}")
+    for seed, (name, (ci, cm, co, ks, acts)) in enumerate(RESBLOCK_CASES.items(), start=81):
+        sd = O.make_residual_block_state_dict(ci, cm, co, ks, acts, seed)
+        blk = ref_rfb.ResidualFeatureBlock(ci, cm, co, ks, acts=acts).eval()
+        blk.load_state_dict(sd, strict=True)
+        x = torch.randn((2, ci, 30, 44), generator=g) * 0.7
+        with torch.no_grad():
+            y = blk(x)
+        np.savez_compressed(os.path.join(GOLD, f"{name}.npz"), seed=seed, x=x.numpy(), y=y.numpy())
+        print(f"{name}: oracle-vs-reference max|d| = {(y - O.residual_block_forward(sd, acts, x)).abs().max().item():.3e}")
+    for f in os.listdir(GOLD):
+        if f.endswith(".npz"):
+            os.chmod(os.path.join(GOLD, f), 0o644)
+
+
+def gen_dither_cases():
+    """dataset_generator/quantize.py: the numba checkerboard / ordered dither kernels and the palette mapping, called
+    directly on seeded images with fixed palettes (palette generation -- k-means etc. -- is not part of the kernels)."""
+    sys.path.insert(0, os.path.join(REF, "dataset_generator"))
+    import quantize as ref_q   # noqa: E402
+    rs = np.random.RandomState(99)
+    h, w = 37, 53
+    yy, xx = np.mgrid[0:h, 0:w]
+    img = np.stack([(xx * 255 // (w - 1)), (yy * 255 // (h - 1)), ((xx + yy) * 255 // (h + w - 2))], axis=2).astype(np.uint8)
+    img[::3, ::2] = rs.randint(0, 256, img[::3, ::2].shape)                      # gradient + noise
+    out = {"img": img}
+    pals = {"p2": np.array([[0, 0, 0], [255, 255, 255]], np.uint8),
+            "p16": (rs.randint(0, 16, (16, 3)) * 17).astype(np.uint8),
+            "p64dup": np.repeat((rs.randint(0, 16, (32, 3)) * 16).astype(np.uint8), 2, axis=0),   # duplicate colours: tie-breaks
+            "p1": np.array([[10, 200, 30]], np.uint8)}
+    img[0, :16] = pals["p16"]                                                  # exact palette hits stay undithered
+    for pname, pal in pals.items():
+        out[pname] = pal
+        palf = pal.astype(np.float64)
+        imf = img.astype(np.float64)
+        res = np.zeros_like(img)
+        ref_q._apply_checkerboard_dithering_numba_optimized(imf, palf, pal, res)
+        out[f"{pname}_checkerboard"] = res.copy()
+        for name, mat in (("bayer2x2", ref_q.BAYER_MATRIX_2X2), ("bayer4x4", ref_q.BAYER_MATRIX_4X4), ("bayer8x8", ref_q.BAYER_MATRIX_8X8)):
+            res = np.zeros_like(img)
+            ref_q._apply_ordered_dithering_numba_optimized(imf, palf, pal, res, mat.astype(np.float64) / (mat.shape[0] ** 2))
+            out[f"{pname}_{name}"] = res.copy()
+        dist = np.sum((imf.reshape(-1, 3)[:, np.newaxis, :] - palf) ** 2, axis=2)      # quantize.py:533-536
+        out[f"{pname}_none"] = pal[np.argmin(dist, axis=1)].reshape(img.shape)
+        for m in ("none", "checkerboard", "bayer2x2", "bayer4x4", "bayer8x8"):
+            print(f"dither {pname} {m}: oracle-vs-reference equal = {np.array_equal(out[f'{pname}_{m}'], O.dither_palette(img, pal, m))}")
+    np.savez_compressed(os.path.join(GOLD, "dither.npz"), **out)
+    os.chmod(os.path.join(GOLD, "dither.npz"), 0o644)
+
+
 def gen_round2_fixtures():
     """Added in round 2 (own option: the earlier fixtures keep their bytes): the other five screenshots + shipped
     predictions of pix_shuffle, conv3_heavy's trained weights with two of its shipped predictions, and the names of the
@@ -163,6 +243,12 @@ def gen_round2_fixtures():
 def main():
     if "--only-round2" in sys.argv:
         gen_round2_fixtures()
+        return
+    if "--only-dither" in sys.argv:
+        gen_dither_cases()
+        return
+    if "--only-ksize" in sys.argv:
+        gen_ksize_and_block_cases()
         return
     if "--only-quantize" in sys.argv:
         gen_quantize_cases()
@@ -243,6 +329,8 @@ def main():
     gen_projection_cases(mps)
     gen_quantize_cases()
     gen_round2_fixtures()
+    gen_dither_cases()
+    gen_ksize_and_block_cases()
     for root, _, files in os.walk(GOLD):
         for f in files:
             os.chmod(os.path.join(root, f), 0o644)

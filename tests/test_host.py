@@ -28,8 +28,8 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layout_matches_header():
     from fs_uae_image_enhancer_project_b200 import _lib
     assert ctypes.sizeof(_lib.ActDesc) == 20
-    assert ctypes.sizeof(_lib.LayerDesc) == 40 + 8 * 20
-    assert ctypes.sizeof(_lib.NetDesc) == 16 + 16 * ctypes.sizeof(_lib.LayerDesc)
+    assert ctypes.sizeof(_lib.LayerDesc) == 40 + 8 * 20 + 8
+    assert ctypes.sizeof(_lib.NetDesc) == 24 + 16 * ctypes.sizeof(_lib.LayerDesc)
 
 
 def test_create_without_gpu_fails_loudly():
@@ -197,8 +197,15 @@ def test_model_constructor_errors():
         model_pix_shuffle.Model(layer3_kernel_size=4)
     with pytest.raises(ValueError, match="odd"):
         model_conv3.Model(kernel_size=2)
-    with pytest.raises(ValueError, match="3x3"):
-        model_pix_shuffle.Model(layer2_kernel_size=5)
+    with pytest.raises(ValueError, match="1, 3, 5 and 7"):
+        model_pix_shuffle.Model(layer2_kernel_size=9)
+    m5 = model_pix_shuffle.Model(layer2_kernel_size=5, layer5_kernel_size=1, layer7_kernel_size=7)     # reference :21-64, 108-115
+    assert tuple(m5.conv2.weight.shape) == (36, 36, 5, 5) and m5.conv2.padding == (2, 2) and tuple(m5.conv5.weight.shape) == (36, 36, 1, 1)
+    from fs_uae_image_enhancer_project_b200.descriptor import build_descriptor
+    d5, blob5 = build_descriptor(m5._layer_specs(), m5._head, m5._tail)
+    assert [d5.layers[i].ksize for i in range(7)] == [3, 5, 3, 3, 3, 3, 7]                             # 1x1 = centre tap of 3x3
+    w5 = blob5[d5.layers[4].w_off:d5.layers[4].w_off + 36 * 36 * 9].reshape(36, 36, 3, 3)
+    assert np.array_equal(w5[:, :, 1, 1], m5.conv5.weight.detach().numpy()[:, :, 0, 0]) and np.abs(w5).sum() == np.abs(w5[:, :, 1, 1]).sum()
     # channel plans with 1x1 skip projections: same parameter names as the reference (:126-128, :143-145), and the
     # projection becomes a layer of its own in the engine descriptor
     m = model_pix_shuffle.Model(layer1_out_channels=24, layer2_out_channels=36, layer3_out_channels=40, layer4_out_channels=40)
@@ -208,6 +215,30 @@ def test_model_constructor_errors():
     assert float(specs[1].weight[:, :, 0, 0].abs().sum()) == 0.0 and specs[1].weight.shape == (36, 24, 3, 3)
     with pytest.raises(ValueError, match="Unsupported activation"):
         model_pix_shuffle.Model(layer1_act1="nonsense")
+
+
+def test_residual_feature_block_keys_and_descriptor():
+    """Drop-in for residual_feature_block.py:5-55: the reference's parameter names, and the block as descriptor layers."""
+    from fs_uae_image_enhancer_project_b200 import _lib, residual_feature_block
+    from fs_uae_image_enhancer_project_b200.descriptor import build_descriptor
+    from tests.util import build_pkg_residual_block
+    m, sd, acts, g = build_pkg_residual_block("resblock_b")                  # 20 -> 32 -> 40 channels, 5x5, projection
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
+    d, blob = build_descriptor(m._layer_specs(), m._head, m._tail, m._in_channels)
+    assert (d.head, d.tail, d.in_channels, d.n_layers) == (_lib.HEAD_FEATURES, _lib.TAIL_FEATURES, 20, 4)
+    L = d.layers
+    assert [(L[i].cin0, L[i].cout, L[i].ksize, L[i].src0, L[i].skip_src) for i in range(4)] == \
+        [(20, 32, 3, 0, -1), (32, 32, 5, 1, -1), (20, 40, 3, 0, -1), (32, 40, 3, 2, 3)]
+    assert (L[1].n_pre, L[3].n_pre, L[3].n_post) == (2, 1, 1)
+    m2, _, _, _ = build_pkg_residual_block("resblock_a")                      # in == out: identity skip, no projection
+    assert m2.proj_conv is None and [s.skip_src for s in m2._layer_specs()] == [-1, -1, 0]
+    with pytest.raises(ValueError, match="odd"):
+        residual_feature_block.ResidualFeatureBlock(8, 8, 8, 4)
+    blk = residual_feature_block.ResidualFeatureBlock(8, 4, 8, 3, acts={"act1": "prelu", "act1_params": {"num_parameters": "channel"},
+                                                                         "act2": "identity", "act2_params": None,
+                                                                         "act3": "prelu", "act3_params": {"num_parameters": "global"},
+                                                                         "act4": "relu", "act4_params": None})
+    assert blk.act1.weight.numel() == 4 and blk.act3.weight.numel() == 1      # reference :24-35
 
 
 def test_onnx_wire_reader_roundtrip(tmp_path):

@@ -117,3 +117,34 @@ def test_synthetic_stream_is_rgb444_in_the_four_pixel_modes():
     assert np.array_equal(O.synth_rgb444_frames(3, 16, 24, seed=5, first_frame=4), fr[4:7])   # a stream can be cut anywhere
     assert not np.array_equal(fr[0], fr[4]) and len(np.unique(fr[3, :, :, 0])) == 16
     assert (O.synth_rgb444_frames(1, 8, 8, seed=5, expand17=False)[..., :3] % 16 == 0).all()
+
+
+def test_dither_oracle_matches_the_reference_numba_kernels():
+    """tests/golden/dither.npz holds outputs of the reference's own _apply_checkerboard_dithering_numba_optimized /
+    _apply_ordered_dithering_numba_optimized (quantize.py:137-331) and its palette mapping (:529-537)."""
+    g = load_gold("dither")
+    for pname in ("p2", "p16", "p64dup", "p1"):
+        for method in ("none", "checkerboard", "bayer2x2", "bayer4x4", "bayer8x8"):
+            assert np.array_equal(O.dither_palette(g["img"], g[pname], method), g[f"{pname}_{method}"]), (pname, method)
+    assert (O.dither_palette(g["img"], np.zeros((0, 3), np.uint8), "checkerboard") == 0).all()
+
+
+@pytest.mark.parametrize("name", ["ksize_a", "ksize_b"])
+def test_oracle_kernel_sizes_match_reference_vectors(name):
+    """layer{i}_kernel_size in {1, 3, 5, 7} (model_pix_shuffle.py:21-64, 108-115): vectors from the real reference Model."""
+    g = load_gold(f"pix_shuffle_{name}")
+    spec = gold_spec(name)
+    sd = O.make_pix_shuffle_state_dict(spec, int(g["seed"]))
+    y = O.pix_shuffle_forward(sd, spec, torch.from_numpy(g["x"])).numpy()
+    assert np.abs(y - g["y"]).max() <= 1e-6
+
+
+@pytest.mark.parametrize("name", ["resblock_a", "resblock_b", "resblock_c"])
+def test_oracle_residual_feature_block_matches_reference_vectors(name):
+    """residual_feature_block.py:5-55 (1x1 -> k x k -> 1x1 bottleneck, optional projection): vectors from the real reference block."""
+    from oracle.gen_golden import RESBLOCK_CASES
+    ci, cm, co, ks, acts = RESBLOCK_CASES[name]
+    g = load_gold(name)
+    sd = O.make_residual_block_state_dict(ci, cm, co, ks, acts, int(g["seed"]))
+    y = O.residual_block_forward(sd, acts, torch.from_numpy(g["x"])).numpy()
+    assert np.abs(y - g["y"]).max() <= 1e-6

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import enhancer_oracle as O
-from tests.util import (GOLD, build_pkg_pix_shuffle, gold_spec, load_gold, load_png_rgb, load_png_rgba,
+from tests.util import (GOLD, build_pkg_pix_shuffle, build_pkg_residual_block, gold_spec, load_gold, load_png_rgb, load_png_rgba,
                         trained_conv3_sd, trained_pix_shuffle_sd)
 
 pytestmark = pytest.mark.gpu
@@ -668,3 +668,142 @@ def test_config4_conv5_heavy_batch32_against_the_oracle():
     m.load_state_dict(sd)
     got = m.to(dev())(x[idx].to(dev())).cpu()          # fp32 build on the two compared frames
     assert (got - want).abs().max().item() <= FP32_TOL
+
+
+# ----------------------------------------------------------------------------------------------
+# The single fused pass (csrc/mega.cuh): the whole flagship network as ONE persistent kernel
+# ----------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("shape", [(2, 64, 96), (3, 34, 254), (5, 40, 600), (4, 2, 2), (7, 6, 508), (2, 130, 752)])
+def test_fused_pass_small_and_ragged_frames(shape, prec, monkeypatch):
+    """One launch for the whole network: 1 / 2 / 3 strips per row (= groups per team), odd frame counts (the last CTA pair
+    computes a frame twice), maps one pixel high (teams with no rows), ranges cut inside a frame (halo rows recomputed)."""
+    B, H, W = shape
+    spec = O.pix_shuffle_preset("lightweight")
+    sd = O.make_pix_shuffle_state_dict(spec, 51)
+    x = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(H + W + B))
+    want = O.pix_shuffle_forward(sd, spec, x)
+    monkeypatch.setenv("FSUAE_MEGA_MIN_FRAMES", "2")
+    m = _tc_model(spec, sd, prec)
+    got = m(x.to(dev())).cpu()
+    eng = m.engine_for(dev(), H, W)
+    assert eng.last_launch_count == 1, eng.last_launch_count           # the fused pass, nothing else
+    tol, psnr = TC_GATES[prec]
+    assert (got - want).abs().max().item() <= tol and O.psnr(got, want, 1.0) >= psnr
+    for _ in range(3):
+        assert torch.equal(m(x.to(dev())).cpu(), got)                  # run-to-run identical bits
+    monkeypatch.setenv("FSUAE_NO_MEGA", "1")                            # layer-by-layer kernels: same network, other MMA order
+    ml = _tc_model(spec, sd, prec)
+    ref = ml(x.to(dev())).cpu()
+    assert ml.engine_for(dev(), H, W).last_launch_count >= 6
+    assert (got - ref).abs().max().item() <= tol / 2
+
+
+@pytest.mark.parametrize("crop16", [False, True])
+def test_fused_pass_framebuffer_contract_full_size(crop16):
+    """uint8 RGBA in -> uint8 RGBA out incl. gamma at 752x576, 12 frames (6 frame pairs over 6 teams: one pair each; with an odd
+    count below, ranges cut frames), against the oracle and against the layer-by-layer kernels."""
+    spec = O.pix_shuffle_preset("lightweight")
+    sd = O.make_pix_shuffle_state_dict(spec, 31)
+    fb = O.synth_framebuffers(12, seed=28)
+    m = _tc_model(spec, sd, "bf16")
+    m.chunk_frames = 16
+    got = m.forward_framebuffer(fb.to(dev()), crop16=crop16).cpu()
+    assert m.engine_for(dev(), 576, 752).last_launch_count == (2 if crop16 else 1)
+    for i in (0, 5, 11):
+        want = O.framebuffer_forward(sd, spec, fb[i:i + 1], crop16=crop16)
+        d = (got[i:i + 1].int() - want.int()).abs()
+        assert d.max().item() <= 8 and (d <= 6).float().mean().item() >= 0.9999 and (d == 0).float().mean().item() >= 0.85
+    assert (got[..., 3] == 255).all()
+    if crop16:
+        assert (got[:, :, :16, :3] == 0).all()
+    got9 = m.forward_framebuffer(fb[:9].to(dev()), crop16=crop16).cpu()      # 5 frame pairs (one frame computed twice) over 6 teams
+    assert torch.equal(got9, got[:9])
+    assert torch.equal(m.run_host(fb.pin_memory(), crop16=crop16), got)
+
+
+def test_fused_pass_is_reproducible_under_load():
+    """The inter-layer rings are re-used every few microseconds and guarded only by flags: 10 runs of a 64-frame pass must
+    give identical bytes, and equal the layer-by-layer result within one rounding step."""
+    spec = O.pix_shuffle_preset("lightweight")
+    sd = O.make_pix_shuffle_state_dict(spec, 82)
+    fb = O.synth_framebuffers(64, seed=5).to(dev())
+    m = _tc_model(spec, sd, "bf16")
+    m.chunk_frames = 64
+    first = m.forward_framebuffer(fb).clone()
+    for _ in range(9):
+        assert torch.equal(m.forward_framebuffer(fb), first)
+
+
+def test_palette_dither_kernels_are_bit_exact():
+    """dataset_generator/quantize.py:137-331 on the device: checkerboard and ordered (Bayer 2/4/8) palette dithers and the
+    nearest-colour mapping, against the outputs of the reference's own numba kernels and, on a batch, against the oracle."""
+    from fs_uae_image_enhancer_project_b200 import synth
+    g = load_gold("dither")
+    img = torch.from_numpy(g["img"])[None].to(dev())
+    methods = ("none", "checkerboard", "bayer2x2", "bayer4x4", "bayer8x8")
+    for pname in ("p2", "p16", "p64dup", "p1"):
+        pal = torch.from_numpy(g[pname])
+        for method in methods:
+            got = synth.dither_frames(img, pal, method).cpu().numpy()
+            assert np.array_equal(got[0, :, :, :3], g[f"{pname}_{method}"]), (pname, method)
+            assert (got[..., 3] == 255).all()
+    rs = np.random.RandomState(5)
+    batch = rs.randint(0, 256, (3, 41, 67, 4)).astype(np.uint8)                     # RGBA input, odd sizes
+    pal = rs.randint(0, 256, (300, 3)).astype(np.uint8)
+    for method in methods:
+        got = synth.dither_frames(torch.from_numpy(batch).to(dev()), torch.from_numpy(pal), method).cpu().numpy()
+        for f in range(3):
+            assert np.array_equal(got[f, :, :, :3], O.dither_palette(batch[f, :, :, :3], pal, method)), method
+    assert (synth.dither_frames(img, torch.zeros((0, 3), dtype=torch.uint8), "bayer4x4").cpu()[..., :3] == 0).all()
+    with pytest.raises(ValueError, match="dithering_method"):
+        synth.dither_frames(img, torch.from_numpy(g["p2"]), "floyd-steinberg")
+
+
+# ----------------------------------------------------------------------------------------------
+# kernel sizes 1 / 5 / 7 (model_pix_shuffle.py:21-64, 108-115) and the residual-UNet building block
+# ----------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "fp16"])
+@pytest.mark.parametrize("name", ["ksize_a", "ksize_b"])
+def test_kernel_sizes_match_reference_vectors(name, prec):
+    """fp32 build: direct k x k taps; tensor-core builds: a k x k kernel as 4 (5x5) / 9 (7x7) shifted 3x3 windows on the
+    K-streamed kernel, 1x1 as the centre tap."""
+    g = load_gold(f"pix_shuffle_{name}")
+    spec = gold_spec(name)
+    sd = O.make_pix_shuffle_state_dict(spec, int(g["seed"]))
+    m = build_pkg_pix_shuffle(spec, sd).to(dev()).set_precision(prec)
+    got = m(torch.from_numpy(g["x"]).to(dev())).cpu()
+    want = torch.from_numpy(g["y"])
+    err, p = (got - want).abs().max().item(), O.psnr(got, want, 1.0)
+    print(f"{name} {prec}: max|d| {err:.2e}, psnr {p:.1f} dB")
+    if prec == "fp32":
+        assert err <= FP32_TOL
+    else:
+        assert err <= TC_GATES[prec][0] and p >= TC_GATES[prec][1]
+    x = torch.rand(3, 3, 30, 520, generator=torch.Generator().manual_seed(12))      # three strips, ragged rows, odd batch
+    got = m(x.to(dev())).cpu()
+    want = O.pix_shuffle_forward(sd, spec, x)
+    assert (got - want).abs().max().item() <= (FP32_TOL if prec == "fp32" else TC_GATES[prec][0])
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "fp16"])
+@pytest.mark.parametrize("name", ["resblock_a", "resblock_b", "resblock_c"])
+def test_residual_feature_block_matches_reference_vectors(name, prec):
+    """residual_feature_block.py:44-55 through the engine: float feature maps in and out (HEAD/TAIL_FEATURES)."""
+    m, sd, acts, g = build_pkg_residual_block(name)
+    m = m.to(dev()).set_precision(prec)
+    got = m(torch.from_numpy(g["x"]).to(dev())).cpu()
+    want = torch.from_numpy(g["y"])
+    scale = float(want.abs().max())
+    err = (got - want).abs().max().item()
+    print(f"{name} {prec}: max|d| {err:.2e} (output scale {scale:.2f})")
+    assert got.shape == want.shape
+    assert err <= (2e-5 if prec == "fp32" else TC_GATES[prec][0] * max(1.0, scale))
+    x = torch.randn(3, m._in_channels, 17, 300, generator=torch.Generator().manual_seed(2)) * 0.5      # three strips
+    want = O.residual_block_forward(sd, acts, x)
+    got = m(x.to(dev())).cpu()
+    assert (got - want).abs().max().item() <= (2e-5 if prec == "fp32" else TC_GATES[prec][0] * max(1.0, float(want.abs().max())))
+    with pytest.raises(ValueError, match="expected"):
+        m(torch.zeros(1, m._in_channels + 1, 8, 8, device=dev()))
