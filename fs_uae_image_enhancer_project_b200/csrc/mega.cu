@@ -1,4 +1,4 @@
-// The single fused pass of the flagship network (included by bf16_tc.cu inside its anonymous namespace).
+// The single fused pass of the flagship network (its own translation unit; compiled once per operand type).
 //
 // Reference semantics: model/model_pix_shuffle.py:227-298 executed as ONE persistent kernel -- input normalisation (gamma LUT,
 // PixelUnshuffle), conv1..conv7 with their activation chains / residual adds / the long-skip concat, PixelShuffle, global
@@ -27,35 +27,13 @@
 //     reads it (the 3x3 taps reach one column into the neighbouring strips).
 //   * Rings: 12 rows per channel, 32 for conv1 -> conv6 (the long skip spans the whole pipeline): 3.4 MB per frame in flight,
 //     12 frames in flight -> 41 MB, well inside the 126 MB L2.
-#pragma once
 
-constexpr int MG_MAXC = 80;          // widest layer of the flagship (72 -> N = 80)
-constexpr int MG_NCH = 6;            // channels: output of conv1..conv6
-constexpr int MG_DMAX = 32;          // deepest ring (power of two: one warp polls a whole ring)
-constexpr int MG_SMAX = 8;           // strips per row the flag block is laid out for
-constexpr int MG_THREADS = 640;      // 4 service warps + 16 epilogue warps
-constexpr int MG_FLAG_WORDS = MG_NCH * MG_DMAX + MG_NCH * 2 * MG_SMAX;      // per (team, rank): prod[ch][slot], cons[ch][consumer][strip]
-__host__ __device__ constexpr int mg_depth(int ch) { return ch == 0 ? 32 : 12; }
+#include "mega_params.h"
+#include "tc_common.cuh"
 
-struct MegaLayerP {
-  float bias[MG_MAXC];
-  float p0[4][MG_MAXC];
-  float p1[4][MG_MAXC];
-  const unsigned char* wpack;        // CTA-pair packing of pack_weights(..., ctas = 2)
-};
+namespace fsuae {
+namespace {
 
-struct MegaK {
-  int Hw, Ww, PW, S, n_frames, n_fp, teams;
-  int H, W, xoff, in_fmt, out_fmt, gamma_in, gamma_out;
-  const void* frame_in;
-  void* frame_out;
-  unsigned char* scratch;                       // [team][rank]{channel rings}
-  unsigned long long rank_stride;               // bytes of one (team, rank) block; team stride = 2 * rank_stride
-  unsigned long long ch_off[MG_NCH];            // channel c inside the block; plane stride = depth * PW * 16
-  unsigned int* flags;                          // [team][rank][MG_FLAG_WORDS]
-  const unsigned char* zero_row;                // one plane row of zeros (rows above / below the frame)
-  MegaLayerP L[7];
-};
 
 // ---- flags ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const unsigned int* p) {
@@ -63,13 +41,46 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const unsigned int* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_gpu(unsigned int* p, uint32_t v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+// Polls use relaxed loads (served by L2, no side effects); the one acquire fence after a successful poll orders what follows.
+// An acquire LOAD invalidates the SM's whole L1 (CCTL.IVALL) every time it is executed -- in a polling loop that stalls
+// every other memory instruction of the SM.
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const unsigned int* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void st_relaxed_gpu(unsigned int* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void red_release_gpu_add(unsigned int* p, uint32_t v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ uint32_t ld_acquire_cta_smem(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t atom_acq_rel_cta_smem_add(uint32_t* p, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+  return old;
+}
 __device__ __forceinline__ unsigned int* mg_prod(unsigned int* fl, int ch) { return fl + ch * MG_DMAX; }
+
+// Cycle accounting of one probe CTA per stage (team 0, middle strip, leader): builds with -DFSUAE_EPI_TIMING only.
+// Per layer: [0] issuer total  [1] issuer waits for input rows  [2] ... for a drained accumulator  [3] issue + commits
+// [4] producer waits for a free ring slot  [5] ... for the upstream layer's rows (flags)  [6] producer total
+// [7] epilogue warp 0 waits for the downstream ring (back-pressure)  [8] ... for the accumulator  [9] math + stores + signals
+// [10] epilogue total  [11] rows of that warp  [12] producer rows  [13] issuer rows  [14] writer-side proxy fence  [15] release of the row counter
+#ifdef FSUAE_EPI_TIMING
+__device__ unsigned long long g_mega_t[8][16];     // row 7: the head producer in detail ([0] next row + loads  [1] slot wait  [2] LUT + stores  [3] fence + arrive  [4] rows)
+#define MG_T(var) const long long var = clock64()
+#define MG_ACC(cond, L, i, v) do { if (cond) g_mega_t[(L) - 1][i] += (unsigned long long)(v); } while (0)
+#else
+#define MG_T(var)
+#define MG_ACC(cond, L, i, v)
+#endif
 __device__ __forceinline__ unsigned int* mg_cons(unsigned int* fl, int ch, int consumer) {
   return fl + MG_NCH * MG_DMAX + (ch * 2 + consumer) * MG_SMAX;
 }
@@ -100,6 +111,11 @@ __device__ __forceinline__ int mg_hi(const MSeg& g, int halo, int Hw) { return m
 // ---- one engine = one layer ---------------------------------------------------------------------------------------------
 // LAYER 1..7.  Sources: conv1 <- the frame (head), conv{2,3,4,5} <- channel LAYER-2, conv6 <- channels 0 (conv1, long skip)
 // and 4 (conv5), conv7 <- channel 5.  Consumer index inside a channel: conv6 is consumer 1 of channel 0, everything else 0.
+// Per-channel epilogue parameters live in shared memory as [9][MG_MAXC] floats (bias, p0[4 slots], p1[4 slots]): the epilogue
+// walks the 8-channel chunks in a ROLLED loop.  Unrolled over 36-72 compile-time channels the code of one stage is ~70 KB of
+// straight-line instructions that a handful of warps run through once per row -- they then wait for the instruction cache
+// more than for anything else (ncu: stall_no_inst).
+constexpr int MG_PRM_BYTES = (9 * MG_MAXC * 4 + 127) / 128 * 128;
 template <int LAYER, int PT_, int NPAD_, int COUT_, int KIND_, class EPI_, int RING_, int STAGES_, int NWG_>
 struct MEng {
   using EPI = EPI_;
@@ -107,7 +123,8 @@ struct MEng {
   static constexpr int HALO = 7 - LAYER;
   static constexpr int STEPS_ROW = (3 * PT + 1) / 2, STEPS = 3 * STEPS_ROW, NB = NPAD / 2;
   static constexpr int WBYTES = STEPS * NB * 32, ROWBYTES = PT * PLANE_ROW;
-  static constexpr int SMEM = WBYTES + RING * ROWBYTES + 128;       // + the 64-byte overrun pad behind the ring (descriptors of the last units reach past it)
+  static constexpr int PRM_OFF = WBYTES + RING * ROWBYTES + 128;    // behind the 64-byte overrun pad of the ring (descriptors of the last units reach past it)
+  static constexpr int SMEM = PRM_OFF + MG_PRM_BYTES;               // + this layer's per-channel epilogue parameters
   static constexpr int TCOLS = STAGES * NPAD;
   static constexpr int NBARS = 3 * RING + 2 * STAGES + 1;           // full, empty, pfull; tfull, tempty; wbar
   static constexpr int IN0 = LAYER == 1 ? -1 : (LAYER == 6 ? 0 : LAYER - 2);
@@ -127,13 +144,19 @@ struct MEng {
 struct MEngSmem {      // shared-memory carve-up of one engine
   uint8_t* w;
   uint8_t* ring;
+  const float* prm;      // [9][MG_MAXC]
   uint64_t *full, *empty, *pfull, *tfull, *tempty, *wbar;
+  uint32_t* rowcnt;      // [MG_NR] epilogue warps that have stored their part of output row q (slot q % MG_NR, never reset)
 };
+constexpr int MG_NR = 8;   // >= accumulator stages: row q + MG_NR cannot reach its epilogue before row q has released its stage
 template <class E>
-__device__ __forceinline__ MEngSmem mg_carve(uint8_t* data, uint64_t* bars) {
+__device__ __forceinline__ MEngSmem mg_carve(uint8_t* data, uint64_t* bars, uint32_t* rowcnt) {
+  static_assert(E::STAGES <= MG_NR, "row counters vs accumulator stages");
   MEngSmem s;
+  s.rowcnt = rowcnt;
   s.w = data;
   s.ring = data + E::WBYTES;
+  s.prm = reinterpret_cast<const float*>(data + E::PRM_OFF);
   s.full = bars;
   s.empty = bars + E::RING;
   s.pfull = bars + 2 * E::RING;
@@ -152,30 +175,41 @@ __device__ __forceinline__ void mg_init_bars(const MEngSmem& s) {     // one thr
 
 struct MCtx {          // where this CTA sits
   int team, strip, rank, f;       // f: the frame this CTA works on inside the current segment is 2 * fp + rank (clamped)
+  bool probe;                     // this CTA feeds the cycle counters (FSUAE_EPI_TIMING builds)
   unsigned char* scratch;         // this (team, rank)'s channel block
   unsigned int* flags;            // this (team, rank)'s flag block
 };
 
 // Wait until rows [q, q + 1) of channel `ch` are complete in every strip.  Whole warp; caches how far the ring is known to be
 // complete (`upto`, exclusive) so that one coalesced poll releases several rows.
-__device__ __forceinline__ void mg_wait_rows(const MegaK& M, const MCtx& c, int ch, uint32_t q, uint32_t& upto, int lane) {
+// A successful poll costs two fences (~1500 cycles) on the one warp that feeds the engine, so it asks for MG_POLL_BATCH rows
+// at a time (fewer at the end of the channel: `qtotal` rows in all).
+#ifndef MG_POLL_BATCH
+#define MG_POLL_BATCH 3
+#endif
+__device__ __forceinline__ void mg_wait_rows(const MegaK& M, const MCtx& c, int ch, uint32_t q, uint32_t qtotal, uint32_t& upto, int lane) {
   if (q < upto) return;
-  const uint32_t D = (uint32_t)mg_depth(ch), need_per_use = 4u * (uint32_t)M.S;     // 4 epilogue warps per strip bump the counter
+  const uint32_t want = min(q + (uint32_t)MG_POLL_BATCH, qtotal) - q;
+  const uint32_t D = (uint32_t)mg_depth(ch), need_per_use = (uint32_t)M.S;          // every strip's publisher bumps the counter once per row
   const unsigned int* prod = mg_prod(c.flags, ch);
   const long long t0 = clock64();
   for (;;) {
     bool ok = false;
     if ((uint32_t)lane < D) {
       const uint32_t qq = q + (uint32_t)lane;
-      ok = ld_acquire_gpu(prod + qq % D) >= need_per_use * (qq / D + 1u);
+      ok = ld_relaxed_gpu(prod + qq % D) >= need_per_use * (qq / D + 1u);
     }
     const uint32_t mask = __ballot_sync(0xffffffffu, ok);
-    const uint32_t cnt = (uint32_t)__ffs((int)~mask) - 1u;      // consecutive complete rows from q on (mask is never all ones: D <= 32 and lanes >= D vote 0 ... D == 32: ffs(0) = 0 -> handled below)
+    const uint32_t cnt = (uint32_t)__ffs((int)~mask) - 1u;      // consecutive complete rows from q on (all ones: ffs(0) = 0 -> handled below)
     const uint32_t n = mask == 0xffffffffu ? 32u : cnt;
-    if (n > 0) { upto = q + n; break; }
+    if (n >= want) { upto = q + n; break; }
     if (clock64() - t0 > (1ll << 31)) __trap();
     __nanosleep(64);
   }
+  // Once per successful poll (it usually reveals several rows): order the bulk copies (async proxy) behind the counters
+  // just read (generic proxy).  The proxy fence costs ~1000 cycles, so it must not sit between "ring slot free" and the copy.
+  fence_acq_rel_gpu();
+  if (lane == 0) fence_proxy_async_all();
   __syncwarp();
 }
 
@@ -197,6 +231,19 @@ __device__ void mg_producer(const MegaK& M, const MCtx& c, const MEngSmem& s, in
   uint32_t fill = 0;                 // ring fills so far
   uint32_t qb0 = 0, qb1 = 0;         // sequence number of the first row the source layers produce in this segment
   uint32_t upto0 = 0, upto1 = 0;
+  uint32_t tot0 = 0, tot1 = 0;       // rows the source layers produce in all
+  {
+    MSegIter it0(M, c.team);
+    MSeg g0;
+    while (it0.next(g0)) {
+      tot0 += (uint32_t)(mg_hi(g0, E::HALO0, M.Hw) - mg_lo(g0, E::HALO0));
+      tot1 += (uint32_t)(mg_hi(g0, E::HALO1, M.Hw) - mg_lo(g0, E::HALO1));
+    }
+  }
+  uint32_t land0[2] = {0, 0}, land1[2] = {0, 0};     // rows of source 0 / 1 below this have been requested by fill - 1 / fill - 2 (lane 0)
+  uint32_t pub0 = 0, pub1 = 0;                       // ... and this is what the producers have been told
+  const bool tprobe = c.probe && lane == 0;
+  MG_T(tp_begin);
   MSegIter it(M, c.team);
   MSeg g;
   while (it.next(g)) {
@@ -206,26 +253,32 @@ __device__ void mg_producer(const MegaK& M, const MCtx& c, const MEngSmem& s, in
       const uint32_t slot = fill % E::RING, par = ((fill / E::RING) & 1u) ^ 1u;
       const bool inframe = y >= 0 && y < M.Hw;
       const uint32_t q0 = qb0 + (uint32_t)(y - lo0), q1 = qb1 + (uint32_t)(y - lo1);
+      MG_T(tp0);
       if (lane == 0) {
-        mbar_wait(&s.empty[slot], par);
-        // the row that lived in this slot has been consumed by the MMAs, so every row more than RING fills back has been
-        // read: tell the producing layer(s) that everything below q - RING may be overwritten
-        if (fill >= (uint32_t)E::RING) {
-          const uint32_t qq0 = inframe ? q0 : (y < 0 ? qb0 : qb0 + (uint32_t)(mg_hi(g, E::HALO0, M.Hw) - lo0));
-          if (qq0 > (uint32_t)E::RING) st_release_gpu(mg_cons(c.flags, E::IN0, E::CONS0) + c.strip, qq0 - (uint32_t)E::RING);
-          if constexpr (E::IN1 >= 0) {
-            const uint32_t qq1 = inframe ? q1 : (y < 0 ? qb1 : qb1 + (uint32_t)(mg_hi(g, E::HALO1, M.Hw) - lo1));
-            if (qq1 > (uint32_t)E::RING) st_release_gpu(mg_cons(c.flags, E::IN1 >= 0 ? E::IN1 : 0, 0) + c.strip, qq1 - (uint32_t)E::RING);
-          }
+        // Credits for the producing layer(s): a channel row may be overwritten once my bulk copy of it has landed.  The copy
+        // of fill - 2 has normally landed long ago (the wait below is a formality), so the producers may run D - 3 rows
+        // ahead of my load pointer.
+        if (fill >= 2u) {
+          const uint32_t f2 = fill - 2u;
+          mbar_wait(&s.full[f2 % E::RING], (f2 / E::RING) & 1u);
+          // relaxed: the store cannot be performed before the wait above has returned, and that wait is what it reports
+          if (land0[1] > pub0) { pub0 = land0[1]; st_relaxed_gpu(mg_cons(c.flags, E::IN0, E::CONS0) + c.strip, pub0); }
+          if constexpr (E::IN1 >= 0)
+            if (land1[1] > pub1) { pub1 = land1[1]; st_relaxed_gpu(mg_cons(c.flags, E::IN1 >= 0 ? E::IN1 : 0, 0) + c.strip, pub1); }
         }
+        land0[1] = land0[0]; land1[1] = land1[0];
+        if (inframe) { land0[0] = q0 + 1u; land1[0] = q1 + 1u; }
       }
       __syncwarp();
-      if (inframe) {
-        mg_wait_rows(M, c, E::IN0, q0, upto0, lane);
-        if constexpr (E::IN1 >= 0) mg_wait_rows(M, c, E::IN1 >= 0 ? E::IN1 : 0, q1, upto1, lane);
+      if (inframe) {       // usually known from an earlier poll: the upstream layer runs ahead while my ring is full
+        mg_wait_rows(M, c, E::IN0, q0, tot0, upto0, lane);
+        if constexpr (E::IN1 >= 0) mg_wait_rows(M, c, E::IN1 >= 0 ? E::IN1 : 0, q1, tot1, upto1, lane);
       }
+      MG_T(tp1);
+      if (lane == 0) mbar_wait(&s.empty[slot], par);
+      MG_T(tp2);
+      MG_ACC(tprobe, E::L, 5, tp1 - tp0); MG_ACC(tprobe, E::L, 4, tp2 - tp1); MG_ACC(tprobe, E::L, 12, 1);
       if (lane == 0) {
-        fence_proxy_async_all();               // the rows were written through the generic proxy (other SMs' epilogues)
         uint8_t* d = s.ring + slot * E::ROWBYTES;
         mbar_arrive_expect_tx(&s.full[slot], E::ROWBYTES);
         if (inframe) {
@@ -247,13 +300,17 @@ __device__ void mg_producer(const MegaK& M, const MCtx& c, const MEngSmem& s, in
     qb0 += (uint32_t)(mg_hi(g, E::HALO0, M.Hw) - lo0);
     qb1 += (uint32_t)(mg_hi(g, E::HALO1, M.Hw) - lo1);
   }
+  MG_T(tp_end);
+  MG_ACC(tprobe, E::L, 6, tp_end - tp_begin);
 }
 
 // ---- producer warp of conv1 = the network head: frame -> gamma LUT -> PixelUnshuffle(2) -> ring rows, no TMA -------------
 // 128 slots per strip row, 4 per lane; a slot is one half-resolution pixel = 2x2 full-resolution pixels x RGB = 12 channels
 // = plane 0 (8 channels) + plane 1 (4 channels, 4 zeros).  Out-of-frame slots are zero (the conv's zero padding).
+// One warp feeds a whole stage, so a row must not cost a trip to HBM: for the framebuffer format (uint8 RGBA) the raw pixels
+// of the NEXT row are already in registers (16 per lane) while the current one goes through the LUT.
 template <class E>
-__device__ void mg_producer_head(const MegaK& M, const MCtx& c, const MEngSmem& s, const float* s_lut, int lane) {
+__device__ void mg_producer_head(const MegaK& M, const MCtx& c, const MEngSmem& s, const float* s_lut, uint4* s_raw, int lane) {
   static_assert(E::L == 1 && E::PT == 2, "head feeds conv1");
   const MegaLayerP& LP = M.L[0];
   if (lane == 0) {
@@ -261,78 +318,141 @@ __device__ void mg_producer_head(const MegaK& M, const MCtx& c, const MEngSmem& 
     tma_load_1d(s.w, LP.wpack + (size_t)c.rank * E::WBYTES, E::WBYTES, s.wbar);
   }
   const size_t fpl = (size_t)M.H * M.W;
+  const bool fb = M.in_fmt == FSUAE_FMT_U8_NHWC4;
   uint32_t fill = 0;
+  const bool tprobe = c.probe && lane == 0;
+  MG_T(tp_begin);
+  // the CTA's row sequence: every segment's input rows lo-1 .. hi
   MSegIter it(M, c.team);
   MSeg g;
-  while (it.next(g)) {
-    const int f = min(2 * g.fp + c.rank, M.n_frames - 1);
-    const int lo = mg_lo(g, E::HALO), hi = mg_hi(g, E::HALO, M.Hw);
-    for (int y = lo - 1; y <= hi; ++y) {
-      const uint32_t slot = fill % E::RING, par = ((fill / E::RING) & 1u) ^ 1u;
-      // issue this row's global loads first, wait for the ring slot afterwards
-      uint32_t raw[4][2][6];          // [slot of this lane][dy][2 pixels x 3 channels: f32 bits, or one u8x4 word per pixel in [0], [1]]
-      bool ok[4];
-#pragma unroll
+  int ycur = 0, yend = -1;
+  auto next_row = [&](int& rf, int& ry) -> bool {
+    if (ycur > yend) {
+      if (!it.next(g)) return false;
+      ycur = mg_lo(g, E::HALO) - 1;
+      yend = mg_hi(g, E::HALO, M.Hw);
+    }
+    rf = min(2 * g.fp + c.rank, M.n_frames - 1);
+    ry = ycur++;
+    return true;
+  };
+  auto store_slot = [&](uint8_t* d, int m, const float (&v)[12]) {
+    *reinterpret_cast<uint4*>(d + m * 16) = make_uint4(pack_op2(v[0], v[1]), pack_op2(v[2], v[3]), pack_op2(v[4], v[5]), pack_op2(v[6], v[7]));
+    *reinterpret_cast<uint4*>(d + PLANE_ROW + m * 16) = make_uint4(pack_op2(v[8], v[9]), pack_op2(v[10], v[11]), 0u, 0u);
+  };
+  auto begin_row = [&]() -> uint8_t* {       // wait for the ring slot of this fill
+    const uint32_t slot = fill % E::RING, par = ((fill / E::RING) & 1u) ^ 1u;
+    MG_T(tp0);
+    if (lane == 0) mbar_wait(&s.empty[slot], par);
+    __syncwarp();
+    MG_T(tp1);
+    MG_ACC(tprobe, E::L, 4, tp1 - tp0); MG_ACC(tprobe, E::L, 12, 1);
+    MG_ACC(tprobe, 8, 1, tp1 - tp0); MG_ACC(tprobe, 8, 4, 1);
+    return s.ring + slot * E::ROWBYTES;
+  };
+  auto end_row = [&]() {
+    fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's reads
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s.full[fill % E::RING]);
+    ++fill;
+  };
+  if (fb) {
+    // Framebuffer format (uint8 RGBA, the streaming case).  The raw pixels of the NEXT row travel global -> shared memory by
+    // cp.async (no registers in between: a register FIFO stalls on its own moves, and unrolled over the lane's four slots the
+    // body was 14 KB of code this single warp fetched anew for every row), the current row goes through the LUT in a rolled
+    // loop of ~100 instructions.  Slot = {dy 0: px 0, px 1; dy 1: px 0, px 1} = 16 bytes; out of frame -> zero fill -> LUT[0] = 0.
+    auto prefetch = [&](int rf, int ry, uint4* buf) {
+#pragma unroll 1
       for (int i = 0; i < 4; ++i) {
-        const int m = lane + 32 * i;
-        const int x = c.strip * STRIP - 1 + m;
-        ok[i] = y >= 0 && y < M.Hw && x >= 0 && x < M.Ww;
-        if (ok[i]) {
+        const int m = lane + 32 * i, x = c.strip * STRIP - 1 + m;
+        const bool ok = ry >= 0 && ry < M.Hw && x >= 0 && x < M.Ww;
+        const unsigned char* ip = (const unsigned char*)M.frame_in + (ok ? ((size_t)rf * fpl + (size_t)(2 * ry) * M.W + 2 * x + M.xoff) * 4 : 0);
+        const uint32_t dst = smem_u32(buf + m), n = ok ? 8u : 0u;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(ip), "r"(n) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + 8u), "l"(ip + (size_t)M.W * 4), "r"(n) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // Three staging rows: the copy of row r + 2 is issued BEHIND row r's proxy fence (the fence waits for every memory
+    // operation of the warp that is still in flight, cp.async included), so it has a whole row period to land.
+    int fC, yC, fN = 0, yN = 0, fP = 0, yP = 0;
+    bool haveC = next_row(fC, yC), haveN = false;
+    uint32_t rowno = 0;
+    if (haveC) {
+      prefetch(fC, yC, s_raw);
+      haveN = next_row(fN, yN);
+      if (haveN) prefetch(fN, yN, s_raw + MROWS);
+    }
+    while (haveC) {
+      const bool haveP = haveN && next_row(fP, yP);
+      uint8_t* d = begin_row();
+      MG_T(tw0);
+      if (haveN) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      const uint4* src = s_raw + (rowno % 3u) * MROWS;
+#pragma unroll 1
+      for (int i = 0; i < 4; ++i) {
+        const uint4 cur = src[lane + 32 * i];          // written by this very lane
+        float v[12];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          v[ch * 4 + 0] = s_lut[(cur.x >> (8 * ch)) & 0xFF];
+          v[ch * 4 + 1] = s_lut[(cur.y >> (8 * ch)) & 0xFF];
+          v[ch * 4 + 2] = s_lut[(cur.z >> (8 * ch)) & 0xFF];
+          v[ch * 4 + 3] = s_lut[(cur.w >> (8 * ch)) & 0xFF];
+        }
+        store_slot(d, lane + 32 * i, v);
+      }
+      MG_T(tw1);
+      end_row();
+      MG_T(tw2);
+      MG_ACC(tprobe, 8, 2, tw1 - tw0); MG_ACC(tprobe, 8, 3, tw2 - tw1);
+      if (haveP) prefetch(fP, yP, s_raw + ((rowno + 2u) % 3u) * MROWS);
+      fC = fN; yC = yN; haveC = haveN;
+      fN = fP; yN = yP; haveN = haveP;
+      ++rowno;
+    }
+  } else {
+    // float / planar uint8 frames (not the streaming format): slot by slot, rolled -- this path only has to be correct
+    int rf, ry;
+    while (next_row(rf, ry)) {
+      uint8_t* d = begin_row();
+#pragma unroll 1
+      for (int i = 0; i < 4; ++i) {
+        const int x = c.strip * STRIP - 1 + lane + 32 * i;
+        const bool ok = ry >= 0 && ry < M.Hw && x >= 0 && x < M.Ww;
+        float v[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) v[k] = 0.f;
+        if (ok) {
 #pragma unroll
           for (int dy = 0; dy < 2; ++dy) {
-            const size_t p0 = (size_t)(2 * y + dy) * M.W + 2 * x + M.xoff;
+            const size_t p0 = (size_t)(2 * ry + dy) * M.W + 2 * x + M.xoff;
             if (M.in_fmt == FSUAE_FMT_F32_NCHW3) {
-              const float* ip = (const float*)M.frame_in + (size_t)f * 3 * fpl + p0;
+              const float* ip = (const float*)M.frame_in + (size_t)rf * 3 * fpl + p0;
 #pragma unroll
               for (int ch = 0; ch < 3; ++ch) {
                 const float2 t2 = __ldg(reinterpret_cast<const float2*>(ip + ch * fpl));
-                raw[i][dy][2 * ch] = __float_as_uint(t2.x); raw[i][dy][2 * ch + 1] = __float_as_uint(t2.y);
+                v[ch * 4 + dy * 2] = t2.x; v[ch * 4 + dy * 2 + 1] = t2.y;
               }
-            } else if (M.in_fmt == FSUAE_FMT_U8_NHWC4) {
-              const uint2 t2 = __ldg(reinterpret_cast<const uint2*>((const unsigned char*)M.frame_in + ((size_t)f * fpl + p0) * 4));
-              raw[i][dy][0] = t2.x; raw[i][dy][1] = t2.y;
             } else {
-              const unsigned char* ip = (const unsigned char*)M.frame_in + (size_t)f * 4 * fpl + p0;
+              const unsigned char* ip = (const unsigned char*)M.frame_in + (size_t)rf * 4 * fpl + p0;
 #pragma unroll
-              for (int ch = 0; ch < 3; ++ch) { raw[i][dy][2 * ch] = __ldg(ip + ch * fpl); raw[i][dy][2 * ch + 1] = __ldg(ip + ch * fpl + 1); }
+              for (int ch = 0; ch < 3; ++ch) { v[ch * 4 + dy * 2] = s_lut[__ldg(ip + ch * fpl)]; v[ch * 4 + dy * 2 + 1] = s_lut[__ldg(ip + ch * fpl + 1)]; }
             }
           }
         }
+        store_slot(d, lane + 32 * i, v);
       }
-      if (lane == 0) mbar_wait(&s.empty[slot], par);
-      __syncwarp();
-      uint8_t* d = s.ring + slot * E::ROWBYTES;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int m = lane + 32 * i;
-        float v[12];
-        if (ok[i]) {
-#pragma unroll
-          for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-              float a, b;
-              if (M.in_fmt == FSUAE_FMT_F32_NCHW3) { a = __uint_as_float(raw[i][dy][2 * ch]); b = __uint_as_float(raw[i][dy][2 * ch + 1]); }
-              else if (M.in_fmt == FSUAE_FMT_U8_NHWC4) { a = s_lut[(raw[i][dy][0] >> (8 * ch)) & 0xFF]; b = s_lut[(raw[i][dy][1] >> (8 * ch)) & 0xFF]; }
-              else { a = s_lut[raw[i][dy][2 * ch] & 0xFF]; b = s_lut[raw[i][dy][2 * ch + 1] & 0xFF]; }
-              v[ch * 4 + dy * 2] = a; v[ch * 4 + dy * 2 + 1] = b;
-            }
-        } else {
-#pragma unroll
-          for (int k = 0; k < 12; ++k) v[k] = 0.f;
-        }
-        *reinterpret_cast<uint4*>(d + m * 16) = make_uint4(pack_op2(v[0], v[1]), pack_op2(v[2], v[3]), pack_op2(v[4], v[5]), pack_op2(v[6], v[7]));
-        *reinterpret_cast<uint4*>(d + PLANE_ROW + m * 16) = make_uint4(pack_op2(v[8], v[9]), pack_op2(v[10], v[11]), 0u, 0u);
-      }
-      fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's reads
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s.full[slot]);
-      ++fill;
+      end_row();
     }
   }
+  MG_T(tp_end);
+  MG_ACC(tprobe, E::L, 6, tp_end - tp_begin);
 }
 
 // ---- peer CTA of the pair: relay "my ring row has landed" to the leader (one lane per ring slot) -------------------------
+// test_wait, not try_wait: try_wait suspends a lane for a while when its barrier is not complete, and the warp's instruction
+// only retires when the slowest lane does -- most lanes watch slots that fill much later.
 template <class E>
 __device__ void mg_relay(const MegaK& M, const MCtx& c, const MEngSmem& s, int lane) {
   uint32_t total = 0;
@@ -346,7 +466,7 @@ __device__ void mg_relay(const MegaK& M, const MCtx& c, const MEngSmem& s, int l
   uint32_t done = 0, par = 0;
   long long t0 = clock64();
   while (__any_sync(0xffffffffu, done < fills)) {
-    if (done < fills && mbar_try_wait(&s.full[active ? lane : 0], par)) {
+    if (done < fills && mbar_test_wait(&s.full[active ? lane : 0], par)) {
       mbar_arrive_cluster(&s.pfull[lane], 0);
       par ^= 1u;
       ++done;
@@ -366,20 +486,30 @@ __device__ void mg_issuer(const MegaK& M, const MCtx& c, const MEngSmem& s, uint
   uint32_t wslot = 0, wpar = 0, stage = 0, spar = 1;
   auto wait_row = [&]() {
     mbar_wait(&s.full[wslot], wpar);
+    MG_T(tw_a);
     mbar_wait(&s.pfull[wslot], wpar);
+    MG_T(tw_b);
+    MG_ACC(c.probe, 8, 7 + E::L, tw_b - tw_a);        // row 7, [8 .. 14]: the part of the input-row waits spent on the peer's relay
     if (++wslot == E::RING) { wslot = 0; wpar ^= 1u; }
   };
+  MG_T(ti_begin);
   MSegIter it(M, c.team);
   MSeg g;
   while (it.next(g)) {
     const int rows = mg_hi(g, E::HALO, M.Hw) - mg_lo(g, E::HALO);
     uint32_t s0 = wslot;
+    MG_T(ti_a);
     wait_row();
     wait_row();
+    MG_T(ti_b);
+    MG_ACC(c.probe, E::L, 1, ti_b - ti_a);
     for (int b = 0; b < rows; ++b) {
+      MG_T(ti0);
       wait_row();
+      MG_T(ti1);
       mbar_wait(&s.tempty[stage], spar);
       tc_fence_after();
+      MG_T(ti2);
       issue_block_2cta<E::PT, PLANE_ROW / 16, E::NB>(tmem_cols + stage * E::NPAD, ring_lo, E::ROWBYTES >> 4, s0, E::RING, w_lo, IDESC);
       umma_commit_2cta(&s.tfull[stage]);
       umma_commit_2cta(&s.empty[s0]);
@@ -388,9 +518,32 @@ __device__ void mg_issuer(const MegaK& M, const MCtx& c, const MEngSmem& s, uint
         umma_commit_2cta(&s.empty[s1]);
         umma_commit_2cta(&s.empty[s2]);
       }
+      MG_T(ti3);
+      MG_ACC(c.probe, E::L, 1, ti1 - ti0); MG_ACC(c.probe, E::L, 2, ti2 - ti1); MG_ACC(c.probe, E::L, 3, ti3 - ti2); MG_ACC(c.probe, E::L, 13, 1);
       if (++s0 == E::RING) s0 = 0;
       if (++stage == E::STAGES) { stage = 0; spar ^= 1u; }
     }
+  }
+  MG_T(ti_end);
+  MG_ACC(c.probe, E::L, 0, ti_end - ti_begin);
+}
+
+// one activation slot (compile-time op-code) on the 8 channels of a chunk; prm -> this chunk's column of the parameter table
+template <int OP>
+__device__ __forceinline__ void mg_slot8(int slot, const float* prm, float (&o)[8]) {
+  if constexpr (OP != FSUAE_ACT_IDENTITY) {
+    float p0[8], p1[8];
+    if constexpr (((ACT_PARAM_MASK >> OP) & 1u) != 0) {
+      const float4 a0 = *reinterpret_cast<const float4*>(prm + (1 + slot) * MG_MAXC), a1 = *reinterpret_cast<const float4*>(prm + (1 + slot) * MG_MAXC + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(prm + (5 + slot) * MG_MAXC), b1 = *reinterpret_cast<const float4*>(prm + (5 + slot) * MG_MAXC + 4);
+      p0[0] = a0.x; p0[1] = a0.y; p0[2] = a0.z; p0[3] = a0.w; p0[4] = a1.x; p0[5] = a1.y; p0[6] = a1.z; p0[7] = a1.w;
+      p1[0] = b0.x; p1[1] = b0.y; p1[2] = b0.z; p1[3] = b0.w; p1[4] = b1.x; p1[5] = b1.y; p1[6] = b1.z; p1[7] = b1.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { p0[i] = 0.f; p1[i] = 0.f; }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = act_rt(OP, o[i], p0[i], p1[i]);
   }
 }
 
@@ -410,6 +563,8 @@ __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, ui
   unsigned int* prod = mg_prod(c.flags, E::OUT >= 0 ? E::OUT : 0);
   uint32_t blk = 0, qrow = 0, qout = 0;          // blocks / ring rows / output rows before this segment
   uint32_t cons_seen = 0;                        // every row below this has been read by all my consumers
+  const bool tprobe = c.probe && wg == 0 && q4 == 0 && lane == 0;
+  MG_T(te_begin);
   MSegIter it(M, c.team);
   MSeg g;
   while (it.next(g)) {
@@ -420,6 +575,7 @@ __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, ui
       const uint32_t stage = blk % E::STAGES, spar = (blk / E::STAGES) & 1u;
       const int y = lo + b;
       const uint32_t q = qout + (uint32_t)b;     // sequence number of this output row in my channel
+      MG_T(te0);
 
       uint32_t raw[E::KIND == EPI_TAIL_SHUFFLE ? 2 : 1][6];
       if constexpr (E::KIND == EPI_TAIL_SHUFFLE) {
@@ -455,18 +611,20 @@ __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, ui
             uint32_t v = 0xFFFFFFFFu;
             if (lane < 3 * E::OUT_NCONS) {
               const int k = lane / 3, sn = c.strip - 1 + lane % 3;
-              if (sn >= 0 && sn < M.S) v = ld_acquire_gpu(mg_cons(c.flags, E::OUT >= 0 ? E::OUT : 0, k) + sn);
+              if (sn >= 0 && sn < M.S) v = ld_relaxed_gpu(mg_cons(c.flags, E::OUT >= 0 ? E::OUT : 0, k) + sn);
             }
             v = __reduce_min_sync(0xffffffffu, v);
-            if (v >= need) { cons_seen = v; break; }
+            if (v >= need) { cons_seen = v; fence_acq_rel_gpu(); break; }
             if (clock64() - t0 > (1ll << 31)) __trap();
             __nanosleep(64);
           }
         }
       }
 
+      MG_T(te1);
       mbar_wait(&s.tfull[stage], spar);
       tc_fence_after();
+      MG_T(te2);
       const uint32_t taddr = tmem_cols + ((uint32_t)(q4 * 32) << 16) + stage * E::NPAD;
       // residual = this layer's input at the same pixel = centre row of the block, still in the ring (see conv3x3_tc_kernel)
       const uint32_t kc = qrow + (uint32_t)b + 1;
@@ -475,39 +633,54 @@ __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, ui
       if constexpr (EPI::kSkip) mbar_wait(&s.full[cslot], (kc / E::RING) & 1);
 
       if constexpr (E::KIND == EPI_STORE) {
-        uint4 sk[EPI::kSkip ? E::OUT_PLANES : 1];
-        if constexpr (EPI::kSkip) {
-#pragma unroll
-          for (int cc = 0; cc < E::OUT_PLANES; ++cc)
-            sk[cc] = valid ? *reinterpret_cast<const uint4*>(sp + cc * PLANE_ROW) : make_uint4(0, 0, 0, 0);
-        }
         unsigned char* dp = och + (size_t)(q % (uint32_t)D) * row_pitch + (size_t)(x + BORDER) * 16;
-#pragma unroll
+#pragma unroll 1
         for (int cc = 0; cc < E::OUT_PLANES; ++cc) {
           uint32_t v[8];
           tmem_ld_x8(taddr + cc * 8, v);
+          const float* prm = s.prm + cc * 8;
+          const float4 b0 = *reinterpret_cast<const float4*>(prm), b1 = *reinterpret_cast<const float4*>(prm + 4);
+          uint4 skc = make_uint4(0, 0, 0, 0);
+          if constexpr (EPI::kSkip) {
+            if (valid) skc = *reinterpret_cast<const uint4*>(sp + cc * PLANE_ROW);
+          }
           tmem_ld_wait();
           float o[8];
+          o[0] = __uint_as_float(v[0]) + b0.x; o[1] = __uint_as_float(v[1]) + b0.y; o[2] = __uint_as_float(v[2]) + b0.z;
+          o[3] = __uint_as_float(v[3]) + b0.w; o[4] = __uint_as_float(v[4]) + b1.x; o[5] = __uint_as_float(v[5]) + b1.y;
+          o[6] = __uint_as_float(v[6]) + b1.z; o[7] = __uint_as_float(v[7]) + b1.w;
+          mg_slot8<EPI::kOp0>(0, prm, o);
+          mg_slot8<EPI::kOp1>(1, prm, o);
+          if constexpr (EPI::kSkip) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int ch = cc * 8 + i;
-            if (ch >= E::COUT) { o[i] = 0.f; continue; }
-            float t = EPI::pre(P, ch, __uint_as_float(v[i]) + P.bias[ch]);
-            if constexpr (EPI::kSkip) {
-              const uint32_t w = (&sk[cc].x)[i >> 1];
-              t += (i & 1) ? op_hi(w) : op_lo(w);
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t w = (&skc.x)[i >> 1];
+              o[i] += (i & 1) ? op_hi(w) : op_lo(w);
             }
-            o[i] = EPI::post(P, ch, t);
+          }
+          mg_slot8<EPI::kOp2>(2, prm, o);
+          mg_slot8<EPI::kOp3>(3, prm, o);
+          if constexpr (E::COUT % 8 != 0) {
+            if (cc == E::OUT_PLANES - 1) {       // padding channels stay exactly zero
+#pragma unroll
+              for (int i = E::COUT % 8; i < 8; ++i) o[i] = 0.f;
+            }
           }
           if (valid)
             *reinterpret_cast<uint4*>(dp + (size_t)cc * plane_pitch) =
                 make_uint4(pack_op2(o[0], o[1]), pack_op2(o[2], o[3]), pack_op2(o[4], o[5]), pack_op2(o[6], o[7]));
         }
-        // publish: my quarter of this strip row is in place (generic stores -> other SMs' TMA reads)
-        fence_proxy_async_all();
+        // The last of the four warps to finish row q bumps the channel's row counter: its release at gpu scope is cumulative
+        // over the CTA-scope acquire / release on the shared-memory counter, so it covers the other warps' stores as well,
+        // and only one warp per row waits (~1000 cycles) for the stores to reach L2.
+        MG_T(tf0);
         __syncwarp();
         if (lane == 0) {
-          red_release_gpu_add(prod + q % (uint32_t)D, 1u);
+          const uint32_t before = atom_acq_rel_cta_smem_add(s.rowcnt + q % (uint32_t)MG_NR, 1u);
+          MG_T(tf1);
+          if ((before & 3u) == 3u) red_release_gpu_add(prod + q % (uint32_t)D, 1u);
+          MG_T(tf2);
+          MG_ACC(tprobe, E::L, 14, tf1 - tf0); MG_ACC(tprobe, E::L, 15, tf2 - tf1);
           if constexpr (EPI::kSkip) {            // residual values consumed: release the ring rows
             mbar_arrive(&s.empty[cslot]);
             if (b == 0) mbar_arrive(&s.empty[(kc - 1) % E::RING]);
@@ -563,10 +736,14 @@ __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, ui
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&s.tempty[stage], 0);
+      MG_T(te3);
+      MG_ACC(tprobe, E::L, 7, te1 - te0); MG_ACC(tprobe, E::L, 8, te2 - te1); MG_ACC(tprobe, E::L, 9, te3 - te2); MG_ACC(tprobe, E::L, 11, 1);
     }
     qrow += (uint32_t)rows + 2u;
     qout += (uint32_t)rows;
   }
+  MG_T(te_end);
+  MG_ACC(tprobe, E::L, 10, te_end - te_begin);
 }
 
 // ---- the engines of the flagship preset (model_pix_shuffle.py:306-311) ---------------------------------------------------
@@ -579,7 +756,7 @@ using MgConv5 = MEng<5, 9, 48, 36, EPI_STORE, Epi<0, 0, 0, 0, false>, 6, 6, 2>;
 using MgConv6 = MEng<6, 10, 48, 36, EPI_STORE, Epi<MG_A(MISH), MG_A(RELU6), 0, 0, false>, 6, 6, 2>;
 using MgConv7 = MEng<7, 5, 16, 12, EPI_TAIL_SHUFFLE, Epi<MG_A(BIASED_PRELU), 0, 0, 0, false>, 6, 6, 2>;
 #undef MG_A
-struct MgNone { static constexpr int SMEM = 0, TCOLS = 0, NBARS = 0, NWG = 0; };
+struct MgNone { static constexpr int SMEM = 0, TCOLS = 0, NBARS = 0, NWG = 0, L = 1; };
 
 template <class E0, class E1>
 struct MStage {
@@ -594,15 +771,15 @@ using MgStageB = MStage<MgConv4, MgNone>;
 using MgStageC = MStage<MgConv5, MgConv7>;
 using MgStageD = MStage<MgConv6, MgConv1>;
 constexpr int mg_max(int a, int b) { return a > b ? a : b; }
-constexpr int MG_BAR_BYTES = 1024;
+constexpr int MG_BAR_BYTES = 1152;       // 120 barriers, the TMEM slot, 2 x MG_NR row counters
 constexpr int MG_SMEM = mg_max(mg_max(MgStageA::SMEM, MgStageB::SMEM), mg_max(MgStageC::SMEM, MgStageD::SMEM)) + MG_BAR_BYTES;
 static_assert(MG_SMEM <= SMEM_LIMIT, "fused pass does not fit in shared memory");
 
 template <class E, bool HEAD>
 __device__ __forceinline__ void mg_run_service(const MegaK& M, const MCtx& c, const MEngSmem& s, uint32_t tmem_cols, const float* s_lut,
-                                               int role, int lane) {
+                                               uint4* s_raw, int role, int lane) {
   if (role == 0) {           // producer warp
-    if constexpr (HEAD) mg_producer_head<E>(M, c, s, s_lut, lane);
+    if constexpr (HEAD) mg_producer_head<E>(M, c, s, s_lut, s_raw, lane);
     else mg_producer<E>(M, c, s, lane);
   } else if (c.rank != 0) {  // peer CTA: relay
     mg_relay<E>(M, c, s, lane);
@@ -612,12 +789,18 @@ __device__ __forceinline__ void mg_run_service(const MegaK& M, const MCtx& c, co
 }
 
 template <class ST, class E0, class E1>
-__device__ __forceinline__ void mg_run_stage(const MegaK& M, MCtx& c, uint8_t* smem, float* s_lut, int warp, int lane) {
+__device__ __forceinline__ void mg_run_stage(const MegaK& M, MCtx& c, uint8_t* smem, float* s_lut, uint4* s_raw, int warp, int lane) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MG_SMEM - MG_BAR_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 120);
-  const MEngSmem s0 = mg_carve<E0>(smem, bars);
+  uint32_t* rowcnt = reinterpret_cast<uint32_t*>(bars + 128);
+  const MEngSmem s0 = mg_carve<E0>(smem, bars, rowcnt);
   MEngSmem s1 = s0;
-  if constexpr (ST::kTwo) s1 = mg_carve<E1>(smem + E0::SMEM, bars + E0::NBARS);
+  if constexpr (ST::kTwo) s1 = mg_carve<E1>(smem + E0::SMEM, bars + E0::NBARS, rowcnt + MG_NR);
+  if (threadIdx.x < 2 * MG_NR) rowcnt[threadIdx.x] = 0u;
+  for (int i = threadIdx.x; i < 9 * MG_MAXC; i += MG_THREADS) {     // MegaLayerP starts with bias[MG_MAXC], p0[4][MG_MAXC], p1[4][MG_MAXC]
+    const_cast<float*>(s0.prm)[i] = reinterpret_cast<const float*>(&M.L[E0::L - 1])[i];
+    if constexpr (ST::kTwo) const_cast<float*>(s1.prm)[i] = reinterpret_cast<const float*>(&M.L[E1::L - 1])[i];
+  }
   static_assert(E0::NBARS + E1::NBARS <= 120, "barrier block");
   if (threadIdx.x == 0) {
     mg_init_bars<E0>(s0);
@@ -641,9 +824,9 @@ __device__ __forceinline__ void mg_run_stage(const MegaK& M, MCtx& c, uint8_t* s
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 2) {
-    mg_run_service<E0, E0::L == 1>(M, c, s0, tmem_base, s_lut, warp, lane);
+    mg_run_service<E0, E0::L == 1>(M, c, s0, tmem_base, s_lut, s_raw, warp, lane);
   } else if (warp < 4) {
-    if constexpr (ST::kTwo) mg_run_service<E1, E1::L == 1>(M, c, s1, tmem_base + E0::TCOLS, s_lut, warp - 2, lane);
+    if constexpr (ST::kTwo) mg_run_service<E1, E1::L == 1>(M, c, s1, tmem_base + E0::TCOLS, s_lut, s_raw, warp - 2, lane);
   } else {
     const int wg = (warp - 4) >> 2;
     if (wg < E0::NWG) mg_epilogue<E0>(M, c, s0, tmem_base, s_lut, wg, warp, lane);
@@ -658,6 +841,7 @@ __device__ __forceinline__ void mg_run_stage(const MegaK& M, MCtx& c, uint8_t* s
 __global__ void __launch_bounds__(MG_THREADS, 1) fused_pass_kernel(const __grid_constant__ MegaK M) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ float s_lut[256];
+  __shared__ uint4 s_raw[3 * MROWS];             // head: raw framebuffer pixels of three strip rows (cp.async staging)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int pair = blockIdx.x >> 1, group = pair >> 2, stage = pair & 3;
@@ -666,13 +850,46 @@ __global__ void __launch_bounds__(MG_THREADS, 1) fused_pass_kernel(const __grid_
   c.strip = group - c.team * M.S;
   c.rank = (int)cluster_ctarank();
   c.f = 0;
+  c.probe = c.team == 0 && c.strip == (M.S > 1 ? 1 : 0) && c.rank == 0;
   if (c.team >= M.teams) return;                 // both CTAs of a pair leave together
   c.scratch = M.scratch + ((size_t)c.team * 2 + c.rank) * M.rank_stride;
   c.flags = M.flags + ((size_t)c.team * 2 + c.rank) * MG_FLAG_WORDS;
   switch (stage) {
-    case 0: mg_run_stage<MgStageA, MgConv2, MgConv3>(M, c, smem, s_lut, warp, lane); break;
-    case 1: mg_run_stage<MgStageB, MgConv4, MgNone>(M, c, smem, s_lut, warp, lane); break;
-    case 2: mg_run_stage<MgStageC, MgConv5, MgConv7>(M, c, smem, s_lut, warp, lane); break;
-    default: mg_run_stage<MgStageD, MgConv6, MgConv1>(M, c, smem, s_lut, warp, lane); break;
+    case 0: mg_run_stage<MgStageA, MgConv2, MgConv3>(M, c, smem, s_lut, s_raw, warp, lane); break;
+    case 1: mg_run_stage<MgStageB, MgConv4, MgNone>(M, c, smem, s_lut, s_raw, warp, lane); break;
+    case 2: mg_run_stage<MgStageC, MgConv5, MgConv7>(M, c, smem, s_lut, s_raw, warp, lane); break;
+    default: mg_run_stage<MgStageD, MgConv6, MgConv1>(M, c, smem, s_lut, s_raw, warp, lane); break;
   }
 }
+
+
+}  // namespace
+
+#if defined(FSUAE_EPI_TIMING) && !defined(FSUAE_OPERAND_FP16)
+extern "C" __attribute__((visibility("default"))) int fsuae_debug_mega_timing(unsigned long long* out, int reset) {   // [7][16] counters
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out, g_mega_t, sizeof(g_mega_t)) != cudaSuccess) return -1;
+  if (reset) { static unsigned long long z[8 * 16]; cudaMemcpyToSymbol(g_mega_t, z, sizeof(z)); }
+  return 0;
+}
+#endif
+
+int TC_FN(mega_prepare)() {
+  return (int)cudaFuncSetAttribute((const void*)fused_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM);
+}
+
+int TC_FN(mega_launch)(const MegaK& k, int grid, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = cudaLaunchConfig_t{};
+  cudaLaunchAttribute attr[1];
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(MG_THREADS);
+  cfg.dynamicSmemBytes = MG_SMEM;
+  cfg.stream = st;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelEx(&cfg, fused_pass_kernel, k);
+}
+
+}  // namespace fsuae
