@@ -1601,7 +1601,7 @@ struct TcPlan {
 
 // bytes of one (team, rank) channel block for rows of PW slots
 static size_t mega_block_bytes(int PW, unsigned long long* ch_off = nullptr) {
-  const int planes[MG_NCH] = {5, 5, 9, 9, 5, 5};
+  const int planes[MG_NCH] = {5, 5, 9, 9, 5, 5, 2};
   size_t off = 0;
   for (int c = 0; c < MG_NCH; ++c) {
     if (ch_off) ch_off[c] = off;

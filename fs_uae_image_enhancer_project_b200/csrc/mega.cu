@@ -11,10 +11,10 @@
 //     here each one is an ENGINE: a set of warps (producer, MMA issuer / peer relay, two or four epilogue warpgroups) with
 //     its own barriers, ring, weights and TMEM columns.  A CTA hosts one or two engines side by side; the hardware warp
 //     scheduler interleaves them, so an MMA-bound layer runs under an activation-bound one:
-//         stage A = conv2 (TeLU, SinLU, BiasedPReLU: SFU-bound)  + conv3 (no activation: tensor-bound)
-//         stage B = conv4 (Mish, BiasedPReLU, Tanh: both)
-//         stage C = conv5 (no activation)                        + conv7 (PixelShuffle tail: store / pow-bound)
-//         stage D = conv6 (Mish)                                 + conv1 (SinLU; its producer warp is also the network head)
+//         stage A = conv5 (no activation: tensor-bound)          + conv2 (TeLU, SinLU, BiasedPReLU: SFU-bound)
+//         stage B = conv4 (Mish, BiasedPReLU, Tanh: both)        + the network head on the two service warps a second engine would use
+//         stage C = conv3 (no activation)                        + conv7 (PixelShuffle tail: store / pow-bound)
+//         stage D = conv6 (Mish)                                 + conv1 (SinLU)
 //     MMA instructions per strip row: A 24+24, B 42, C 42+24, D 45+9 -- balanced to within 15 % at N = 48/80.
 //   * 4 stage pairs = 1 group = one 126-column strip of a frame pair; S groups (S strips) = 1 team = whole rows of a frame
 //     pair; the rows of all frame pairs are cut into equal contiguous ranges, one per team.  Where a range starts or ends
@@ -53,6 +53,9 @@ __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_re
 __device__ __forceinline__ void st_relaxed_gpu(unsigned int* p, uint32_t v) {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void red_relaxed_gpu_add(unsigned int* p, uint32_t v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void red_release_gpu_add(unsigned int* p, uint32_t v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -76,7 +79,7 @@ __device__ __forceinline__ unsigned int* mg_prod(unsigned int* fl, int ch) { ret
 #ifdef FSUAE_EPI_TIMING
 __device__ unsigned long long g_mega_t[8][16];     // row 7: the head producer in detail ([0] next row + loads  [1] slot wait  [2] LUT + stores  [3] fence + arrive  [4] rows)
 #define MG_T(var) const long long var = clock64()
-#define MG_ACC(cond, L, i, v) do { if (cond) g_mega_t[(L) - 1][i] += (unsigned long long)(v); } while (0)
+#define MG_ACC(cond, L, i, v) do { if (cond) atomicAdd(&g_mega_t[(L) - 1][i], (unsigned long long)(v)); } while (0)   // RED: fire and forget, a load-add-store would stall the probed warp for a memory round trip
 #else
 #define MG_T(var)
 #define MG_ACC(cond, L, i, v)
@@ -109,7 +112,7 @@ __device__ __forceinline__ int mg_lo(const MSeg& g, int halo) { return max(0, g.
 __device__ __forceinline__ int mg_hi(const MSeg& g, int halo, int Hw) { return min(Hw, g.y0 + g.rows + halo); }
 
 // ---- one engine = one layer ---------------------------------------------------------------------------------------------
-// LAYER 1..7.  Sources: conv1 <- the frame (head), conv{2,3,4,5} <- channel LAYER-2, conv6 <- channels 0 (conv1, long skip)
+// LAYER 1..7.  Sources: conv1 <- channel 6 (the head's output), conv{2,3,4,5} <- channel LAYER-2, conv6 <- channels 0 (conv1, long skip)
 // and 4 (conv5), conv7 <- channel 5.  Consumer index inside a channel: conv6 is consumer 1 of channel 0, everything else 0.
 // Per-channel epilogue parameters live in shared memory as [9][MG_MAXC] floats (bias, p0[4 slots], p1[4 slots]): the epilogue
 // walks the 8-channel chunks in a ROLLED loop.  Unrolled over 36-72 compile-time channels the code of one stage is ~70 KB of
@@ -127,7 +130,7 @@ struct MEng {
   static constexpr int SMEM = PRM_OFF + MG_PRM_BYTES;               // + this layer's per-channel epilogue parameters
   static constexpr int TCOLS = STAGES * NPAD;
   static constexpr int NBARS = 3 * RING + 2 * STAGES + 1;           // full, empty, pfull; tfull, tempty; wbar
-  static constexpr int IN0 = LAYER == 1 ? -1 : (LAYER == 6 ? 0 : LAYER - 2);
+  static constexpr int IN0 = LAYER == 1 ? 6 : (LAYER == 6 ? 0 : LAYER - 2);
   static constexpr int IN1 = LAYER == 6 ? 4 : -1;
   static constexpr int P0 = LAYER == 6 ? 5 : PT, P1 = LAYER == 6 ? 5 : 0;
   static constexpr int HALO0 = LAYER == 6 ? 6 : HALO + 1;           // halo of the layer that produced source 0 / 1
@@ -136,7 +139,7 @@ struct MEng {
   static constexpr int OUT = LAYER <= 6 ? LAYER - 1 : -1;
   static constexpr int OUT_PLANES = (COUT + 7) / 8;
   static constexpr int OUT_NCONS = LAYER == 1 ? 2 : 1;              // conv1's output is read by conv2 and conv6
-  static_assert(STAGES >= NWG && STAGES <= 2 * NWG + 2, "accumulator stages vs epilogue warpgroups");
+  static_assert(STAGES >= NWG, "a warpgroup's previous block must be at least one use of the stage back (mbarrier parity waits)");
   static_assert(RING >= 4 && RING <= 16, "ring depth (one relay lane per slot)");
   static_assert(NB % 8 == 0, "each CTA of the pair holds whole core matrices of B");
 };
@@ -184,6 +187,12 @@ struct MCtx {          // where this CTA sits
 // complete (`upto`, exclusive) so that one coalesced poll releases several rows.
 // A successful poll costs two fences (~1500 cycles) on the one warp that feeds the engine, so it asks for MG_POLL_BATCH rows
 // at a time (fewer at the end of the channel: `qtotal` rows in all).
+#ifndef MG_POLL_ACQ
+#define MG_POLL_ACQ 1
+#endif
+#ifndef MG_POLL_PROXY
+#define MG_POLL_PROXY 1
+#endif
 #ifndef MG_POLL_BATCH
 #define MG_POLL_BATCH 3
 #endif
@@ -208,15 +217,18 @@ __device__ __forceinline__ void mg_wait_rows(const MegaK& M, const MCtx& c, int 
   }
   // Once per successful poll (it usually reveals several rows): order the bulk copies (async proxy) behind the counters
   // just read (generic proxy).  The proxy fence costs ~1000 cycles, so it must not sit between "ring slot free" and the copy.
+#if MG_POLL_ACQ
   fence_acq_rel_gpu();
+#endif
+#if MG_POLL_PROXY
   if (lane == 0) fence_proxy_async_all();
+#endif
   __syncwarp();
 }
 
 // ---- producer warp: channel rows -> shared-memory ring (TMA) -----------------------------------------------------------
 template <class E>
 __device__ void mg_producer(const MegaK& M, const MCtx& c, const MEngSmem& s, int lane) {
-  static_assert(E::L != 1, "conv1 has its own producer (the head)");
   const MegaLayerP& LP = M.L[E::L - 1];
   if (lane == 0) {
     mbar_arrive_expect_tx(s.wbar, E::WBYTES);
@@ -270,6 +282,8 @@ __device__ void mg_producer(const MegaK& M, const MCtx& c, const MEngSmem& s, in
         if (inframe) { land0[0] = q0 + 1u; land1[0] = q1 + 1u; }
       }
       __syncwarp();
+      MG_T(tp0b);
+      MG_ACC(tprobe, 8, 4 + E::L, tp0b - tp0);      // row 7, [5 .. 11]: the credit step (waits for the copy of fill - 2)
       if (inframe) {       // usually known from an earlier poll: the upstream layer runs ahead while my ring is full
         mg_wait_rows(M, c, E::IN0, q0, tot0, upto0, lane);
         if constexpr (E::IN1 >= 0) mg_wait_rows(M, c, E::IN1 >= 0 ? E::IN1 : 0, q1, tot1, upto1, lane);
@@ -277,7 +291,7 @@ __device__ void mg_producer(const MegaK& M, const MCtx& c, const MEngSmem& s, in
       MG_T(tp1);
       if (lane == 0) mbar_wait(&s.empty[slot], par);
       MG_T(tp2);
-      MG_ACC(tprobe, E::L, 5, tp1 - tp0); MG_ACC(tprobe, E::L, 4, tp2 - tp1); MG_ACC(tprobe, E::L, 12, 1);
+      MG_ACC(tprobe, E::L, 5, tp1 - tp0b); MG_ACC(tprobe, E::L, 4, tp2 - tp1); MG_ACC(tprobe, E::L, 12, 1);
       if (lane == 0) {
         uint8_t* d = s.ring + slot * E::ROWBYTES;
         mbar_arrive_expect_tx(&s.full[slot], E::ROWBYTES);
@@ -304,94 +318,91 @@ __device__ void mg_producer(const MegaK& M, const MCtx& c, const MEngSmem& s, in
   MG_ACC(tprobe, E::L, 6, tp_end - tp_begin);
 }
 
-// ---- producer warp of conv1 = the network head: frame -> gamma LUT -> PixelUnshuffle(2) -> ring rows, no TMA -------------
-// 128 slots per strip row, 4 per lane; a slot is one half-resolution pixel = 2x2 full-resolution pixels x RGB = 12 channels
-// = plane 0 (8 channels) + plane 1 (4 channels, 4 zeros).  Out-of-frame slots are zero (the conv's zero padding).
-// One warp feeds a whole stage, so a row must not cost a trip to HBM: for the framebuffer format (uint8 RGBA) the raw pixels
-// of the NEXT row are already in registers (16 per lane) while the current one goes through the LUT.
-template <class E>
-__device__ void mg_producer_head(const MegaK& M, const MCtx& c, const MEngSmem& s, const float* s_lut, uint4* s_raw, int lane) {
-  static_assert(E::L == 1 && E::PT == 2, "head feeds conv1");
-  const MegaLayerP& LP = M.L[0];
-  if (lane == 0) {
-    mbar_arrive_expect_tx(s.wbar, E::WBYTES);
-    tma_load_1d(s.w, LP.wpack + (size_t)c.rank * E::WBYTES, E::WBYTES, s.wbar);
-  }
-  const size_t fpl = (size_t)M.H * M.W;
+// ---- the network head: frame -> gamma LUT -> PixelUnshuffle(2) -> channel 6 ------------------------------------------------
+// Two warps (the service warps stage B has no second engine for), each converts one half of every strip row: a slot is one
+// half-resolution pixel = 2x2 full-resolution pixels x RGB = 12 channels = plane 0 (8 channels) + plane 1 (4 channels, 4 zeros).
+// One warp cannot keep a stage fed: ~500 dependent instructions per row are ~3000 cycles however they are arranged.
+// Framebuffer format (uint8 RGBA, the streaming case): the raw pixels travel global -> shared memory by cp.async two rows
+// ahead (no registers in between), issued behind the row's stores; out-of-frame columns are zero filled -> LUT[0] = 0.
+__device__ void mg_head_worker(const MegaK& M, const MCtx& c, const float* s_lut, uint4* s_raw, int w, int lane) {
+  constexpr int CH = 6, HALO = 7;
+  constexpr uint32_t D = (uint32_t)mg_depth(CH);
+  const size_t row_pitch = (size_t)M.PW * 16, plane_pitch = (size_t)D * row_pitch, fpl = (size_t)M.H * M.W;
+  unsigned char* och = c.scratch + M.ch_off[CH];
+  unsigned int* prod = mg_prod(c.flags, CH);
   const bool fb = M.in_fmt == FSUAE_FMT_U8_NHWC4;
-  uint32_t fill = 0;
-  const bool tprobe = c.probe && lane == 0;
-  MG_T(tp_begin);
-  // the CTA's row sequence: every segment's input rows lo-1 .. hi
+  const bool tprobe = c.probe && w == 0 && lane == 0;
+  // my two slots of a strip row: m = 63 w + lane, 63 w + 32 + lane (the second one only for lane < 31)
+  int mm[2], xx[2];
+  bool okx[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    mm[k] = 63 * w + 32 * k + lane;
+    xx[k] = c.strip * STRIP + mm[k];
+    okx[k] = (k == 0 || lane < 31) && xx[k] < M.Ww;
+  }
+  uint4* stage = s_raw + 64 * w;                 // my half of the three staging rows
+  // the CTA's row sequence: every segment's rows lo .. hi-1 (in-frame rows only; conv1's producer supplies the zero rows)
   MSegIter it(M, c.team);
   MSeg g;
-  int ycur = 0, yend = -1;
+  int ycur = 0, yend = 0;
   auto next_row = [&](int& rf, int& ry) -> bool {
-    if (ycur > yend) {
+    if (ycur >= yend) {
       if (!it.next(g)) return false;
-      ycur = mg_lo(g, E::HALO) - 1;
-      yend = mg_hi(g, E::HALO, M.Hw);
+      ycur = mg_lo(g, HALO);
+      yend = mg_hi(g, HALO, M.Hw);
     }
     rf = min(2 * g.fp + c.rank, M.n_frames - 1);
     ry = ycur++;
     return true;
   };
-  auto store_slot = [&](uint8_t* d, int m, const float (&v)[12]) {
-    *reinterpret_cast<uint4*>(d + m * 16) = make_uint4(pack_op2(v[0], v[1]), pack_op2(v[2], v[3]), pack_op2(v[4], v[5]), pack_op2(v[6], v[7]));
-    *reinterpret_cast<uint4*>(d + PLANE_ROW + m * 16) = make_uint4(pack_op2(v[8], v[9]), pack_op2(v[10], v[11]), 0u, 0u);
-  };
-  auto begin_row = [&]() -> uint8_t* {       // wait for the ring slot of this fill
-    const uint32_t slot = fill % E::RING, par = ((fill / E::RING) & 1u) ^ 1u;
-    MG_T(tp0);
-    if (lane == 0) mbar_wait(&s.empty[slot], par);
-    __syncwarp();
-    MG_T(tp1);
-    MG_ACC(tprobe, E::L, 4, tp1 - tp0); MG_ACC(tprobe, E::L, 12, 1);
-    MG_ACC(tprobe, 8, 1, tp1 - tp0); MG_ACC(tprobe, 8, 4, 1);
-    return s.ring + slot * E::ROWBYTES;
-  };
-  auto end_row = [&]() {
-    fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's reads
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&s.full[fill % E::RING]);
-    ++fill;
-  };
-  if (fb) {
-    // Framebuffer format (uint8 RGBA, the streaming case).  The raw pixels of the NEXT row travel global -> shared memory by
-    // cp.async (no registers in between: a register FIFO stalls on its own moves, and unrolled over the lane's four slots the
-    // body was 14 KB of code this single warp fetched anew for every row), the current row goes through the LUT in a rolled
-    // loop of ~100 instructions.  Slot = {dy 0: px 0, px 1; dy 1: px 0, px 1} = 16 bytes; out of frame -> zero fill -> LUT[0] = 0.
-    auto prefetch = [&](int rf, int ry, uint4* buf) {
-#pragma unroll 1
-      for (int i = 0; i < 4; ++i) {
-        const int m = lane + 32 * i, x = c.strip * STRIP - 1 + m;
-        const bool ok = ry >= 0 && ry < M.Hw && x >= 0 && x < M.Ww;
-        const unsigned char* ip = (const unsigned char*)M.frame_in + (ok ? ((size_t)rf * fpl + (size_t)(2 * ry) * M.W + 2 * x + M.xoff) * 4 : 0);
-        const uint32_t dst = smem_u32(buf + m), n = ok ? 8u : 0u;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(ip), "r"(n) : "memory");
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + 8u), "l"(ip + (size_t)M.W * 4), "r"(n) : "memory");
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    // Three staging rows: the copy of row r + 2 is issued BEHIND row r's proxy fence (the fence waits for every memory
-    // operation of the warp that is still in flight, cp.async included), so it has a whole row period to land.
-    int fC, yC, fN = 0, yN = 0, fP = 0, yP = 0;
-    bool haveC = next_row(fC, yC), haveN = false;
-    uint32_t rowno = 0;
-    if (haveC) {
-      prefetch(fC, yC, s_raw);
-      haveN = next_row(fN, yN);
-      if (haveN) prefetch(fN, yN, s_raw + MROWS);
+  auto prefetch = [&](int rf, int ry, uint4* buf) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const unsigned char* ip = (const unsigned char*)M.frame_in + (okx[k] ? ((size_t)rf * fpl + (size_t)(2 * ry) * M.W + 2 * xx[k] + M.xoff) * 4 : 0);
+      const uint32_t dst = smem_u32(buf + 32 * k + lane), nb = okx[k] ? 8u : 0u;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(ip), "r"(nb) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + 8u), "l"(ip + (size_t)M.W * 4), "r"(nb) : "memory");
     }
-    while (haveC) {
-      const bool haveP = haveN && next_row(fP, yP);
-      uint8_t* d = begin_row();
-      MG_T(tw0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int fC, yC, fN = 0, yN = 0, fP = 0, yP = 0;
+  bool haveC = next_row(fC, yC), haveN = false;
+  uint32_t q = 0, cons_seen = 0;
+  if (haveC && fb) {
+    prefetch(fC, yC, stage);
+    haveN = next_row(fN, yN);
+    if (haveN) prefetch(fN, yN, stage + MROWS);
+  } else if (haveC) {
+    haveN = next_row(fN, yN);
+  }
+  while (haveC) {
+    const bool haveP = haveN && next_row(fP, yP);
+    MG_T(th0);
+    // back-pressure: slot q % D still holds row q - D until conv1's producers of strips s-1, s, s+1 have loaded it
+    if (q >= D && cons_seen < q - D + 1u) {
+      const uint32_t need = q - D + 1u;
+      const long long t0 = clock64();
+      for (;;) {
+        uint32_t v = 0xFFFFFFFFu;
+        if (lane < 3) {
+          const int sn = c.strip - 1 + lane;
+          if (sn >= 0 && sn < M.S) v = ld_relaxed_gpu(mg_cons(c.flags, CH, 0) + sn);
+        }
+        v = __reduce_min_sync(0xffffffffu, v);
+        if (v >= need) { cons_seen = v; fence_acq_rel_gpu(); break; }
+        if (clock64() - t0 > (1ll << 31)) __trap();
+        __nanosleep(64);
+      }
+    }
+    MG_T(th1);
+    unsigned char* dp = och + (size_t)(q % D) * row_pitch;
+    if (fb) {
       if (haveN) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
-      const uint4* src = s_raw + (rowno % 3u) * MROWS;
-#pragma unroll 1
-      for (int i = 0; i < 4; ++i) {
-        const uint4 cur = src[lane + 32 * i];          // written by this very lane
+      const uint4* src = stage + (q % 3u) * MROWS;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const uint4 cur = src[32 * k + lane];          // written by this very lane: {dy 0: px 0, px 1; dy 1: px 0, px 1}
         float v[12];
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
@@ -400,54 +411,52 @@ __device__ void mg_producer_head(const MegaK& M, const MCtx& c, const MEngSmem& 
           v[ch * 4 + 2] = s_lut[(cur.z >> (8 * ch)) & 0xFF];
           v[ch * 4 + 3] = s_lut[(cur.w >> (8 * ch)) & 0xFF];
         }
-        store_slot(d, lane + 32 * i, v);
+        if (okx[k]) {
+          unsigned char* d = dp + (size_t)(xx[k] + BORDER) * 16;
+          *reinterpret_cast<uint4*>(d) = make_uint4(pack_op2(v[0], v[1]), pack_op2(v[2], v[3]), pack_op2(v[4], v[5]), pack_op2(v[6], v[7]));
+          *reinterpret_cast<uint4*>(d + plane_pitch) = make_uint4(pack_op2(v[8], v[9]), pack_op2(v[10], v[11]), 0u, 0u);
+        }
       }
-      MG_T(tw1);
-      end_row();
-      MG_T(tw2);
-      MG_ACC(tprobe, 8, 2, tw1 - tw0); MG_ACC(tprobe, 8, 3, tw2 - tw1);
-      if (haveP) prefetch(fP, yP, s_raw + ((rowno + 2u) % 3u) * MROWS);
-      fC = fN; yC = yN; haveC = haveN;
-      fN = fP; yN = yP; haveN = haveP;
-      ++rowno;
-    }
-  } else {
-    // float / planar uint8 frames (not the streaming format): slot by slot, rolled -- this path only has to be correct
-    int rf, ry;
-    while (next_row(rf, ry)) {
-      uint8_t* d = begin_row();
+    } else {
+      // float / planar uint8 frames (not the streaming format): this path only has to be correct
 #pragma unroll 1
-      for (int i = 0; i < 4; ++i) {
-        const int x = c.strip * STRIP - 1 + lane + 32 * i;
-        const bool ok = ry >= 0 && ry < M.Hw && x >= 0 && x < M.Ww;
+      for (int k = 0; k < 2; ++k) {
+        if (!okx[k]) continue;
         float v[12];
 #pragma unroll
-        for (int k = 0; k < 12; ++k) v[k] = 0.f;
-        if (ok) {
+        for (int dy = 0; dy < 2; ++dy) {
+          const size_t p0 = (size_t)(2 * yC + dy) * M.W + 2 * xx[k] + M.xoff;
+          if (M.in_fmt == FSUAE_FMT_F32_NCHW3) {
+            const float* ip = (const float*)M.frame_in + (size_t)fC * 3 * fpl + p0;
 #pragma unroll
-          for (int dy = 0; dy < 2; ++dy) {
-            const size_t p0 = (size_t)(2 * ry + dy) * M.W + 2 * x + M.xoff;
-            if (M.in_fmt == FSUAE_FMT_F32_NCHW3) {
-              const float* ip = (const float*)M.frame_in + (size_t)rf * 3 * fpl + p0;
-#pragma unroll
-              for (int ch = 0; ch < 3; ++ch) {
-                const float2 t2 = __ldg(reinterpret_cast<const float2*>(ip + ch * fpl));
-                v[ch * 4 + dy * 2] = t2.x; v[ch * 4 + dy * 2 + 1] = t2.y;
-              }
-            } else {
-              const unsigned char* ip = (const unsigned char*)M.frame_in + (size_t)rf * 4 * fpl + p0;
-#pragma unroll
-              for (int ch = 0; ch < 3; ++ch) { v[ch * 4 + dy * 2] = s_lut[__ldg(ip + ch * fpl)]; v[ch * 4 + dy * 2 + 1] = s_lut[__ldg(ip + ch * fpl + 1)]; }
+            for (int ch = 0; ch < 3; ++ch) {
+              const float2 t2 = __ldg(reinterpret_cast<const float2*>(ip + ch * fpl));
+              v[ch * 4 + dy * 2] = t2.x; v[ch * 4 + dy * 2 + 1] = t2.y;
             }
+          } else {
+            const unsigned char* ip = (const unsigned char*)M.frame_in + (size_t)fC * 4 * fpl + p0;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) { v[ch * 4 + dy * 2] = s_lut[__ldg(ip + ch * fpl)]; v[ch * 4 + dy * 2 + 1] = s_lut[__ldg(ip + ch * fpl + 1)]; }
           }
         }
-        store_slot(d, lane + 32 * i, v);
+        unsigned char* d = dp + (size_t)(xx[k] + BORDER) * 16;
+        *reinterpret_cast<uint4*>(d) = make_uint4(pack_op2(v[0], v[1]), pack_op2(v[2], v[3]), pack_op2(v[4], v[5]), pack_op2(v[6], v[7]));
+        *reinterpret_cast<uint4*>(d + plane_pitch) = make_uint4(pack_op2(v[8], v[9]), pack_op2(v[10], v[11]), 0u, 0u);
       }
-      end_row();
     }
+    MG_T(th2);
+    // both halves stored -> the row counter; the two warps take the release (~1000 cycles) in turn.  Its gpu scope is
+    // cumulative over the CTA-scope barrier, so it covers the other warp's stores as well.
+    asm volatile("bar.sync 1, 64;" ::: "memory");
+    if ((q & 1u) == (uint32_t)w && lane == 0) red_release_gpu_add(prod + q % D, 1u);
+    MG_T(th3);
+    if (haveP && fb) prefetch(fP, yP, stage + ((q + 2u) % 3u) * MROWS);
+    MG_T(th4);
+    MG_ACC(tprobe, 8, 0, th4 - th3); MG_ACC(tprobe, 8, 1, th1 - th0); MG_ACC(tprobe, 8, 2, th2 - th1); MG_ACC(tprobe, 8, 3, th3 - th2); MG_ACC(tprobe, 8, 4, 1);
+    fC = fN; yC = yN; haveC = haveN;
+    fN = fP; yN = yP; haveN = haveP;
+    ++q;
   }
-  MG_T(tp_end);
-  MG_ACC(tprobe, E::L, 6, tp_end - tp_begin);
 }
 
 // ---- peer CTA of the pair: relay "my ring row has landed" to the leader (one lane per ring slot) -------------------------
@@ -476,7 +485,98 @@ __device__ void mg_relay(const MegaK& M, const MCtx& c, const MEngSmem& s, int l
   }
 }
 
-// ---- MMA issuer (leader CTA): block-major, one accumulator per strip row -------------------------------------------------
+// ---- MMA issuer (leader CTA), input-row-major order with A-collector reuse ---------------------------------------------------
+// Input row k of a segment feeds output rows k-2 (kernel row 2), k-1 (row 1) and k (row 0).  The three MMAs of a step share
+// their A tile (collector fill / use / lastuse): it is read from shared memory once instead of three times, and the A read
+// is what bounds narrow-N UMMA (tools/umma_probe.cu: 19 / 33 / 49 cycles per instruction in such triples at N = 16 / 48 / 80
+// against 38 / 46 / 59).  Every output row keeps its own accumulator stage (block n in stage n % STAGES), three are open at a
+// time, so the order needs STAGES >= 5.  One input row = STEPS_ROW steps; the unit / LBO pattern is that of issue_block_2cta.
+template <class E>
+__device__ void mg_issuer_rm(const MegaK& M, const MCtx& c, const MEngSmem& s, uint32_t tmem_cols) {
+  constexpr uint32_t IDESC = umma_idesc_op(2 * MROWS, E::NPAD);
+  constexpr uint32_t HI = (uint32_t)((128u >> 4)) | (1u << 14);
+  constexpr uint32_t BSTEP = (E::NB * 32) >> 4, BROW = E::STEPS_ROW * BSTEP, PR16 = PLANE_ROW / 16;
+  constexpr uint32_t L16 = 1u << 16, L2K = (uint32_t)(PR16 - 2) << 16;
+  constexpr int G3 = E::STEPS_ROW / 3, REM = E::STEPS_ROW % 3;
+  static_assert(REM == 0 || REM == 2, "unexpected instruction count per row");
+  const uint32_t ring_lo = (smem_u32(s.ring) & 0x3FFFFu) >> 4;
+  const uint32_t w_lo = ((smem_u32(s.w) & 0x3FFFFu) >> 4) | ((uint32_t)((E::NB * 16) >> 4) << 16);
+  const uint64_t hi = (uint64_t)HI << 32;
+  mbar_wait(s.wbar, 0);
+  uint32_t blk0 = 0, grow = 0;       // blocks / input rows of the CTA before this segment
+  MG_T(ti_begin);
+  MSegIter it(M, c.team);
+  MSeg g;
+  while (it.next(g)) {
+    const int rows = mg_hi(g, E::HALO, M.Hw) - mg_lo(g, E::HALO);
+    for (int k = 0; k < rows + 2; ++k) {
+      const uint32_t r = grow + (uint32_t)k, rs = r % E::RING, rpar = (r / E::RING) & 1u;
+      MG_T(ti0);
+      mbar_wait(&s.full[rs], rpar);
+      mbar_wait(&s.pfull[rs], rpar);
+      MG_T(ti1);
+      const uint32_t n = blk0 + (uint32_t)k;           // block (output row) this input row opens
+      const uint32_t sk = n % E::STAGES, pk = ((n / E::STAGES) & 1u) ^ 1u;
+      const bool v0 = k <= rows - 1, v1 = k >= 1 && k <= rows, v2 = k >= 2;
+      if (v0) mbar_wait(&s.tempty[sk], pk);
+      tc_fence_after();
+      MG_T(ti2);
+      const uint32_t s1 = sk >= 1u ? sk - 1u : sk + E::STAGES - 1u, s2 = sk >= 2u ? sk - 2u : sk + E::STAGES - 2u;
+      const uint32_t d0 = tmem_cols + sk * E::NPAD, d1 = tmem_cols + s1 * E::NPAD, d2 = tmem_cols + s2 * E::NPAD;
+      uint32_t a_lo = ring_lo + rs * (E::ROWBYTES >> 4), b_lo = w_lo, acc0 = 0;
+      if (v0 && v1 && v2) {
+        auto step3 = [&](uint32_t a, uint32_t b) {
+          umma_bf16_coll<2, 1>(d2, hi | a, hi | (b + 2u * BROW), IDESC, 1u);
+          umma_bf16_coll<2, 2>(d1, hi | a, hi | (b + BROW), IDESC, 1u);
+          umma_bf16_coll<2, 3>(d0, hi | a, hi | b, IDESC, acc0);
+          acc0 = 1u;
+        };
+#pragma unroll 1
+        for (int g3 = 0; g3 < G3; ++g3) {
+          step3(a_lo | L16, b_lo);
+          step3((a_lo + 2) | L2K, b_lo + BSTEP);
+          step3((a_lo + PR16 + 1) | L16, b_lo + 2 * BSTEP);
+          a_lo += 2 * PR16;
+          b_lo += 3 * BSTEP;
+        }
+        if constexpr (REM == 2) {
+          step3(a_lo | L16, b_lo);
+          step3((a_lo + 1) | L16, b_lo + BSTEP);
+        }
+      } else {
+        // the first and last two input rows of a segment feed fewer than three output rows
+        auto step = [&](uint32_t a, uint32_t b) {
+          if (v2) umma_bf16_2cta(d2, hi | a, hi | (b + 2u * BROW), IDESC, 1u);
+          if (v1) umma_bf16_2cta(d1, hi | a, hi | (b + BROW), IDESC, 1u);
+          if (v0) umma_bf16_2cta(d0, hi | a, hi | b, IDESC, acc0);
+          acc0 = 1u;
+        };
+#pragma unroll 1
+        for (int g3 = 0; g3 < G3; ++g3) {
+          step(a_lo | L16, b_lo);
+          step((a_lo + 2) | L2K, b_lo + BSTEP);
+          step((a_lo + PR16 + 1) | L16, b_lo + 2 * BSTEP);
+          a_lo += 2 * PR16;
+          b_lo += 3 * BSTEP;
+        }
+        if constexpr (REM == 2) {
+          step(a_lo | L16, b_lo);
+          step((a_lo + 1) | L16, b_lo + BSTEP);
+        }
+      }
+      umma_commit_2cta(&s.empty[rs]);                  // the MMAs are done with this input row (the pipe completes in issue order)
+      if (v2) umma_commit_2cta(&s.tfull[s2]);          // output row k-2 is complete
+      MG_T(ti3);
+      MG_ACC(c.probe, E::L, 1, ti1 - ti0); MG_ACC(c.probe, E::L, 2, ti2 - ti1); MG_ACC(c.probe, E::L, 3, ti3 - ti2); MG_ACC(c.probe && v2, E::L, 13, 1);
+    }
+    blk0 += (uint32_t)rows;
+    grow += (uint32_t)rows + 2u;
+  }
+  MG_T(ti_end);
+  MG_ACC(c.probe, E::L, 0, ti_end - ti_begin);
+}
+
+// ---- MMA issuer (leader CTA): block-major, one accumulator per strip row (engines with fewer than 5 accumulator stages) ------
 template <class E>
 __device__ void mg_issuer(const MegaK& M, const MCtx& c, const MEngSmem& s, uint32_t tmem_cols) {
   constexpr uint32_t IDESC = umma_idesc_op(2 * MROWS, E::NPAD);
@@ -489,7 +589,7 @@ __device__ void mg_issuer(const MegaK& M, const MCtx& c, const MEngSmem& s, uint
     MG_T(tw_a);
     mbar_wait(&s.pfull[wslot], wpar);
     MG_T(tw_b);
-    MG_ACC(c.probe, 8, 7 + E::L, tw_b - tw_a);        // row 7, [8 .. 14]: the part of the input-row waits spent on the peer's relay
+    MG_ACC(c.probe && E::L == 4, 8, 12, tw_b - tw_a);   // row 7, [12]: conv4's input-row waits spent on the peer's relay
     if (++wslot == E::RING) { wslot = 0; wpar ^= 1u; }
   };
   MG_T(ti_begin);
@@ -562,6 +662,12 @@ __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, ui
   unsigned char* och = E::OUT >= 0 ? c.scratch + M.ch_off[E::OUT >= 0 ? E::OUT : 0] : nullptr;
   unsigned int* prod = mg_prod(c.flags, E::OUT >= 0 ? E::OUT : 0);
   uint32_t blk = 0, qrow = 0, qout = 0;          // blocks / ring rows / output rows before this segment
+  uint32_t qtotal = 0;                           // output rows of this engine in all
+  if constexpr (E::NWG == 1) {
+    MSegIter itq(M, c.team);
+    MSeg gq;
+    while (itq.next(gq)) qtotal += (uint32_t)(mg_hi(gq, E::HALO, M.Hw) - mg_lo(gq, E::HALO));
+  }
   uint32_t cons_seen = 0;                        // every row below this has been read by all my consumers
   const bool tprobe = c.probe && wg == 0 && q4 == 0 && lane == 0;
   MG_T(te_begin);
@@ -634,23 +740,31 @@ __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, ui
 
       if constexpr (E::KIND == EPI_STORE) {
         unsigned char* dp = och + (size_t)(q % (uint32_t)D) * row_pitch + (size_t)(x + BORDER) * 16;
+        // the accumulator chunk of the NEXT iteration is already on its way while this one goes through the activations
+        // (a tcgen05.ld takes several hundred cycles while the MMAs keep the tensor memory busy)
+        uint32_t vn[8];
+        tmem_ld_x8(taddr, vn);
 #pragma unroll 1
         for (int cc = 0; cc < E::OUT_PLANES; ++cc) {
+          tmem_ld_wait();
           uint32_t v[8];
-          tmem_ld_x8(taddr + cc * 8, v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = vn[i];
+          if (cc + 1 < E::OUT_PLANES) tmem_ld_x8(taddr + (cc + 1) * 8, vn);
           const float* prm = s.prm + cc * 8;
           const float4 b0 = *reinterpret_cast<const float4*>(prm), b1 = *reinterpret_cast<const float4*>(prm + 4);
           uint4 skc = make_uint4(0, 0, 0, 0);
           if constexpr (EPI::kSkip) {
             if (valid) skc = *reinterpret_cast<const uint4*>(sp + cc * PLANE_ROW);
           }
-          tmem_ld_wait();
           float o[8];
           o[0] = __uint_as_float(v[0]) + b0.x; o[1] = __uint_as_float(v[1]) + b0.y; o[2] = __uint_as_float(v[2]) + b0.z;
           o[3] = __uint_as_float(v[3]) + b0.w; o[4] = __uint_as_float(v[4]) + b1.x; o[5] = __uint_as_float(v[5]) + b1.y;
           o[6] = __uint_as_float(v[6]) + b1.z; o[7] = __uint_as_float(v[7]) + b1.w;
+#ifndef MG_DBG_NOACT      // timing experiment (garbage results): what the pass costs without any activation math
           mg_slot8<EPI::kOp0>(0, prm, o);
           mg_slot8<EPI::kOp1>(1, prm, o);
+#endif
           if constexpr (EPI::kSkip) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -658,8 +772,10 @@ __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, ui
               o[i] += (i & 1) ? op_hi(w) : op_lo(w);
             }
           }
+#ifndef MG_DBG_NOACT
           mg_slot8<EPI::kOp2>(2, prm, o);
           mg_slot8<EPI::kOp3>(3, prm, o);
+#endif
           if constexpr (E::COUT % 8 != 0) {
             if (cc == E::OUT_PLANES - 1) {       // padding channels stay exactly zero
 #pragma unroll
@@ -678,7 +794,18 @@ __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, ui
         if (lane == 0) {
           const uint32_t before = atom_acq_rel_cta_smem_add(s.rowcnt + q % (uint32_t)MG_NR, 1u);
           MG_T(tf1);
-          if ((before & 3u) == 3u) red_release_gpu_add(prod + q % (uint32_t)D, 1u);
+          if ((before & 3u) == 3u) {
+            if constexpr (E::NWG == 1) {
+              // a single warpgroup takes the rows in order and pays for every release itself: two rows per fence
+              if ((q & 1u) == 1u || q + 1u == qtotal) {
+                fence_acq_rel_gpu();
+                if ((q & 1u) == 1u) red_relaxed_gpu_add(prod + (q - 1u) % (uint32_t)D, 1u);
+                red_relaxed_gpu_add(prod + q % (uint32_t)D, 1u);
+              }
+            } else {
+              red_release_gpu_add(prod + q % (uint32_t)D, 1u);
+            }
+          }
           MG_T(tf2);
           MG_ACC(tprobe, E::L, 14, tf1 - tf0); MG_ACC(tprobe, E::L, 15, tf2 - tf1);
           if constexpr (EPI::kSkip) {            // residual values consumed: release the ring rows
@@ -748,11 +875,18 @@ __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, ui
 
 // ---- the engines of the flagship preset (model_pix_shuffle.py:306-311) ---------------------------------------------------
 #define MG_A(x) FSUAE_ACT_##x
+// <layer, input planes, N, Cout, kind, epilogue, ring rows, accumulator stages (>= 5: row-major MMA order), epilogue warpgroups>
+// Who shares an SM is decided by three budgets -- tensor time (MMA instructions per row x their cost), issue slots /
+// SFU time of the activation chains, and TMEM columns (stages x N <= 512 per SM):
+//   conv5 (42 MMAs, no activation: ONE warpgroup)     + conv2 (24 MMAs, the longest chain: THREE warpgroups)
+//   conv4 (42 MMAs at N = 80, long chain: all four)   + the head
+//   conv3 (24 MMAs at N = 80, no activation)          + conv7 (24 MMAs at N = 16, PixelShuffle tail)
+//   conv6 (45 MMAs, Mish)                             + conv1 (9 MMAs, SinLU)
 using MgConv1 = MEng<1, 2, 48, 36, EPI_STORE, Epi<MG_A(SINLU), MG_A(RELU6), 0, 0, false>, 8, 4, 2>;
-using MgConv2 = MEng<2, 5, 48, 36, EPI_STORE, Epi<MG_A(TELU), 0, MG_A(SINLU), MG_A(BIASED_PRELU), true>, 8, 4, 2>;
-using MgConv3 = MEng<3, 5, 80, 72, EPI_STORE, Epi<0, 0, 0, 0, false>, 8, 4, 2>;
+using MgConv2 = MEng<2, 5, 48, 36, EPI_STORE, Epi<MG_A(TELU), 0, MG_A(SINLU), MG_A(BIASED_PRELU), true>, 6, 5, 3>;
+using MgConv3 = MEng<3, 5, 80, 72, EPI_STORE, Epi<0, 0, 0, 0, false>, 8, 5, 2>;
 using MgConv4 = MEng<4, 9, 80, 72, EPI_STORE, Epi<MG_A(MISH), MG_A(BIASED_PRELU), MG_A(TANH), MG_A(RELU), true>, 9, 6, 4>;
-using MgConv5 = MEng<5, 9, 48, 36, EPI_STORE, Epi<0, 0, 0, 0, false>, 6, 6, 2>;
+using MgConv5 = MEng<5, 9, 48, 36, EPI_STORE, Epi<0, 0, 0, 0, false>, 5, 5, 1>;
 using MgConv6 = MEng<6, 10, 48, 36, EPI_STORE, Epi<MG_A(MISH), MG_A(RELU6), 0, 0, false>, 6, 6, 2>;
 using MgConv7 = MEng<7, 5, 16, 12, EPI_TAIL_SHUFFLE, Epi<MG_A(BIASED_PRELU), 0, 0, 0, false>, 6, 6, 2>;
 #undef MG_A
@@ -766,25 +900,24 @@ struct MStage {
   static_assert(E0::TCOLS + E1::TCOLS <= 512, "TMEM columns");
   static_assert((E0::SMEM % 128) == 0, "operand alignment of the second engine");
 };
-using MgStageA = MStage<MgConv2, MgConv3>;
+using MgStageA = MStage<MgConv5, MgConv2>;
 using MgStageB = MStage<MgConv4, MgNone>;
-using MgStageC = MStage<MgConv5, MgConv7>;
+using MgStageC = MStage<MgConv3, MgConv7>;
 using MgStageD = MStage<MgConv6, MgConv1>;
 constexpr int mg_max(int a, int b) { return a > b ? a : b; }
 constexpr int MG_BAR_BYTES = 1152;       // 120 barriers, the TMEM slot, 2 x MG_NR row counters
 constexpr int MG_SMEM = mg_max(mg_max(MgStageA::SMEM, MgStageB::SMEM), mg_max(MgStageC::SMEM, MgStageD::SMEM)) + MG_BAR_BYTES;
 static_assert(MG_SMEM <= SMEM_LIMIT, "fused pass does not fit in shared memory");
 
-template <class E, bool HEAD>
-__device__ __forceinline__ void mg_run_service(const MegaK& M, const MCtx& c, const MEngSmem& s, uint32_t tmem_cols, const float* s_lut,
-                                               uint4* s_raw, int role, int lane) {
+template <class E>
+__device__ __forceinline__ void mg_run_service(const MegaK& M, const MCtx& c, const MEngSmem& s, uint32_t tmem_cols, int role, int lane) {
   if (role == 0) {           // producer warp
-    if constexpr (HEAD) mg_producer_head<E>(M, c, s, s_lut, s_raw, lane);
-    else mg_producer<E>(M, c, s, lane);
+    mg_producer<E>(M, c, s, lane);
   } else if (c.rank != 0) {  // peer CTA: relay
     mg_relay<E>(M, c, s, lane);
   } else if (elect_one()) {  // leader CTA: MMA issue
-    mg_issuer<E>(M, c, s, tmem_cols);
+    if constexpr (E::STAGES >= 5) mg_issuer_rm<E>(M, c, s, tmem_cols);
+    else mg_issuer<E>(M, c, s, tmem_cols);
   }
 }
 
@@ -824,9 +957,10 @@ __device__ __forceinline__ void mg_run_stage(const MegaK& M, MCtx& c, uint8_t* s
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 2) {
-    mg_run_service<E0, E0::L == 1>(M, c, s0, tmem_base, s_lut, s_raw, warp, lane);
+    mg_run_service<E0>(M, c, s0, tmem_base, warp, lane);
   } else if (warp < 4) {
-    if constexpr (ST::kTwo) mg_run_service<E1, E1::L == 1>(M, c, s1, tmem_base + E0::TCOLS, s_lut, s_raw, warp - 2, lane);
+    if constexpr (ST::kTwo) mg_run_service<E1>(M, c, s1, tmem_base + E0::TCOLS, warp - 2, lane);
+    else mg_head_worker(M, c, s_lut, s_raw, warp - 2, lane);      // the stage without a second engine hosts the head
   } else {
     const int wg = (warp - 4) >> 2;
     if (wg < E0::NWG) mg_epilogue<E0>(M, c, s0, tmem_base, s_lut, wg, warp, lane);
@@ -855,9 +989,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) fused_pass_kernel(const __grid_
   c.scratch = M.scratch + ((size_t)c.team * 2 + c.rank) * M.rank_stride;
   c.flags = M.flags + ((size_t)c.team * 2 + c.rank) * MG_FLAG_WORDS;
   switch (stage) {
-    case 0: mg_run_stage<MgStageA, MgConv2, MgConv3>(M, c, smem, s_lut, s_raw, warp, lane); break;
+    case 0: mg_run_stage<MgStageA, MgConv5, MgConv2>(M, c, smem, s_lut, s_raw, warp, lane); break;
     case 1: mg_run_stage<MgStageB, MgConv4, MgNone>(M, c, smem, s_lut, s_raw, warp, lane); break;
-    case 2: mg_run_stage<MgStageC, MgConv5, MgConv7>(M, c, smem, s_lut, s_raw, warp, lane); break;
+    case 2: mg_run_stage<MgStageC, MgConv3, MgConv7>(M, c, smem, s_lut, s_raw, warp, lane); break;
     default: mg_run_stage<MgStageD, MgConv6, MgConv1>(M, c, smem, s_lut, s_raw, warp, lane); break;
   }
 }

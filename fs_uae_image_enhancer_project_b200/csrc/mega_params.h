@@ -6,7 +6,7 @@
 namespace fsuae {
 
 constexpr int MG_MAXC = 80;          // widest layer of the flagship (72 -> N = 80)
-constexpr int MG_NCH = 6;            // channels: output of conv1..conv6
+constexpr int MG_NCH = 7;            // channels: output of conv1..conv6, and the unshuffled input frame (the head's output)
 constexpr int MG_DMAX = 64;          // deepest ring
 constexpr int MG_SMAX = 8;           // strips per row the flag block is laid out for
 constexpr int MG_THREADS = 640;      // 4 service warps + 16 epilogue warps
