@@ -119,8 +119,9 @@ __device__ __forceinline__ int mg_hi(const MSeg& g, int halo, int Hw) { return m
 // straight-line instructions that a handful of warps run through once per row -- they then wait for the instruction cache
 // more than for anything else (ncu: stall_no_inst).
 constexpr int MG_PRM_BYTES = (9 * MG_MAXC * 4 + 127) / 128 * 128;
-template <int LAYER, int PT_, int NPAD_, int COUT_, int KIND_, class EPI_, int RING_, int STAGES_, int NWG_>
+template <int LAYER, int PT_, int NPAD_, int COUT_, int KIND_, class EPI_, int RING_, int STAGES_, int NWG_, bool RM_ = true>
 struct MEng {
+  static constexpr bool RM = RM_;      // input-row-major MMA order (three accumulators open at a time) / block-major
   using EPI = EPI_;
   static constexpr int L = LAYER, PT = PT_, NPAD = NPAD_, COUT = COUT_, KIND = KIND_, RING = RING_, STAGES = STAGES_, NWG = NWG_;
   static constexpr int HALO = 7 - LAYER;
@@ -140,6 +141,7 @@ struct MEng {
   static constexpr int OUT_PLANES = (COUT + 7) / 8;
   static constexpr int OUT_NCONS = LAYER == 1 ? 2 : 1;              // conv1's output is read by conv2 and conv6
   static_assert(STAGES >= NWG, "a warpgroup's previous block must be at least one use of the stage back (mbarrier parity waits)");
+  static_assert(!RM || STAGES >= 4, "row-major order: three open accumulators and at least one being drained");
   static_assert(RING >= 4 && RING <= 16, "ring depth (one relay lane per slot)");
   static_assert(NB % 8 == 0, "each CTA of the pair holds whole core matrices of B");
 };
@@ -368,7 +370,12 @@ __device__ void mg_head_worker(const MegaK& M, const MCtx& c, const float* s_lut
   };
   int fC, yC, fN = 0, yN = 0, fP = 0, yP = 0;
   bool haveC = next_row(fC, yC), haveN = false;
-  uint32_t q = 0, cons_seen = 0;
+  uint32_t q = 0, cons_seen = 0, qtotal = 0;
+  {
+    MSegIter itq(M, c.team);
+    MSeg gq;
+    while (itq.next(gq)) qtotal += (uint32_t)(mg_hi(gq, HALO, M.Hw) - mg_lo(gq, HALO));
+  }
   if (haveC && fb) {
     prefetch(fC, yC, stage);
     haveN = next_row(fN, yN);
@@ -445,10 +452,14 @@ __device__ void mg_head_worker(const MegaK& M, const MCtx& c, const float* s_lut
       }
     }
     MG_T(th2);
-    // both halves stored -> the row counter; the two warps take the release (~1000 cycles) in turn.  Its gpu scope is
-    // cumulative over the CTA-scope barrier, so it covers the other warp's stores as well.
+    // both halves stored -> the row counters, four rows per release: the fence behind it costs ~1000 cycles (every store of
+    // the SM must have reached L2) and the head runs rows ahead of conv1 anyway.  The two warps take it in turn; its gpu scope
+    // is cumulative over the CTA-scope barrier, so it covers the other warp's stores as well.
     asm volatile("bar.sync 1, 64;" ::: "memory");
-    if ((q & 1u) == (uint32_t)w && lane == 0) red_release_gpu_add(prod + q % D, 1u);
+    if (((q & 3u) == 3u || q + 1u == qtotal) && ((q >> 2) & 1u) == (uint32_t)w && lane == 0) {
+      fence_acq_rel_gpu();
+      for (uint32_t qq = q & ~3u; qq <= q; ++qq) red_relaxed_gpu_add(prod + qq % D, 1u);
+    }
     MG_T(th3);
     if (haveP && fb) prefetch(fP, yP, stage + ((q + 2u) % 3u) * MROWS);
     MG_T(th4);
@@ -647,6 +658,30 @@ __device__ __forceinline__ void mg_slot8(int slot, const float* prm, float (&o)[
   }
 }
 
+// Layers without activations or residual (conv3, conv5): bias, round, store -- NCHUNK 8-channel chunks per accumulator read-back
+// (one tcgen05.ld + one wait for up to 32 columns instead of a wait per chunk: the read-back latency is all this epilogue costs).
+template <int NCHUNK>
+__device__ __forceinline__ void mg_ident_group(uint32_t taddr, const float* prm, unsigned char* dp, size_t plane_pitch, bool valid, int nlast) {
+  uint32_t v[NCHUNK * 8];
+  tmem_ld_cols<NCHUNK * 8>(taddr, v);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < NCHUNK; ++j) {
+    const float4 b0 = *reinterpret_cast<const float4*>(prm + j * 8), b1 = *reinterpret_cast<const float4*>(prm + j * 8 + 4);
+    float o[8];
+    o[0] = __uint_as_float(v[j * 8 + 0]) + b0.x; o[1] = __uint_as_float(v[j * 8 + 1]) + b0.y; o[2] = __uint_as_float(v[j * 8 + 2]) + b0.z;
+    o[3] = __uint_as_float(v[j * 8 + 3]) + b0.w; o[4] = __uint_as_float(v[j * 8 + 4]) + b1.x; o[5] = __uint_as_float(v[j * 8 + 5]) + b1.y;
+    o[6] = __uint_as_float(v[j * 8 + 6]) + b1.z; o[7] = __uint_as_float(v[j * 8 + 7]) + b1.w;
+    if (j == NCHUNK - 1) {           // padding channels stay exactly zero
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = i < nlast ? o[i] : 0.f;
+    }
+    if (valid)
+      *reinterpret_cast<uint4*>(dp + (size_t)j * plane_pitch) =
+          make_uint4(pack_op2(o[0], o[1]), pack_op2(o[2], o[3]), pack_op2(o[4], o[5]), pack_op2(o[6], o[7]));
+  }
+}
+
 // ---- epilogue warpgroup `wg` of the engine's NWG --------------------------------------------------------------------------
 template <class E>
 __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, uint32_t tmem_cols, const float* s_lut, int wg, int warp, int lane) {
@@ -738,8 +773,16 @@ __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, ui
       const uint8_t* sp = s.ring + cslot * E::ROWBYTES + (m + 1) * 16;
       if constexpr (EPI::kSkip) mbar_wait(&s.full[cslot], (kc / E::RING) & 1);
 
+      constexpr bool kPlain = !EPI::kSkip && EPI::kOp0 == 0 && EPI::kOp1 == 0 && EPI::kOp2 == 0 && EPI::kOp3 == 0;
       if constexpr (E::KIND == EPI_STORE) {
         unsigned char* dp = och + (size_t)(q % (uint32_t)D) * row_pitch + (size_t)(x + BORDER) * 16;
+        if constexpr (kPlain) {
+          constexpr int NC = E::OUT_PLANES, NLAST = E::COUT - 8 * (NC - 1);
+          static_assert(NC == 5 || NC == 9, "plain layers of the flagship: 36 or 72 channels");
+          mg_ident_group<4>(taddr, s.prm, dp, plane_pitch, valid, 8);
+          if constexpr (NC == 9) mg_ident_group<4>(taddr + 32, s.prm + 32, dp + 4 * plane_pitch, plane_pitch, valid, 8);
+          mg_ident_group<1>(taddr + (NC - 1) * 8, s.prm + (NC - 1) * 8, dp + (size_t)(NC - 1) * plane_pitch, plane_pitch, valid, NLAST);
+        } else {
         // the accumulator chunk of the NEXT iteration is already on its way while this one goes through the activations
         // (a tcgen05.ld takes several hundred cycles while the MMAs keep the tensor memory busy)
         uint32_t vn[8];
@@ -785,6 +828,7 @@ __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, ui
           if (valid)
             *reinterpret_cast<uint4*>(dp + (size_t)cc * plane_pitch) =
                 make_uint4(pack_op2(o[0], o[1]), pack_op2(o[2], o[3]), pack_op2(o[4], o[5]), pack_op2(o[6], o[7]));
+        }
         }
         // The last of the four warps to finish row q bumps the channel's row counter: its release at gpu scope is cumulative
         // over the CTA-scope acquire / release on the shared-memory counter, so it covers the other warps' stores as well,
@@ -875,18 +919,20 @@ __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, ui
 
 // ---- the engines of the flagship preset (model_pix_shuffle.py:306-311) ---------------------------------------------------
 #define MG_A(x) FSUAE_ACT_##x
-// <layer, input planes, N, Cout, kind, epilogue, ring rows, accumulator stages (>= 5: row-major MMA order), epilogue warpgroups>
+// <layer, input planes, N, Cout, kind, epilogue, ring rows, accumulator stages, epilogue warpgroups, row-major MMA order>
+// Accumulator stages: the row-major order keeps three open; on top of that one per row being drained at a time -- a plain
+// layer drains a row in ~1300 cycles (one stage), an activation chain takes ~4500 (one stage per warpgroup).
 // Who shares an SM is decided by three budgets -- tensor time (MMA instructions per row x their cost), issue slots /
 // SFU time of the activation chains, and TMEM columns (stages x N <= 512 per SM):
 //   conv5 (42 MMAs, no activation: ONE warpgroup)     + conv2 (24 MMAs, the longest chain: THREE warpgroups)
 //   conv4 (42 MMAs at N = 80, long chain: all four)   + the head
 //   conv3 (24 MMAs at N = 80, no activation)          + conv7 (24 MMAs at N = 16, PixelShuffle tail)
 //   conv6 (45 MMAs, Mish)                             + conv1 (9 MMAs, SinLU)
-using MgConv1 = MEng<1, 2, 48, 36, EPI_STORE, Epi<MG_A(SINLU), MG_A(RELU6), 0, 0, false>, 8, 4, 2>;
-using MgConv2 = MEng<2, 5, 48, 36, EPI_STORE, Epi<MG_A(TELU), 0, MG_A(SINLU), MG_A(BIASED_PRELU), true>, 6, 5, 3>;
+using MgConv1 = MEng<1, 2, 48, 36, EPI_STORE, Epi<MG_A(SINLU), MG_A(RELU6), 0, 0, false>, 8, 4, 2, false>;
+using MgConv2 = MEng<2, 5, 48, 36, EPI_STORE, Epi<MG_A(TELU), 0, MG_A(SINLU), MG_A(BIASED_PRELU), true>, 6, 6, 3>;
 using MgConv3 = MEng<3, 5, 80, 72, EPI_STORE, Epi<0, 0, 0, 0, false>, 8, 5, 2>;
 using MgConv4 = MEng<4, 9, 80, 72, EPI_STORE, Epi<MG_A(MISH), MG_A(BIASED_PRELU), MG_A(TANH), MG_A(RELU), true>, 9, 6, 4>;
-using MgConv5 = MEng<5, 9, 48, 36, EPI_STORE, Epi<0, 0, 0, 0, false>, 5, 5, 1>;
+using MgConv5 = MEng<5, 9, 48, 36, EPI_STORE, Epi<0, 0, 0, 0, false>, 5, 4, 1>;
 using MgConv6 = MEng<6, 10, 48, 36, EPI_STORE, Epi<MG_A(MISH), MG_A(RELU6), 0, 0, false>, 6, 6, 2>;
 using MgConv7 = MEng<7, 5, 16, 12, EPI_TAIL_SHUFFLE, Epi<MG_A(BIASED_PRELU), 0, 0, 0, false>, 6, 6, 2>;
 #undef MG_A
@@ -916,7 +962,7 @@ __device__ __forceinline__ void mg_run_service(const MegaK& M, const MCtx& c, co
   } else if (c.rank != 0) {  // peer CTA: relay
     mg_relay<E>(M, c, s, lane);
   } else if (elect_one()) {  // leader CTA: MMA issue
-    if constexpr (E::STAGES >= 5) mg_issuer_rm<E>(M, c, s, tmem_cols);
+    if constexpr (E::RM) mg_issuer_rm<E>(M, c, s, tmem_cols);
     else mg_issuer<E>(M, c, s, tmem_cols);
   }
 }
