@@ -153,7 +153,10 @@ struct MEngSmem {      // shared-memory carve-up of one engine
   uint64_t *full, *empty, *pfull, *tfull, *tempty, *wbar;
   uint32_t* rowcnt;      // [MG_NR] epilogue warps that have stored their part of output row q (slot q % MG_NR, never reset)
 };
-constexpr int MG_NR = 8;   // >= accumulator stages: row q + MG_NR cannot reach its epilogue before row q has released its stage
+constexpr int MG_NR = 8;   // counters of MG_NR row groups in flight: group g + MG_NR cannot reach its epilogue before group g has released its stages
+#ifndef MG_PUB_ROWS
+#define MG_PUB_ROWS 4      // rows per release of an engine's output (one fence for all of them)
+#endif
 template <class E>
 __device__ __forceinline__ MEngSmem mg_carve(uint8_t* data, uint64_t* bars, uint32_t* rowcnt) {
   static_assert(E::STAGES <= MG_NR, "row counters vs accumulator stages");
@@ -698,7 +701,7 @@ __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, ui
   unsigned int* prod = mg_prod(c.flags, E::OUT >= 0 ? E::OUT : 0);
   uint32_t blk = 0, qrow = 0, qout = 0;          // blocks / ring rows / output rows before this segment
   uint32_t qtotal = 0;                           // output rows of this engine in all
-  if constexpr (E::NWG == 1) {
+  {
     MSegIter itq(M, c.team);
     MSeg gq;
     while (itq.next(gq)) qtotal += (uint32_t)(mg_hi(gq, E::HALO, M.Hw) - mg_lo(gq, E::HALO));
@@ -830,25 +833,20 @@ __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, ui
                 make_uint4(pack_op2(o[0], o[1]), pack_op2(o[2], o[3]), pack_op2(o[4], o[5]), pack_op2(o[6], o[7]));
         }
         }
-        // The last of the four warps to finish row q bumps the channel's row counter: its release at gpu scope is cumulative
-        // over the CTA-scope acquire / release on the shared-memory counter, so it covers the other warps' stores as well,
-        // and only one warp per row waits (~1000 cycles) for the stores to reach L2.
+        // Rows are published in groups of MG_PUB_ROWS: the last warp to finish the group (4 warps per row, whichever
+        // warpgroups they belong to) bumps the rows' counters behind ONE fence.  Its gpu scope is cumulative over the
+        // CTA-scope acquire / release on the shared-memory counter, so it covers the other warps' stores as well, and only
+        // that warp waits (1000-1700 cycles) for the SM's stores to reach L2.
         MG_T(tf0);
         __syncwarp();
         if (lane == 0) {
-          const uint32_t before = atom_acq_rel_cta_smem_add(s.rowcnt + q % (uint32_t)MG_NR, 1u);
+          const uint32_t grp = q / (uint32_t)MG_PUB_ROWS, q_lo = grp * (uint32_t)MG_PUB_ROWS;
+          const uint32_t nrows = min((uint32_t)MG_PUB_ROWS, qtotal - q_lo);           // the channel's last group may be short
+          const uint32_t before = atom_acq_rel_cta_smem_add(s.rowcnt + grp % (uint32_t)MG_NR, 1u);
           MG_T(tf1);
-          if ((before & 3u) == 3u) {
-            if constexpr (E::NWG == 1) {
-              // a single warpgroup takes the rows in order and pays for every release itself: two rows per fence
-              if ((q & 1u) == 1u || q + 1u == qtotal) {
-                fence_acq_rel_gpu();
-                if ((q & 1u) == 1u) red_relaxed_gpu_add(prod + (q - 1u) % (uint32_t)D, 1u);
-                red_relaxed_gpu_add(prod + q % (uint32_t)D, 1u);
-              }
-            } else {
-              red_release_gpu_add(prod + q % (uint32_t)D, 1u);
-            }
+          if ((before + 1u) % (4u * (uint32_t)MG_PUB_ROWS) == (4u * nrows) % (4u * (uint32_t)MG_PUB_ROWS)) {
+            fence_acq_rel_gpu();
+            for (uint32_t qq = q_lo; qq < q_lo + nrows; ++qq) red_relaxed_gpu_add(prod + qq % (uint32_t)D, 1u);
           }
           MG_T(tf2);
           MG_ACC(tprobe, E::L, 14, tf1 - tf0); MG_ACC(tprobe, E::L, 15, tf2 - tf1);

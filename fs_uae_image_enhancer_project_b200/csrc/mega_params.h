@@ -7,7 +7,10 @@ namespace fsuae {
 
 constexpr int MG_MAXC = 80;          // widest layer of the flagship (72 -> N = 80)
 constexpr int MG_NCH = 7;            // channels: output of conv1..conv6, and the unshuffled input frame (the head's output)
-constexpr int MG_DMAX = 64;          // deepest ring
+#ifndef MG_DMAX_ROWS
+#define MG_DMAX_ROWS 64
+#endif
+constexpr int MG_DMAX = MG_DMAX_ROWS;  // deepest ring
 constexpr int MG_SMAX = 8;           // strips per row the flag block is laid out for
 constexpr int MG_THREADS = 640;      // 4 service warps + 16 epilogue warps
 constexpr int MG_FLAG_WORDS = MG_NCH * MG_DMAX + MG_NCH * 2 * MG_SMAX;      // per (team, rank): prod[ch][slot], cons[ch][consumer][strip]
@@ -15,7 +18,7 @@ constexpr int MG_FLAG_WORDS = MG_NCH * MG_DMAX + MG_NCH * 2 * MG_SMAX;      // p
 #define MG_D0 64                     // rows of the conv1 -> conv2 / conv6 ring: the long skip spans the whole pipeline
 #endif
 #ifndef MG_D1
-#define MG_D1 12                     // rows of every other ring
+#define MG_D1 20                     // rows of every other ring
 #endif
 __host__ __device__ constexpr int mg_depth(int ch) { return ch == 0 ? MG_D0 : MG_D1; }
 static_assert(MG_D0 <= MG_DMAX && MG_D1 <= MG_DMAX, "flag block layout");
