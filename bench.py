@@ -257,6 +257,32 @@ def main():
     eng.set_profiling(False)
     per_kernel = {k: sum(v) / len(v) for k, v in per_kernel.items()}
 
+    # the other arithmetic path of the same library, same frames, same weights: one kernel per layer (conv3 -> conv4 fused),
+    # feature maps through HBM.  Timed like the headline; reported beside it, never instead of it.
+    alt = None
+    if eng.last_launch_count <= 2 and not args.quick:
+        os.environ["FSUAE_NO_MEGA"] = "1"
+        try:
+            model2 = seeded_model().to(dev)
+            model2.chunk_frames = args.chunk
+            model2.set_precision(precision)
+            eng2 = model2.engine_for(dev, FRAME_H, FRAME_W)
+        finally:
+            os.environ.pop("FSUAE_NO_MEGA", None)
+        for i in range(args.warmup):
+            eng2.enqueue(d_in[i & 1], d_out[i & 1], BATCH, _lib.FMT_U8_NHWC4, _lib.FMT_U8_NHWC4, flags)
+        barrier()
+        ev0.record()
+        for i in range(args.steps):
+            eng2.enqueue(d_in[i & 1], d_out[i & 1], BATCH, _lib.FMT_U8_NHWC4, _lib.FMT_U8_NHWC4, flags)
+        ev1.record()
+        barrier()
+        alt_ms = ev0.elapsed_time(ev1)
+        alt = {"path": "one kernel per layer (conv3 -> conv4 fused), feature maps through HBM", "variant": eng2.variant,
+               "launches_per_step": int(eng2.last_launch_count), "ms_per_step": alt_ms / args.steps}
+        del eng2, model2
+        torch.cuda.empty_cache()
+
     if args.quick:
         if rank == 0:
             print(json.dumps({"chunk": args.chunk, "fps": BATCH * world * args.steps / (ms / 1000.0),
@@ -390,6 +416,10 @@ def main():
                      "unit": "frames/s", "clocks": sampler2.stop() if rank == 0 else None}
 
     ms, e2e_s, e2e_sync_s, copy_s = (max_over_ranks(v, dev) for v in (ms, e2e_s, e2e_sync_s, copy_s))   # slowest rank
+    if alt is not None:
+        alt["ms_per_step"] = max_over_ranks(alt["ms_per_step"], dev)
+        alt["value"] = BATCH * world / (alt["ms_per_step"] / 1000.0)
+        alt["unit"] = "frames/s"
 
     if rank == 0:
         frames = BATCH * world * args.steps
@@ -455,6 +485,7 @@ def main():
                                     "note": f"algorithmic 29.472 GFLOP/frame x {BATCH} frames / step device time (all kernels of the "
                                             f"pass); HBM floor: {algo_bytes / 1e9 / (hbm_peak) * 1e3:.3f} ms/step"},
             "kernel_ms": per_kernel,
+            "layer_by_layer": alt,
             "parity_check": parity,
             "stream_config5": stream5,
             "sustained": sustained,

@@ -15,18 +15,27 @@
 //         stage B = conv4 (Mish, BiasedPReLU, Tanh: both)        + the network head on the two service warps a second engine would use
 //         stage C = conv3 (no activation)                        + conv7 (PixelShuffle tail: store / pow-bound)
 //         stage D = conv6 (Mish)                                 + conv1 (SinLU)
-//     MMA instructions per strip row: A 24+24, B 42, C 42+24, D 45+9 -- balanced to within 15 % at N = 48/80.
+//     MMA instructions per strip row: A 42+24, B 42, C 24+24, D 45+9 (see the budget table at the engine definitions).
 //   * 4 stage pairs = 1 group = one 126-column strip of a frame pair; S groups (S strips) = 1 team = whole rows of a frame
 //     pair; the rows of all frame pairs are cut into equal contiguous ranges, one per team.  Where a range starts or ends
 //     inside a frame, layer i recomputes 7-i halo rows (1.3 % extra MMAs at 64 frames) -- teams never talk to each other.
-//   * Engines talk through CHANNELS in global memory: the producer layer's epilogue stores row q of its output into slot
-//     q % D of a D-row ring (chunk-planar, full image width, zero borders baked in exactly as in the per-layer buffers) and
-//     then bumps a per-slot counter (red.release.gpu); the consumer layer's producer warp polls those counters
-//     (ld.acquire.gpu, one coalesced load covers the whole ring) before its TMA bulk copies, and publishes how far it has
-//     read so the ring slot can be overwritten.  All S strips of a row must be complete before any strip of the next layer
-//     reads it (the 3x3 taps reach one column into the neighbouring strips).
-//   * Rings: 12 rows per channel, 32 for conv1 -> conv6 (the long skip spans the whole pipeline): 3.4 MB per frame in flight,
-//     12 frames in flight -> 41 MB, well inside the 126 MB L2.
+//   * Engines talk through CHANNELS in global memory (7 of them: the outputs of conv1..conv6 and the head's unshuffled input
+//     frame): the producing epilogue stores row q of its output into slot q % D of a D-row ring (chunk-planar, full image
+//     width, zero borders baked in exactly as in the per-layer buffers); the last warp to finish a group of MG_PUB_ROWS rows
+//     bumps their per-slot counters behind ONE gpu-scope release (cumulative over a CTA-scope counter, so no other warp ever
+//     waits for its stores to reach L2).  The consuming layer's producer warp polls those counters with relaxed loads (an
+//     acquire LOAD invalidates the SM's L1 every time), fences once per successful poll, issues its TMA bulk copies, and
+//     hands out credits ("rows below b have landed in my shared memory") so the ring slot can be overwritten.  All S strips
+//     of a row must be complete before any strip of the next layer reads it (the 3x3 taps reach one column into the
+//     neighbouring strips).
+//   * Rings: MG_D1 = 16 rows per channel, MG_D0 = 64 for conv1 -> conv2 / conv6 (the long skip spans the whole pipeline):
+//     5.4 MB per (team, frame of the pair), 65 MB for the 6 teams a B200 holds.  The depth is what hides the credit loop
+//     (store -> release -> poll -> copy -> credit -> poll); measured at 64 frames, DRAM bytes per pass / time per frame:
+//     D1 = 12: 0.57 GB / 42.9 us, 14: 0.73 / 41.7, 16: 1.07 / 39.8, 20: 2.38 / 38.4 (the layer kernels: 7.7 GB / 37.4 us;
+//     algorithmic: 0.22 GB).  Past ~60 MB of rings the dirty lines of consumed rows start to be evicted before they are
+//     overwritten.
+
+#include <algorithm>
 
 #include "mega_params.h"
 #include "tc_common.cuh"

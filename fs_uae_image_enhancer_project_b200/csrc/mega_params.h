@@ -18,7 +18,7 @@ constexpr int MG_FLAG_WORDS = MG_NCH * MG_DMAX + MG_NCH * 2 * MG_SMAX;      // p
 #define MG_D0 64                     // rows of the conv1 -> conv2 / conv6 ring: the long skip spans the whole pipeline
 #endif
 #ifndef MG_D1
-#define MG_D1 20                     // rows of every other ring
+#define MG_D1 16                     // rows of every other ring
 #endif
 __host__ __device__ constexpr int mg_depth(int ch) { return ch == 0 ? MG_D0 : MG_D1; }
 static_assert(MG_D0 <= MG_DMAX && MG_D1 <= MG_DMAX, "flag block layout");

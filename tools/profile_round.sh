@@ -1,7 +1,12 @@
+#!/bin/bash
+# On the GPU box: tests, bench line, ncu launch list and full captures of this round.  Nothing printed under ncu is a bench value.
+cd "$(dirname "$0")/.." || exit 1
+R=${1:-r02}
+mkdir -p gpurun_out
 set -x
-timeout 500 python bench.py --steps 20 --warmup 3 2>/dev/null | tail -1 > gpurun_out/r01_bench_line.json
-timeout 300 python tools/bench_models.py > gpurun_out/r01_model_families.log 2>&1
-for a in "conv3 heavyweight" "conv5 heavyweight" "pix_shuffle heavyweight" "conv3 lightweight" "conv5 lightweight"; do echo "== $a"; timeout 120 python tools/kernel_times.py $a bf16 16; done > gpurun_out/r01_family_kernel_times.log 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 24 -c 16 --csv --log-file gpurun_out/r01_launch_list.csv python bench.py --steps 2 --warmup 3 --quick > gpurun_out/ncu_list.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv3x3_tc_wide -s 2 -c 2 -o gpurun_out/wide_conv3heavy python tools/kernel_times.py conv3 heavyweight bf16 8 > gpurun_out/ncu_wide.log 2>&1
-tail -2 gpurun_out/ncu_wide.log
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${R}_gputest.log 2>&1; echo "rc=$?" >> gpurun_out/${R}_gputest.log
+timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/${R}_bench.log 2>&1 && tail -1 gpurun_out/${R}_bench.log > gpurun_out/${R}_bench_line.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${R}_launch_list.csv python bench.py --steps 2 --warmup 3 --quick > gpurun_out/${R}_ncu_list.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:fused_pass -s 2 -c 1 -o gpurun_out/${R}_fused_pass python bench.py --steps 2 --warmup 3 --quick > gpurun_out/${R}_ncu_fused.log 2>&1
+FSUAE_NO_MEGA=1 timeout 600 ncu --set full --clock-control none -k regex:conv3x3_tc -s 12 -c 6 -o gpurun_out/${R}_layers python bench.py --steps 2 --warmup 3 --quick > gpurun_out/${R}_ncu_layers.log 2>&1
+tail -3 gpurun_out/${R}_gputest.log; tail -c 600 gpurun_out/${R}_bench_line.json
