@@ -210,8 +210,9 @@ struct MCtx {          // where this CTA sits
 #ifndef MG_POLL_BATCH
 #define MG_POLL_BATCH 3
 #endif
-__device__ __forceinline__ void mg_wait_rows(const MegaK& M, const MCtx& c, int ch, uint32_t q, uint32_t qtotal, uint32_t& upto, int lane) {
-  if (q < upto) return;
+// Returns true when it polled (the caller then fences once for all its sources).
+__device__ __forceinline__ bool mg_wait_rows(const MegaK& M, const MCtx& c, int ch, uint32_t q, uint32_t qtotal, uint32_t& upto, int lane) {
+  if (q < upto) return false;
   const uint32_t want = min(q + (uint32_t)MG_POLL_BATCH, qtotal) - q;
   const uint32_t D = (uint32_t)mg_depth(ch), need_per_use = (uint32_t)M.S;          // every strip's publisher bumps the counter once per row
   const unsigned int* prod = mg_prod(c.flags, ch);
@@ -229,8 +230,12 @@ __device__ __forceinline__ void mg_wait_rows(const MegaK& M, const MCtx& c, int 
     if (clock64() - t0 > (1ll << 31)) __trap();
     __nanosleep(64);
   }
-  // Once per successful poll (it usually reveals several rows): order the bulk copies (async proxy) behind the counters
-  // just read (generic proxy).  The proxy fence costs ~1000 cycles, so it must not sit between "ring slot free" and the copy.
+  return true;
+}
+// Once per successful poll (it usually reveals several rows, of both sources of conv6): order the bulk copies (async proxy)
+// behind the counters just read (generic proxy).  The two fences cost ~1500 cycles, so they must not sit between "ring slot
+// free" and the copy.
+__device__ __forceinline__ void mg_fence_after_poll(int lane) {
 #if MG_POLL_ACQ
   fence_acq_rel_gpu();
 #endif
@@ -299,29 +304,25 @@ __device__ void mg_producer(const MegaK& M, const MCtx& c, const MEngSmem& s, in
       MG_T(tp0b);
       MG_ACC(tprobe, 8, 4 + E::L, tp0b - tp0);      // row 7, [5 .. 11]: the credit step (waits for the copy of fill - 2)
       if (inframe) {       // usually known from an earlier poll: the upstream layer runs ahead while my ring is full
-        mg_wait_rows(M, c, E::IN0, q0, tot0, upto0, lane);
-        if constexpr (E::IN1 >= 0) mg_wait_rows(M, c, E::IN1 >= 0 ? E::IN1 : 0, q1, tot1, upto1, lane);
+        bool polled = mg_wait_rows(M, c, E::IN0, q0, tot0, upto0, lane);
+        if constexpr (E::IN1 >= 0) polled = mg_wait_rows(M, c, E::IN1 >= 0 ? E::IN1 : 0, q1, tot1, upto1, lane) || polled;
+        if (polled) mg_fence_after_poll(lane);
       }
       MG_T(tp1);
       if (lane == 0) mbar_wait(&s.empty[slot], par);
       MG_T(tp2);
       MG_ACC(tprobe, E::L, 5, tp1 - tp0b); MG_ACC(tprobe, E::L, 4, tp2 - tp1); MG_ACC(tprobe, E::L, 12, 1);
-      if (lane == 0) {
-        uint8_t* d = s.ring + slot * E::ROWBYTES;
-        mbar_arrive_expect_tx(&s.full[slot], E::ROWBYTES);
+      // one bulk copy per plane, one lane each: a single issue slot for the whole row instead of PT in a row
+      if (lane == 0) mbar_arrive_expect_tx(&s.full[slot], E::ROWBYTES);
+      __syncwarp();
+      if (lane < E::PT) {
+        uint8_t* d = s.ring + slot * E::ROWBYTES + lane * PLANE_ROW;
+        const unsigned char* src = M.zero_row;
         if (inframe) {
-          const unsigned char* g0 = ch0 + (size_t)(q0 % (uint32_t)mg_depth(E::IN0)) * row_pitch + xoff_b;
-#pragma unroll 1
-          for (int j = 0; j < E::P0; ++j) tma_load_1d(d + j * PLANE_ROW, g0 + (size_t)j * pp0, PLANE_ROW, &s.full[slot]);
-          if constexpr (E::IN1 >= 0) {
-            const unsigned char* g1 = ch1 + (size_t)(q1 % (uint32_t)mg_depth(E::IN1 >= 0 ? E::IN1 : 0)) * row_pitch + xoff_b;
-#pragma unroll 1
-            for (int j = 0; j < E::P1; ++j) tma_load_1d(d + (E::P0 + j) * PLANE_ROW, g1 + (size_t)j * pp1, PLANE_ROW, &s.full[slot]);
-          }
-        } else {
-#pragma unroll 1
-          for (int j = 0; j < E::PT; ++j) tma_load_1d(d + j * PLANE_ROW, M.zero_row, PLANE_ROW, &s.full[slot]);
+          if (lane < E::P0) src = ch0 + (size_t)(q0 % (uint32_t)mg_depth(E::IN0)) * row_pitch + xoff_b + (size_t)lane * pp0;
+          else src = ch1 + (size_t)(q1 % (uint32_t)mg_depth(E::IN1 >= 0 ? E::IN1 : 0)) * row_pitch + xoff_b + (size_t)(lane - E::P0) * pp1;
         }
+        tma_load_1d(d, src, PLANE_ROW, &s.full[slot]);
       }
       ++fill;
     }
