@@ -424,6 +424,10 @@ __device__ void mg_head_worker(const MegaK& M, const MCtx& c, const float* s_lut
       for (int k = 0; k < 2; ++k) {
         const uint4 cur = src[32 * k + lane];          // written by this very lane: {dy 0: px 0, px 1; dy 1: px 0, px 1}
         float v[12];
+#ifdef MG_DBG_NOHEAD      // timing experiment (garbage results): the head without its table look-ups
+#pragma unroll
+        for (int ch = 0; ch < 12; ++ch) v[ch] = __uint_as_float(cur.x);
+#else
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
           v[ch * 4 + 0] = s_lut[(cur.x >> (8 * ch)) & 0xFF];
@@ -431,6 +435,7 @@ __device__ void mg_head_worker(const MegaK& M, const MCtx& c, const float* s_lut
           v[ch * 4 + 2] = s_lut[(cur.z >> (8 * ch)) & 0xFF];
           v[ch * 4 + 3] = s_lut[(cur.w >> (8 * ch)) & 0xFF];
         }
+#endif
         if (okx[k]) {
           unsigned char* d = dp + (size_t)(xx[k] + BORDER) * 16;
           *reinterpret_cast<uint4*>(d) = make_uint4(pack_op2(v[0], v[1]), pack_op2(v[2], v[3]), pack_op2(v[4], v[5]), pack_op2(v[6], v[7]));

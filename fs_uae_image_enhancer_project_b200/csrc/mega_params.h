@@ -15,10 +15,10 @@ constexpr int MG_SMAX = 8;           // strips per row the flag block is laid ou
 constexpr int MG_THREADS = 640;      // 4 service warps + 16 epilogue warps
 constexpr int MG_FLAG_WORDS = MG_NCH * MG_DMAX + MG_NCH * 2 * MG_SMAX;      // per (team, rank): prod[ch][slot], cons[ch][consumer][strip]
 #ifndef MG_D0
-#define MG_D0 64                     // rows of the conv1 -> conv2 / conv6 ring: the long skip spans the whole pipeline
+#define MG_D0 56                     // rows of the conv1 -> conv2 / conv6 ring: the long skip spans the whole pipeline
 #endif
 #ifndef MG_D1
-#define MG_D1 16                     // rows of every other ring
+#define MG_D1 13                     // rows of every other ring
 #endif
 __host__ __device__ constexpr int mg_depth(int ch) { return ch == 0 ? MG_D0 : MG_D1; }
 static_assert(MG_D0 <= MG_DMAX && MG_D1 <= MG_DMAX, "flag block layout");
