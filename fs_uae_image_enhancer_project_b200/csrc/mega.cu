@@ -28,12 +28,12 @@
 //     hands out credits ("rows below b have landed in my shared memory") so the ring slot can be overwritten.  All S strips
 //     of a row must be complete before any strip of the next layer reads it (the 3x3 taps reach one column into the
 //     neighbouring strips).
-//   * Rings: MG_D1 = 16 rows per channel, MG_D0 = 64 for conv1 -> conv2 / conv6 (the long skip spans the whole pipeline):
-//     5.4 MB per (team, frame of the pair), 65 MB for the 6 teams a B200 holds.  The depth is what hides the credit loop
-//     (store -> release -> poll -> copy -> credit -> poll); measured at 64 frames, DRAM bytes per pass / time per frame:
-//     D1 = 12: 0.57 GB / 42.9 us, 14: 0.73 / 41.7, 16: 1.07 / 39.8, 20: 2.38 / 38.4 (the layer kernels: 7.7 GB / 37.4 us;
-//     algorithmic: 0.22 GB).  Past ~60 MB of rings the dirty lines of consumed rows start to be evicted before they are
-//     overwritten.
+//   * Rings: MG_D1 = 13 rows per channel, MG_D0 = 56 for conv1 -> conv2 / conv6 (the long skip spans the whole pipeline):
+//     4.5 MB per (team, frame of the pair), 54 MB for the 6 teams a B200 holds.  The depth is what hides the credit loop
+//     (store -> release -> poll -> copy -> credit -> poll); measured at 64 frames, D0/D1 -> DRAM bytes per pass / time per
+//     frame: 48/12 -> 0.31 GB / 40.1 us, 56/13 -> 0.45 / 38.5, 64/16 -> 1.15 / 37.9, 64/20 -> 2.33 / 37.6 (the layer kernels:
+//     7.7 GB / 37.2-38.2 us; algorithmic: 0.22 GB).  Past ~55 MB of rings the dirty lines of consumed rows start to be
+//     evicted before they are overwritten.
 
 #include <algorithm>
 
