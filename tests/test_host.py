@@ -205,7 +205,7 @@ def test_model_constructor_errors():
     d5, blob5 = build_descriptor(m5._layer_specs(), m5._head, m5._tail)
     assert [d5.layers[i].ksize for i in range(7)] == [3, 5, 3, 3, 3, 3, 7]                             # 1x1 = centre tap of 3x3
     w5 = blob5[d5.layers[4].w_off:d5.layers[4].w_off + 36 * 36 * 9].reshape(36, 36, 3, 3)
-    assert np.array_equal(w5[:, :, 1, 1], m5.conv5.weight.detach().numpy()[:, :, 0, 0]) and np.abs(w5).sum() == np.abs(w5[:, :, 1, 1]).sum()
+    assert np.array_equal(w5[:, :, 1, 1], m5.conv5.weight.detach().numpy()[:, :, 0, 0]) and np.count_nonzero(w5) == np.count_nonzero(w5[:, :, 1, 1])
     # channel plans with 1x1 skip projections: same parameter names as the reference (:126-128, :143-145), and the
     # projection becomes a layer of its own in the engine descriptor
     m = model_pix_shuffle.Model(layer1_out_channels=24, layer2_out_channels=36, layer3_out_channels=40, layer4_out_channels=40)
