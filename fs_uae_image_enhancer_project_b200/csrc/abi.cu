@@ -36,6 +36,7 @@ static Tuning read_tuning() {
   num("FSUAE_DEBUG_GRID", t.grid);
   num("FSUAE_R3", t.r3);
   num("FSUAE_MEGA_MIN_FRAMES", t.mega_min_frames);
+  num("FSUAE_HOST_CHUNK", t.host_chunk);
   flag("FSUAE_NO_FUSION", t.no_fusion);
   flag("FSUAE_NO_PAIRS", t.no_pairs);
   flag("FSUAE_NO_WIDE", t.no_wide);
@@ -215,7 +216,7 @@ int fsuae_engine_create(const fsuae_net_desc* desc, const float* blob, size_t bl
   }
 
   // host-pipeline staging: sized for the widest formats
-  e->host_chunk = std::min(e->chunk, 32);  // largest stage of the host-buffer pipeline (H2D / compute / D2H overlap): the fused pass is 9 % faster per frame on 32 frames than on 16
+  e->host_chunk = std::min(e->chunk, e->tuning.host_chunk > 0 ? e->tuning.host_chunk : 32);  // largest stage of the host-buffer pipeline (H2D / compute / D2H overlap): the fused pass is 9 % faster per frame on 32 frames than on 16
   size_t in_b = (size_t)e->host_chunk * std::max<size_t>(12, frame_bytes(e, FSUAE_FMT_F32_NCHW, true) / ((size_t)height * width)) * height * width;
   size_t out_b = (size_t)e->host_chunk * std::max<size_t>(16, frame_bytes(e, FSUAE_FMT_F32_NCHW, false) / ((size_t)height * width)) * height * width;
   for (int i = 0; i < FSUAE_STAGE_BUFS && ce == cudaSuccess; ++i) {

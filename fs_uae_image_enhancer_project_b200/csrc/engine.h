@@ -26,6 +26,7 @@ struct Tuning {
   bool no_mega = false;         // FSUAE_NO_MEGA: never use the single fused pass (layer-by-layer kernels only)
   int mega_min_frames = -1;     // FSUAE_MEGA_MIN_FRAMES=n: smallest pass the fused kernel takes
   std::vector<int> host_stages; // FSUAE_HOST_STAGES=a,b,...: stage sizes of the host-buffer pipeline
+  int host_chunk = 0;           // FSUAE_HOST_CHUNK=n: largest stage of the host-buffer pipeline (default 32)
   std::string tag;              // " [FSUAE_R3=1 ...]" for the variant string
 };
 

@@ -85,6 +85,7 @@ __device__ __forceinline__ unsigned int* mg_prod(unsigned int* fl, int ch) { ret
 // [4] producer waits for a free ring slot  [5] ... for the upstream layer's rows (flags)  [6] producer total
 // [7] epilogue warp 0 waits for the downstream ring (back-pressure)  [8] ... for the accumulator  [9] math + stores + signals
 // [10] epilogue total  [11] rows of that warp  [12] producer rows  [13] issuer rows  [14] writer-side proxy fence  [15] release of the row counter
+// Row 7 (the head and extras): [0..4] see g_mega_t, [5..11] credit step of conv1..conv7's producers, [12] conv4 relay wait, [13] head worker 0 total
 #ifdef FSUAE_EPI_TIMING
 __device__ unsigned long long g_mega_t[8][16];     // row 7: the head producer in detail ([0] next row + loads  [1] slot wait  [2] LUT + stores  [3] fence + arrive  [4] rows)
 #define MG_T(var) const long long var = clock64()
@@ -92,6 +93,9 @@ __device__ unsigned long long g_mega_t[8][16];     // row 7: the head producer i
 #else
 #define MG_T(var)
 #define MG_ACC(cond, L, i, v)
+#endif
+#ifdef MG_DBG_FINISH      // timing experiment: cycles every CTA took from entry to its last engine's last row (per-stage run time)
+__device__ long long g_mega_finish[160];
 #endif
 __device__ __forceinline__ unsigned int* mg_cons(unsigned int* fl, int ch, int consumer) {
   return fl + MG_NCH * MG_DMAX + (ch * 2 + consumer) * MG_SMAX;
@@ -128,9 +132,15 @@ __device__ __forceinline__ int mg_hi(const MSeg& g, int halo, int Hw) { return m
 // straight-line instructions that a handful of warps run through once per row -- they then wait for the instruction cache
 // more than for anything else (ncu: stall_no_inst).
 constexpr int MG_PRM_BYTES = (9 * MG_MAXC * 4 + 127) / 128 * 128;
-template <int LAYER, int PT_, int NPAD_, int COUT_, int KIND_, class EPI_, int RING_, int STAGES_, int NWG_, bool RM_ = true>
+template <int LAYER, int PT_, int NPAD_, int COUT_, int KIND_, class EPI_, int RING_, int STAGES_, int NWG_, bool RM_ = true, bool SPLIT_ = false>
 struct MEng {
   static constexpr bool RM = RM_;      // input-row-major MMA order (three accumulators open at a time) / block-major
+  // SPLIT: two warpgroups drain one output row together (the channel chunks are cut in two), so an accumulator stage is held
+  // for half as long.  With the row-major order only STAGES - 3 stages are being drained at a time: the row time of a layer
+  // with a long activation chain is (drain + hand-over) / (STAGES - 3), whatever the number of warpgroups.
+  static constexpr bool SPLIT = SPLIT_;
+  static constexpr int NG = SPLIT_ ? NWG_ / 2 : NWG_;      // row groups: output row n is drained by group n % NG
+  static constexpr int WPR = SPLIT_ ? 8 : 4;               // epilogue warps per output row
   using EPI = EPI_;
   static constexpr int L = LAYER, PT = PT_, NPAD = NPAD_, COUT = COUT_, KIND = KIND_, RING = RING_, STAGES = STAGES_, NWG = NWG_;
   static constexpr int HALO = 7 - LAYER;
@@ -150,18 +160,37 @@ struct MEng {
   static constexpr int OUT_PLANES = (COUT + 7) / 8;
   static constexpr int OUT_NCONS = LAYER == 1 ? 2 : 1;              // conv1's output is read by conv2 and conv6
   static_assert(STAGES >= NWG, "a warpgroup's previous block must be at least one use of the stage back (mbarrier parity waits)");
+  static_assert(!SPLIT_ || (NWG_ % 2 == 0 && KIND_ == EPI_STORE), "split drain: pairs of warpgroups, store epilogue");
   static_assert(!RM || STAGES >= 4, "row-major order: three open accumulators and at least one being drained");
   static_assert(RING >= 4 && RING <= 16, "ring depth (one relay lane per slot)");
   static_assert(NB % 8 == 0, "each CTA of the pair holds whole core matrices of B");
 };
 
+// The two issuers of a stage take the tensor pipe in turn, one input row at a time: interleaved instruction by instruction,
+// each engine's MMA evicts the other's A tile from the collector (fill / use / lastuse triples, see mg_issuer_rm) and every
+// instruction pays the full shared-memory operand read again.
+#ifndef MG_MMA_LOCK
+#define MG_MMA_LOCK 0xD     // bit i: stage i (A = 0 .. D = 3)
+#endif
 struct MEngSmem {      // shared-memory carve-up of one engine
   uint8_t* w;
   uint8_t* ring;
   const float* prm;      // [9][MG_MAXC]
   uint64_t *full, *empty, *pfull, *tfull, *tempty, *wbar;
   uint32_t* rowcnt;      // [MG_NR] epilogue warps that have stored their part of output row q (slot q % MG_NR, never reset)
+  uint32_t* mmalock;     // MG_MMA_LOCK: the stage's MMA-stream lock (nullptr in a stage with one engine)
 };
+__device__ __forceinline__ void mg_lock(uint32_t* l) {
+  if (!MG_MMA_LOCK || l == nullptr) return;
+  uint32_t old;
+  do {
+    asm volatile("atom.acquire.cta.shared::cta.cas.b32 %0, [%1], 0, 1;" : "=r"(old) : "r"(smem_u32(l)) : "memory");
+  } while (old != 0u);
+}
+__device__ __forceinline__ void mg_unlock(uint32_t* l) {
+  if (!MG_MMA_LOCK || l == nullptr) return;
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(l)), "r"(0u) : "memory");
+}
 constexpr int MG_NR = 8;   // counters of MG_NR row groups in flight: group g + MG_NR cannot reach its epilogue before group g has released its stages
 #ifndef MG_PUB_ROWS
 #define MG_PUB_ROWS 4      // rows per release of an engine's output (one fence for all of them)
@@ -171,6 +200,7 @@ __device__ __forceinline__ MEngSmem mg_carve(uint8_t* data, uint64_t* bars, uint
   static_assert(E::STAGES <= MG_NR, "row counters vs accumulator stages");
   MEngSmem s;
   s.rowcnt = rowcnt;
+  s.mmalock = nullptr;
   s.w = data;
   s.ring = data + E::WBYTES;
   s.prm = reinterpret_cast<const float*>(data + E::PRM_OFF);
@@ -185,8 +215,8 @@ __device__ __forceinline__ MEngSmem mg_carve(uint8_t* data, uint64_t* bars, uint
 template <class E>
 __device__ __forceinline__ void mg_init_bars(const MEngSmem& s) {     // one thread
   // a ring row is released by the MMA commit and, when the residual is read from it, by the 4 epilogue warps of its block
-  for (int i = 0; i < E::RING; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], E::EPI::kSkip ? 5 : 1); mbar_init(&s.pfull[i], 1); }
-  for (int i = 0; i < E::STAGES; ++i) { mbar_init(&s.tfull[i], 1); mbar_init(&s.tempty[i], 8); }      // 4 epilogue warps in each CTA of the pair
+  for (int i = 0; i < E::RING; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], E::EPI::kSkip ? 1 + E::WPR : 1); mbar_init(&s.pfull[i], 1); }
+  for (int i = 0; i < E::STAGES; ++i) { mbar_init(&s.tfull[i], 1); mbar_init(&s.tempty[i], 2 * E::WPR); }      // the row's epilogue warps in each CTA of the pair
   mbar_init(s.wbar, 1);
 }
 
@@ -201,6 +231,26 @@ struct MCtx {          // where this CTA sits
 // complete (`upto`, exclusive) so that one coalesced poll releases several rows.
 // A successful poll costs two fences (~1500 cycles) on the one warp that feeds the engine, so it asks for MG_POLL_BATCH rows
 // at a time (fewer at the end of the channel: `qtotal` rows in all).
+// Timing experiment (garbage results): bit ch set = nobody waits on channel ch, neither for its rows nor for its credits, so
+// the engines on either side run at their own pace (all bits: every engine free-running -> its stand-alone row time).
+#ifndef MG_DBG_CUT
+#define MG_DBG_CUT 0
+#endif
+// Acquire fence behind a successful back-pressure poll of a WRITER (epilogue warps, head).  What the poll guards is a
+// write-after-read: the slot about to be overwritten was read by the consumer's bulk copy, whose completion the consumer
+// observed on its mbarrier BEFORE it stored the credit this poll has just seen.  The overwriting stores depend on the polled
+// value through the loop exit and are not performed speculatively, so nothing is left for a fence to order -- and a
+// fence.acq_rel.gpu here first waits for all the warp's stores of the previous row to reach L2 (1000+ cycles per row, on the
+// epilogue's critical path: 38.9 -> 37.8 us/frame without it).  The READER side (mg_fence_after_poll) keeps its fences: there
+// later loads -- the bulk copies -- must not pass the poll.
+#ifndef MG_BP_FENCE
+#define MG_BP_FENCE 0
+#endif
+// 36-channel plain layer (conv5: ONE warpgroup drains every row, one accumulator stage beyond the three open ones): the whole
+// accumulator row goes to registers and the stage is released before bias / pack / store (38.9 -> 38.0 us/frame).
+#ifndef MG_EARLY_REL
+#define MG_EARLY_REL 1
+#endif
 #ifndef MG_POLL_ACQ
 #define MG_POLL_ACQ 1
 #endif
@@ -213,6 +263,7 @@ struct MCtx {          // where this CTA sits
 // Returns true when it polled (the caller then fences once for all its sources).
 __device__ __forceinline__ bool mg_wait_rows(const MegaK& M, const MCtx& c, int ch, uint32_t q, uint32_t qtotal, uint32_t& upto, int lane) {
   if (q < upto) return false;
+  if ((MG_DBG_CUT >> ch) & 1) { upto = qtotal; return false; }      // timing experiment: this link is cut
   const uint32_t want = min(q + (uint32_t)MG_POLL_BATCH, qtotal) - q;
   const uint32_t D = (uint32_t)mg_depth(ch), need_per_use = (uint32_t)M.S;          // every strip's publisher bumps the counter once per row
   const unsigned int* prod = mg_prod(c.flags, ch);
@@ -396,11 +447,12 @@ __device__ void mg_head_worker(const MegaK& M, const MCtx& c, const float* s_lut
   } else if (haveC) {
     haveN = next_row(fN, yN);
   }
+  MG_T(th_begin);
   while (haveC) {
     const bool haveP = haveN && next_row(fP, yP);
     MG_T(th0);
     // back-pressure: slot q % D still holds row q - D until conv1's producers of strips s-1, s, s+1 have loaded it
-    if (q >= D && cons_seen < q - D + 1u) {
+    if (!((MG_DBG_CUT >> CH) & 1) && q >= D && cons_seen < q - D + 1u) {
       const uint32_t need = q - D + 1u;
       const long long t0 = clock64();
       for (;;) {
@@ -410,7 +462,7 @@ __device__ void mg_head_worker(const MegaK& M, const MCtx& c, const float* s_lut
           if (sn >= 0 && sn < M.S) v = ld_relaxed_gpu(mg_cons(c.flags, CH, 0) + sn);
         }
         v = __reduce_min_sync(0xffffffffu, v);
-        if (v >= need) { cons_seen = v; fence_acq_rel_gpu(); break; }
+        if (v >= need) { cons_seen = v; if (MG_BP_FENCE) fence_acq_rel_gpu(); break; }
         if (clock64() - t0 > (1ll << 31)) __trap();
         __nanosleep(64);
       }
@@ -486,6 +538,8 @@ __device__ void mg_head_worker(const MegaK& M, const MCtx& c, const float* s_lut
     fN = fP; yN = yP; haveN = haveP;
     ++q;
   }
+  MG_T(th_end);
+  MG_ACC(tprobe, 8, 13, th_end - th_begin);
 }
 
 // ---- peer CTA of the pair: relay "my ring row has landed" to the leader (one lane per ring slot) -------------------------
@@ -553,6 +607,7 @@ __device__ void mg_issuer_rm(const MegaK& M, const MCtx& c, const MEngSmem& s, u
       const uint32_t s1 = sk >= 1u ? sk - 1u : sk + E::STAGES - 1u, s2 = sk >= 2u ? sk - 2u : sk + E::STAGES - 2u;
       const uint32_t d0 = tmem_cols + sk * E::NPAD, d1 = tmem_cols + s1 * E::NPAD, d2 = tmem_cols + s2 * E::NPAD;
       uint32_t a_lo = ring_lo + rs * (E::ROWBYTES >> 4), b_lo = w_lo, acc0 = 0;
+      mg_lock(s.mmalock);
       if (v0 && v1 && v2) {
         auto step3 = [&](uint32_t a, uint32_t b) {
           umma_bf16_coll<2, 1>(d2, hi | a, hi | (b + 2u * BROW), IDESC, 1u);
@@ -595,6 +650,7 @@ __device__ void mg_issuer_rm(const MegaK& M, const MCtx& c, const MEngSmem& s, u
       }
       umma_commit_2cta(&s.empty[rs]);                  // the MMAs are done with this input row (the pipe completes in issue order)
       if (v2) umma_commit_2cta(&s.tfull[s2]);          // output row k-2 is complete
+      mg_unlock(s.mmalock);
       MG_T(ti3);
       MG_ACC(c.probe, E::L, 1, ti1 - ti0); MG_ACC(c.probe, E::L, 2, ti2 - ti1); MG_ACC(c.probe, E::L, 3, ti3 - ti2); MG_ACC(c.probe && v2, E::L, 13, 1);
     }
@@ -639,9 +695,11 @@ __device__ void mg_issuer(const MegaK& M, const MCtx& c, const MEngSmem& s, uint
       mbar_wait(&s.tempty[stage], spar);
       tc_fence_after();
       MG_T(ti2);
+      mg_lock(s.mmalock);
       issue_block_2cta<E::PT, PLANE_ROW / 16, E::NB>(tmem_cols + stage * E::NPAD, ring_lo, E::ROWBYTES >> 4, s0, E::RING, w_lo, IDESC);
       umma_commit_2cta(&s.tfull[stage]);
       umma_commit_2cta(&s.empty[s0]);
+      mg_unlock(s.mmalock);
       if (b == rows - 1) {
         const uint32_t s1 = s0 + 1 == E::RING ? 0 : s0 + 1, s2 = s1 + 1 == E::RING ? 0 : s1 + 1;
         umma_commit_2cta(&s.empty[s1]);
@@ -730,7 +788,7 @@ __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, ui
     const int f = min(2 * g.fp + c.rank, M.n_frames - 1);
     const int lo = mg_lo(g, E::HALO), rows = mg_hi(g, E::HALO, M.Hw) - lo;
     for (int b = 0; b < rows; ++b, ++blk) {
-      if ((int)(blk % E::NWG) != wg) continue;
+      if ((int)(blk % E::NG) != (E::SPLIT ? wg >> 1 : wg)) continue;
       const uint32_t stage = blk % E::STAGES, spar = (blk / E::STAGES) & 1u;
       const int y = lo + b;
       const uint32_t q = qout + (uint32_t)b;     // sequence number of this output row in my channel
@@ -763,7 +821,7 @@ __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, ui
       } else {
         // back-pressure: slot q % D still holds row q - D until every consumer strip that reads my columns (s-1, s, s+1)
         // has loaded it.  Checked before the accumulator wait, so the poll hides behind the MMAs.
-        if (q >= (uint32_t)D && cons_seen < q - (uint32_t)D + 1u) {
+        if (!((MG_DBG_CUT >> (E::OUT >= 0 ? E::OUT : 0)) & 1) && q >= (uint32_t)D && cons_seen < q - (uint32_t)D + 1u) {
           const uint32_t need = q - (uint32_t)D + 1u;
           const long long t0 = clock64();
           for (;;) {
@@ -773,7 +831,7 @@ __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, ui
               if (sn >= 0 && sn < M.S) v = ld_relaxed_gpu(mg_cons(c.flags, E::OUT >= 0 ? E::OUT : 0, k) + sn);
             }
             v = __reduce_min_sync(0xffffffffu, v);
-            if (v >= need) { cons_seen = v; fence_acq_rel_gpu(); break; }
+            if (v >= need) { cons_seen = v; if (MG_BP_FENCE) fence_acq_rel_gpu(); break; }
             if (clock64() - t0 > (1ll << 31)) __trap();
             __nanosleep(64);
           }
@@ -797,21 +855,52 @@ __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, ui
         if constexpr (kPlain) {
           constexpr int NC = E::OUT_PLANES, NLAST = E::COUT - 8 * (NC - 1);
           static_assert(NC == 5 || NC == 9, "plain layers of the flagship: 36 or 72 channels");
+          if constexpr (NC == 5 && MG_EARLY_REL) {
+            // one WG drains every row of this engine and only one accumulator stage is not open: hold it for the read-back only
+            uint32_t v[40];
+            tmem_ld_cols<40>(taddr, v);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&s.tempty[stage], 0);
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+              const float4 b0 = *reinterpret_cast<const float4*>(s.prm + j * 8), b1 = *reinterpret_cast<const float4*>(s.prm + j * 8 + 4);
+              float o[8];
+              o[0] = __uint_as_float(v[j * 8 + 0]) + b0.x; o[1] = __uint_as_float(v[j * 8 + 1]) + b0.y; o[2] = __uint_as_float(v[j * 8 + 2]) + b0.z;
+              o[3] = __uint_as_float(v[j * 8 + 3]) + b0.w; o[4] = __uint_as_float(v[j * 8 + 4]) + b1.x; o[5] = __uint_as_float(v[j * 8 + 5]) + b1.y;
+              o[6] = __uint_as_float(v[j * 8 + 6]) + b1.z; o[7] = __uint_as_float(v[j * 8 + 7]) + b1.w;
+              if (j == 4) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = i < NLAST ? o[i] : 0.f;
+              }
+              if (valid)
+                *reinterpret_cast<uint4*>(dp + (size_t)j * plane_pitch) =
+                    make_uint4(pack_op2(o[0], o[1]), pack_op2(o[2], o[3]), pack_op2(o[4], o[5]), pack_op2(o[6], o[7]));
+            }
+          } else {
           mg_ident_group<4>(taddr, s.prm, dp, plane_pitch, valid, 8);
           if constexpr (NC == 9) mg_ident_group<4>(taddr + 32, s.prm + 32, dp + 4 * plane_pitch, plane_pitch, valid, 8);
           mg_ident_group<1>(taddr + (NC - 1) * 8, s.prm + (NC - 1) * 8, dp + (size_t)(NC - 1) * plane_pitch, plane_pitch, valid, NLAST);
+          }
         } else {
         // the accumulator chunk of the NEXT iteration is already on its way while this one goes through the activations
         // (a tcgen05.ld takes several hundred cycles while the MMAs keep the tensor memory busy)
+        // split drain: the two warpgroups of a row take 4 and 5 (of 9) chunks, in turn
+        int c0 = 0, c1 = E::OUT_PLANES;
+        if constexpr (E::SPLIT) {
+          const int cut = E::OUT_PLANES / 2 + (int)((blk / E::NG) & 1u);
+          if (wg & 1) c0 = cut; else c1 = cut;
+        }
         uint32_t vn[8];
-        tmem_ld_x8(taddr, vn);
+        tmem_ld_x8(taddr + c0 * 8, vn);
 #pragma unroll 1
-        for (int cc = 0; cc < E::OUT_PLANES; ++cc) {
+        for (int cc = c0; cc < c1; ++cc) {
           tmem_ld_wait();
           uint32_t v[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = vn[i];
-          if (cc + 1 < E::OUT_PLANES) tmem_ld_x8(taddr + (cc + 1) * 8, vn);
+          if (cc + 1 < c1) tmem_ld_x8(taddr + (cc + 1) * 8, vn);
           const float* prm = s.prm + cc * 8;
           const float4 b0 = *reinterpret_cast<const float4*>(prm), b1 = *reinterpret_cast<const float4*>(prm + 4);
           uint4 skc = make_uint4(0, 0, 0, 0);
@@ -859,7 +948,7 @@ __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, ui
           const uint32_t nrows = min((uint32_t)MG_PUB_ROWS, qtotal - q_lo);           // the channel's last group may be short
           const uint32_t before = atom_acq_rel_cta_smem_add(s.rowcnt + grp % (uint32_t)MG_NR, 1u);
           MG_T(tf1);
-          if ((before + 1u) % (4u * (uint32_t)MG_PUB_ROWS) == (4u * nrows) % (4u * (uint32_t)MG_PUB_ROWS)) {
+          if ((before + 1u) % ((uint32_t)E::WPR * (uint32_t)MG_PUB_ROWS) == ((uint32_t)E::WPR * nrows) % ((uint32_t)E::WPR * (uint32_t)MG_PUB_ROWS)) {
             fence_acq_rel_gpu();
             for (uint32_t qq = q_lo; qq < q_lo + nrows; ++qq) red_relaxed_gpu_add(prod + qq % (uint32_t)D, 1u);
           }
@@ -917,9 +1006,12 @@ __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, ui
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(&s.tempty[stage], 0);
+      constexpr bool kReleased = E::KIND == EPI_STORE && kPlain && E::OUT_PLANES == 5 && MG_EARLY_REL;
+      if constexpr (!kReleased) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&s.tempty[stage], 0);
+      }
       MG_T(te3);
       MG_ACC(tprobe, E::L, 7, te1 - te0); MG_ACC(tprobe, E::L, 8, te2 - te1); MG_ACC(tprobe, E::L, 9, te3 - te2); MG_ACC(tprobe, E::L, 11, 1);
     }
@@ -944,25 +1036,29 @@ __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, ui
 using MgConv1 = MEng<1, 2, 48, 36, EPI_STORE, Epi<MG_A(SINLU), MG_A(RELU6), 0, 0, false>, 8, 4, 2, false>;
 using MgConv2 = MEng<2, 5, 48, 36, EPI_STORE, Epi<MG_A(TELU), 0, MG_A(SINLU), MG_A(BIASED_PRELU), true>, 6, 6, 3>;
 using MgConv3 = MEng<3, 5, 80, 72, EPI_STORE, Epi<0, 0, 0, 0, false>, 8, 5, 2>;
-using MgConv4 = MEng<4, 9, 80, 72, EPI_STORE, Epi<MG_A(MISH), MG_A(BIASED_PRELU), MG_A(TANH), MG_A(RELU), true>, 9, 6, 4>;
+#ifndef MG_SPLIT4
+#define MG_SPLIT4 0      // measured: 38.2 vs 37.4 us/frame -- conv4 is bound by its 16 warps' issue slots and the SFU, not by how long a stage is held
+#endif
+using MgConv4 = MEng<4, 9, 80, 72, EPI_STORE, Epi<MG_A(MISH), MG_A(BIASED_PRELU), MG_A(TANH), MG_A(RELU), true>, 9, 6, 4, true, MG_SPLIT4 != 0>;
 using MgConv5 = MEng<5, 9, 48, 36, EPI_STORE, Epi<0, 0, 0, 0, false>, 5, 4, 1>;
 using MgConv6 = MEng<6, 10, 48, 36, EPI_STORE, Epi<MG_A(MISH), MG_A(RELU6), 0, 0, false>, 6, 6, 2>;
 using MgConv7 = MEng<7, 5, 16, 12, EPI_TAIL_SHUFFLE, Epi<MG_A(BIASED_PRELU), 0, 0, 0, false>, 6, 6, 2>;
 #undef MG_A
 struct MgNone { static constexpr int SMEM = 0, TCOLS = 0, NBARS = 0, NWG = 0, L = 1; };
 
-template <class E0, class E1>
+template <class E0, class E1, int IDX_>
 struct MStage {
+  static constexpr int IDX = IDX_;
   static constexpr bool kTwo = E1::NWG > 0;
   static constexpr int SMEM = E0::SMEM + E1::SMEM;
   static_assert(E0::NWG + E1::NWG == 4, "16 epilogue warps per CTA");
   static_assert(E0::TCOLS + E1::TCOLS <= 512, "TMEM columns");
   static_assert((E0::SMEM % 128) == 0, "operand alignment of the second engine");
 };
-using MgStageA = MStage<MgConv5, MgConv2>;
-using MgStageB = MStage<MgConv4, MgNone>;
-using MgStageC = MStage<MgConv3, MgConv7>;
-using MgStageD = MStage<MgConv6, MgConv1>;
+using MgStageA = MStage<MgConv5, MgConv2, 0>;
+using MgStageB = MStage<MgConv4, MgNone, 1>;
+using MgStageC = MStage<MgConv3, MgConv7, 2>;
+using MgStageD = MStage<MgConv6, MgConv1, 3>;
 constexpr int mg_max(int a, int b) { return a > b ? a : b; }
 constexpr int MG_BAR_BYTES = 1152;       // 120 barriers, the TMEM slot, 2 x MG_NR row counters
 constexpr int MG_SMEM = mg_max(mg_max(MgStageA::SMEM, MgStageB::SMEM), mg_max(MgStageC::SMEM, MgStageD::SMEM)) + MG_BAR_BYTES;
@@ -982,12 +1078,23 @@ __device__ __forceinline__ void mg_run_service(const MegaK& M, const MCtx& c, co
 
 template <class ST, class E0, class E1>
 __device__ __forceinline__ void mg_run_stage(const MegaK& M, MCtx& c, uint8_t* smem, float* s_lut, uint4* s_raw, int warp, int lane) {
+#ifdef MG_DBG_FINISH
+  const long long t_start = clock64();
+#endif
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MG_SMEM - MG_BAR_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 120);
   uint32_t* rowcnt = reinterpret_cast<uint32_t*>(bars + 128);
-  const MEngSmem s0 = mg_carve<E0>(smem, bars, rowcnt);
-  MEngSmem s1 = s0;
+  const MEngSmem s0c = mg_carve<E0>(smem, bars, rowcnt);
+  MEngSmem s1 = s0c;
+  MEngSmem s0m = s0c;
   if constexpr (ST::kTwo) s1 = mg_carve<E1>(smem + E0::SMEM, bars + E0::NBARS, rowcnt + MG_NR);
+  if constexpr (ST::kTwo && ((MG_MMA_LOCK >> ST::IDX) & 1) != 0) {
+    uint32_t* lock = reinterpret_cast<uint32_t*>(bars + 140);
+    if (threadIdx.x == 0) *lock = 0u;
+    s0m.mmalock = lock;
+    s1.mmalock = lock;
+  }
+  const MEngSmem s0 = s0m;
   if (threadIdx.x < 2 * MG_NR) rowcnt[threadIdx.x] = 0u;
   for (int i = threadIdx.x; i < 9 * MG_MAXC; i += MG_THREADS) {     // MegaLayerP starts with bias[MG_MAXC], p0[4][MG_MAXC], p1[4][MG_MAXC]
     const_cast<float*>(s0.prm)[i] = reinterpret_cast<const float*>(&M.L[E0::L - 1])[i];
@@ -1027,6 +1134,9 @@ __device__ __forceinline__ void mg_run_stage(const MegaK& M, MCtx& c, uint8_t* s
   }
   tc_fence_before();
   __syncthreads();
+#ifdef MG_DBG_FINISH
+  if (threadIdx.x == 0) g_mega_finish[blockIdx.x] = clock64() - t_start;
+#endif
   cluster_sync_all();
   if (warp == 1) tmem_dealloc_2cta(tmem_base, 512);
 }
@@ -1064,6 +1174,13 @@ extern "C" __attribute__((visibility("default"))) int fsuae_debug_mega_timing(un
   if (cudaMemcpyFromSymbol(out, g_mega_t, sizeof(g_mega_t)) != cudaSuccess) return -1;
   if (reset) { static unsigned long long z[8 * 16]; cudaMemcpyToSymbol(g_mega_t, z, sizeof(z)); }
   return 0;
+}
+#endif
+
+#if defined(MG_DBG_FINISH) && !defined(FSUAE_OPERAND_FP16)
+extern "C" __attribute__((visibility("default"))) int fsuae_debug_mega_finish(long long* out) {   // [160] cycles per CTA of the last pass
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out, g_mega_finish, sizeof(g_mega_finish)) == cudaSuccess ? 0 : -1;
 }
 #endif
 

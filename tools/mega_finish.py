@@ -1,0 +1,32 @@
+#!/usr/bin/env python3
+"""Debug aid: cycles every CTA of the single fused pass took (entry -> its last engine's last row), by stage.
+
+Needs a library built with FSUAE_EXTRA_NVCC_FLAGS=-DMG_DBG_FINISH (point FSUAE_LIB_PATH at it); with -DMG_DBG_CUT=0x7F on top
+the engines run free of each other and the figures are each stage's stand-alone run time.
+
+    python tools/mega_finish.py [frames]
+"""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from fs_uae_image_enhancer_project_b200 import _lib, model_pix_shuffle  # noqa: E402
+
+dev = torch.device("cuda", 0)
+b = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+m = model_pix_shuffle.get_model("lightweight").to(dev).set_precision("bf16")
+m.chunk_frames = b
+x = (torch.randint(0, 16, (b, 576, 752, 4), dtype=torch.uint8) * 17).to(dev)
+for _ in range(3):
+    m.forward_framebuffer(x)
+lib = _lib.load()
+out = (C.c_longlong * 160)()
+lib.fsuae_debug_mega_finish(out)
+rows = 288 * ((b + 1) // 2) / 6
+names = ["A conv5+conv2", "B conv4+head", "C conv3+conv7", "D conv6+conv1"]
+for st in range(4):
+    v = [out[blk] for blk in range(144) if (blk >> 1) & 3 == st]
+    print(f"stage {names[st]}: cycles per row min {min(v) / rows:7.0f}  mean {sum(v) / len(v) / rows:7.0f}  max {max(v) / rows:7.0f}")

@@ -48,4 +48,5 @@ h = [out[7 * 16 + i] for i in range(16)]
 hr = max(h[4], 1)
 print("producer credit step (wait for the copy of fill - 2), cycles per row: " + "  ".join(f"conv{l + 1} {h[5 + l] / max(out[l * 16 + 12], 1):.0f}" for l in range(7)))
 print(f"conv4 issuer: waits for the peer's relay {h[12] / max(out[3 * 16 + 13], 1):.0f} cycles per row")
+print(f"head worker 0 (stage B): {h[4]} rows, {h[13] / hr:.0f} cycles per row in all")
 print(f"head worker 0 (stage B) per row: back-pressure {h[1] / hr:.0f}  wait + LUT + stores {h[2] / hr:.0f}  barrier + release {h[3] / hr:.0f}  prefetch {h[0] / hr:.0f}")
