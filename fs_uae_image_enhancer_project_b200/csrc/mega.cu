@@ -166,6 +166,25 @@ struct MEng {
   static_assert(NB % 8 == 0, "each CTA of the pair holds whole core matrices of B");
 };
 
+// Phase of a layer's publish groups.  Output rows are released MG_PUB_ROWS at a time, and layer L + 1 needs layer L's rows up
+// to y + 1 to finish its own row y: with every layer's groups ending on the same rows ([0..3], [4..7], ...) layer L + 1 can
+// finish row 3 -- and release ITS first group -- only after layer L's SECOND group, so every hop of the pipeline lags a whole
+// group (4 rows = 5 us) behind the one before, at the start of a pass and again at its end.  Layer L's groups therefore end
+// `step` rows earlier than layer L - 1's ([0..3], [0..2] [3..6], [0..1] [2..5], ...): step = 1 when the team's range starts at
+// the top of a frame (sequence number q = image row y in every layer), 2 when it starts inside one (layer L - 1 has one halo
+// row more in front, so its q runs one ahead).  Any phase is correct; this one takes ~35 us out of every pass.
+#ifndef MG_PUB_ROWS
+#define MG_PUB_ROWS 4      // rows per release of an engine's output (one fence for all of them)
+#endif
+#ifndef MG_PUB_PHASE
+#define MG_PUB_PHASE 1
+#endif
+__device__ __forceinline__ uint32_t mg_pub_phase(const MegaK& M, int team, int layer) {
+  if (!MG_PUB_PHASE) return 0u;
+  const long long first = (long long)M.n_fp * M.Hw * team / M.teams;      // first row of the team's range (see MSegIter)
+  const uint32_t step = (first % M.Hw) != 0 ? 2u : 1u;
+  return ((uint32_t)layer * step) % (uint32_t)MG_PUB_ROWS;
+}
 // The two issuers of a stage take the tensor pipe in turn, one input row at a time: interleaved instruction by instruction,
 // each engine's MMA evicts the other's A tile from the collector (fill / use / lastuse triples, see mg_issuer_rm) and every
 // instruction pays the full shared-memory operand read again.
@@ -179,6 +198,7 @@ struct MEngSmem {      // shared-memory carve-up of one engine
   uint64_t *full, *empty, *pfull, *tfull, *tempty, *wbar;
   uint32_t* rowcnt;      // [MG_NR] epilogue warps that have stored their part of output row q (slot q % MG_NR, never reset)
   uint32_t* mmalock;     // MG_MMA_LOCK: the stage's MMA-stream lock (nullptr in a stage with one engine)
+  uint32_t ph;           // phase of this engine's publish groups (see mg_pub_phase)
 };
 __device__ __forceinline__ void mg_lock(uint32_t* l) {
   if (!MG_MMA_LOCK || l == nullptr) return;
@@ -192,15 +212,13 @@ __device__ __forceinline__ void mg_unlock(uint32_t* l) {
   asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(l)), "r"(0u) : "memory");
 }
 constexpr int MG_NR = 8;   // counters of MG_NR row groups in flight: group g + MG_NR cannot reach its epilogue before group g has released its stages
-#ifndef MG_PUB_ROWS
-#define MG_PUB_ROWS 4      // rows per release of an engine's output (one fence for all of them)
-#endif
 template <class E>
 __device__ __forceinline__ MEngSmem mg_carve(uint8_t* data, uint64_t* bars, uint32_t* rowcnt) {
   static_assert(E::STAGES <= MG_NR, "row counters vs accumulator stages");
   MEngSmem s;
   s.rowcnt = rowcnt;
   s.mmalock = nullptr;
+  s.ph = 0u;
   s.w = data;
   s.ring = data + E::WBYTES;
   s.prm = reinterpret_cast<const float*>(data + E::PRM_OFF);
@@ -884,28 +902,24 @@ __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, ui
           mg_ident_group<1>(taddr + (NC - 1) * 8, s.prm + (NC - 1) * 8, dp + (size_t)(NC - 1) * plane_pitch, plane_pitch, valid, NLAST);
           }
         } else {
-        // the accumulator chunk of the NEXT iteration is already on its way while this one goes through the activations
-        // (a tcgen05.ld takes several hundred cycles while the MMAs keep the tensor memory busy)
         // split drain: the two warpgroups of a row take 4 and 5 (of 9) chunks, in turn
         int c0 = 0, c1 = E::OUT_PLANES;
         if constexpr (E::SPLIT) {
           const int cut = E::OUT_PLANES / 2 + (int)((blk / E::NG) & 1u);
           if (wg & 1) c0 = cut; else c1 = cut;
         }
-        uint32_t vn[8];
-        tmem_ld_x8(taddr + c0 * 8, vn);
-#pragma unroll 1
-        for (int cc = c0; cc < c1; ++cc) {
-          tmem_ld_wait();
-          uint32_t v[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = vn[i];
-          if (cc + 1 < c1) tmem_ld_x8(taddr + (cc + 1) * 8, vn);
-          const float* prm = s.prm + cc * 8;
+        // Two chunks per trip, their accumulators in two register sets (the next read-back is issued before this chunk's math:
+        // a tcgen05.ld takes several hundred cycles while the MMAs keep the tensor memory busy); pointers advance by
+        // increments.  The one-chunk loop spent 27 % of its 171 instructions on register moves and 64-bit address products.
+        const float* prm = s.prm + c0 * 8;
+        const uint8_t* spc = sp + c0 * PLANE_ROW;
+        unsigned char* dpc = dp + (size_t)c0 * plane_pitch;
+        uint32_t tc = taddr + c0 * 8;
+        auto chunk = [&](const uint32_t (&v)[8], int cc) {
           const float4 b0 = *reinterpret_cast<const float4*>(prm), b1 = *reinterpret_cast<const float4*>(prm + 4);
           uint4 skc = make_uint4(0, 0, 0, 0);
           if constexpr (EPI::kSkip) {
-            if (valid) skc = *reinterpret_cast<const uint4*>(sp + cc * PLANE_ROW);
+            if (valid) skc = *reinterpret_cast<const uint4*>(spc);
           }
           float o[8];
           o[0] = __uint_as_float(v[0]) + b0.x; o[1] = __uint_as_float(v[1]) + b0.y; o[2] = __uint_as_float(v[2]) + b0.z;
@@ -933,8 +947,24 @@ __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, ui
             }
           }
           if (valid)
-            *reinterpret_cast<uint4*>(dp + (size_t)cc * plane_pitch) =
-                make_uint4(pack_op2(o[0], o[1]), pack_op2(o[2], o[3]), pack_op2(o[4], o[5]), pack_op2(o[6], o[7]));
+            *reinterpret_cast<uint4*>(dpc) = make_uint4(pack_op2(o[0], o[1]), pack_op2(o[2], o[3]), pack_op2(o[4], o[5]), pack_op2(o[6], o[7]));
+          prm += 8;
+          spc += PLANE_ROW;
+          dpc += plane_pitch;
+        };
+        uint32_t va[8], vb[8];
+        tmem_ld_x8(tc, va);
+#pragma unroll 1
+        for (int cc = c0; cc < c1; cc += 2) {
+          tmem_ld_wait();
+          if (cc + 1 < c1) tmem_ld_x8(tc + 8, vb);
+          chunk(va, cc);
+          if (cc + 1 < c1) {
+            tmem_ld_wait();
+            if (cc + 2 < c1) tmem_ld_x8(tc + 16, va);
+            chunk(vb, cc + 1);
+          }
+          tc += 16;
         }
         }
         // Rows are published in groups of MG_PUB_ROWS: the last warp to finish the group (4 warps per row, whichever
@@ -944,13 +974,17 @@ __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, ui
         MG_T(tf0);
         __syncwarp();
         if (lane == 0) {
-          const uint32_t grp = q / (uint32_t)MG_PUB_ROWS, q_lo = grp * (uint32_t)MG_PUB_ROWS;
-          const uint32_t nrows = min((uint32_t)MG_PUB_ROWS, qtotal - q_lo);           // the channel's last group may be short
+          // group g = rows [g * MG_PUB_ROWS - ph, (g + 1) * MG_PUB_ROWS - ph): the first ph rows of group 0 do not exist (their
+          // arrivals are preloaded into the counter), the channel's last group may be short
+          const uint32_t grp = (q + s.ph) / (uint32_t)MG_PUB_ROWS;
+          const int q_lo_s = (int)(grp * (uint32_t)MG_PUB_ROWS) - (int)s.ph;
+          const uint32_t q_lo = (uint32_t)max(q_lo_s, 0), q_hi = min((uint32_t)(q_lo_s + MG_PUB_ROWS), qtotal);
+          const uint32_t nrows = (uint32_t)((int)q_hi - q_lo_s);
           const uint32_t before = atom_acq_rel_cta_smem_add(s.rowcnt + grp % (uint32_t)MG_NR, 1u);
           MG_T(tf1);
           if ((before + 1u) % ((uint32_t)E::WPR * (uint32_t)MG_PUB_ROWS) == ((uint32_t)E::WPR * nrows) % ((uint32_t)E::WPR * (uint32_t)MG_PUB_ROWS)) {
             fence_acq_rel_gpu();
-            for (uint32_t qq = q_lo; qq < q_lo + nrows; ++qq) red_relaxed_gpu_add(prod + qq % (uint32_t)D, 1u);
+            for (uint32_t qq = q_lo; qq < q_hi; ++qq) red_relaxed_gpu_add(prod + qq % (uint32_t)D, 1u);
           }
           MG_T(tf2);
           MG_ACC(tprobe, E::L, 14, tf1 - tf0); MG_ACC(tprobe, E::L, 15, tf2 - tf1);
@@ -1035,7 +1069,15 @@ __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, ui
 //   conv6 (45 MMAs, Mish)                             + conv1 (9 MMAs, SinLU)
 using MgConv1 = MEng<1, 2, 48, 36, EPI_STORE, Epi<MG_A(SINLU), MG_A(RELU6), 0, 0, false>, 8, 4, 2, false>;
 using MgConv2 = MEng<2, 5, 48, 36, EPI_STORE, Epi<MG_A(TELU), 0, MG_A(SINLU), MG_A(BIASED_PRELU), true>, 6, 6, 3>;
-using MgConv3 = MEng<3, 5, 80, 72, EPI_STORE, Epi<0, 0, 0, 0, false>, 8, 5, 2>;
+// Which stage hosts the head (1 = B, on the service warps conv4 has no second engine for; 2 = C, on two warps of a warpgroup
+// conv3 gives up).  Stage B is the slowest stage on its own (tools/mega_finish.py, free-running engines: A 2190, B 2640,
+// C 1820, D 2460 cycles per row) -- conv4's activation chain keeps its 16 epilogue warps' issue slots and the SFU busy, and
+// the head's ~1000 warp instructions per row come on top -- while stage C has the most slack: conv3 is a plain layer that one
+// warpgroup drains in ~1500 cycles per row.
+#ifndef MG_HEAD_STAGE
+#define MG_HEAD_STAGE 1
+#endif
+using MgConv3 = MEng<3, 5, 80, 72, EPI_STORE, Epi<0, 0, 0, 0, false>, 8, 5, MG_HEAD_STAGE == 2 ? 1 : 2>;
 #ifndef MG_SPLIT4
 #define MG_SPLIT4 0      // measured: 38.2 vs 37.4 us/frame -- conv4 is bound by its 16 warps' issue slots and the SFU, not by how long a stage is held
 #endif
@@ -1044,14 +1086,15 @@ using MgConv5 = MEng<5, 9, 48, 36, EPI_STORE, Epi<0, 0, 0, 0, false>, 5, 4, 1>;
 using MgConv6 = MEng<6, 10, 48, 36, EPI_STORE, Epi<MG_A(MISH), MG_A(RELU6), 0, 0, false>, 6, 6, 2>;
 using MgConv7 = MEng<7, 5, 16, 12, EPI_TAIL_SHUFFLE, Epi<MG_A(BIASED_PRELU), 0, 0, 0, false>, 6, 6, 2>;
 #undef MG_A
-struct MgNone { static constexpr int SMEM = 0, TCOLS = 0, NBARS = 0, NWG = 0, L = 1; };
+struct MgNone { static constexpr int SMEM = 0, TCOLS = 0, NBARS = 0, NWG = 0, L = 1, WPR = 0; };
 
 template <class E0, class E1, int IDX_>
 struct MStage {
   static constexpr int IDX = IDX_;
   static constexpr bool kTwo = E1::NWG > 0;
+  static constexpr bool kHead = IDX_ == MG_HEAD_STAGE;       // this stage hosts the head
   static constexpr int SMEM = E0::SMEM + E1::SMEM;
-  static_assert(E0::NWG + E1::NWG == 4, "16 epilogue warps per CTA");
+  static_assert(E0::NWG + E1::NWG == (kHead && kTwo ? 3 : 4), "16 epilogue warps per CTA (a stage with two engines and the head: 12 + the head's two)");
   static_assert(E0::TCOLS + E1::TCOLS <= 512, "TMEM columns");
   static_assert((E0::SMEM % 128) == 0, "operand alignment of the second engine");
 };
@@ -1094,8 +1137,11 @@ __device__ __forceinline__ void mg_run_stage(const MegaK& M, MCtx& c, uint8_t* s
     s0m.mmalock = lock;
     s1.mmalock = lock;
   }
+  s0m.ph = mg_pub_phase(M, c.team, E0::L);
+  if constexpr (ST::kTwo) s1.ph = mg_pub_phase(M, c.team, E1::L);
   const MEngSmem s0 = s0m;
-  if (threadIdx.x < 2 * MG_NR) rowcnt[threadIdx.x] = 0u;
+  if (threadIdx.x < 2 * MG_NR)      // slot 0 starts with the arrivals of group 0's rows that do not exist
+    rowcnt[threadIdx.x] = threadIdx.x == 0 ? (uint32_t)E0::WPR * s0.ph : (ST::kTwo && threadIdx.x == MG_NR ? (uint32_t)E1::WPR * s1.ph : 0u);
   for (int i = threadIdx.x; i < 9 * MG_MAXC; i += MG_THREADS) {     // MegaLayerP starts with bias[MG_MAXC], p0[4][MG_MAXC], p1[4][MG_MAXC]
     const_cast<float*>(s0.prm)[i] = reinterpret_cast<const float*>(&M.L[E0::L - 1])[i];
     if constexpr (ST::kTwo) const_cast<float*>(s1.prm)[i] = reinterpret_cast<const float*>(&M.L[E1::L - 1])[i];
@@ -1126,11 +1172,18 @@ __device__ __forceinline__ void mg_run_stage(const MegaK& M, MCtx& c, uint8_t* s
     mg_run_service<E0>(M, c, s0, tmem_base, warp, lane);
   } else if (warp < 4) {
     if constexpr (ST::kTwo) mg_run_service<E1>(M, c, s1, tmem_base + E0::TCOLS, warp - 2, lane);
-    else mg_head_worker(M, c, s_lut, s_raw, warp - 2, lane);      // the stage without a second engine hosts the head
+    else if constexpr (ST::kHead) mg_head_worker(M, c, s_lut, s_raw, warp - 2, lane);      // no second engine: the head takes its service warps
   } else {
     const int wg = (warp - 4) >> 2;
-    if (wg < E0::NWG) mg_epilogue<E0>(M, c, s0, tmem_base, s_lut, wg, warp, lane);
-    else if constexpr (ST::kTwo) mg_epilogue<E1>(M, c, s1, tmem_base + E0::TCOLS, s_lut, wg - E0::NWG, warp, lane);
+    if (wg < E0::NWG) {
+      mg_epilogue<E0>(M, c, s0, tmem_base, s_lut, wg, warp, lane);
+    } else if constexpr (ST::kTwo) {
+      if (wg < E0::NWG + E1::NWG) mg_epilogue<E1>(M, c, s1, tmem_base + E0::TCOLS, s_lut, wg - E0::NWG, warp, lane);
+      else if constexpr (ST::kHead) {           // two warps of the warpgroup the engines leave free
+        const int hw = warp - 4 - 4 * (E0::NWG + E1::NWG);
+        if (hw < 2) mg_head_worker(M, c, s_lut, s_raw, hw, lane);
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();

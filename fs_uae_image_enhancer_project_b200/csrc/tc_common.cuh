@@ -61,6 +61,9 @@ __device__ __forceinline__ float rcp_fast(float x) {
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(tanh_fast(0.5f * x), 0.5f, 0.5f); }
 
+// Products that end an activation are __fmul_rn: a plain `*` may be contracted with the residual add or the next slot's
+// subtraction into one FFMA, or not, depending on the surrounding code -- the layer kernels and the fused pass must agree bit
+// for bit, and an unfused product is also what the reference computes.
 __device__ __forceinline__ float act_rt(int op, float x, float p0, float p1) {
   switch (op) {
     case FSUAE_ACT_IDENTITY: return x;
@@ -68,23 +71,23 @@ __device__ __forceinline__ float act_rt(int op, float x, float p0, float p1) {
     case FSUAE_ACT_RELU6: return fminf(fmaxf(x, 0.f), 6.f);
     case FSUAE_ACT_TANH: return tanh_fast(x);
     case FSUAE_ACT_SIGMOID: return sigmoid_fast(x);
-    case FSUAE_ACT_SILU: return x * sigmoid_fast(x);
+    case FSUAE_ACT_SILU: return __fmul_rn(x, sigmoid_fast(x));
     case FSUAE_ACT_MISH: {   // x * tanh(softplus(x)) = x * w / (w + 2) = x - 2x / (w + 2), w = e^x (e^x + 2)
       float n = __expf(x);                     // overflow is benign: d = inf -> 1/d = 0 -> x
       float d = fmaf(n, n + 2.f, 2.f);         // w + 2
       return fmaf(x * rcp_fast(d), -2.f, x);
     }
-    case FSUAE_ACT_GELU: return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
-    case FSUAE_ACT_ELU: return x > 0.f ? x : p0 * (__expf(x) - 1.f);
+    case FSUAE_ACT_GELU: return __fmul_rn(0.5f * x, 1.f + erff(x * 0.70710678118654752440f));
+    case FSUAE_ACT_ELU: return x > 0.f ? x : __fmul_rn(p0, __expf(x) - 1.f);
     case FSUAE_ACT_SOFTPLUS: {
       float bx = x * p0;
       return bx > p1 ? x : __fdividef(__logf(1.f + __expf(bx)), p0);
     }
-    case FSUAE_ACT_LEAKY_RELU: return x >= 0.f ? x : p0 * x;
+    case FSUAE_ACT_LEAKY_RELU: return x >= 0.f ? x : __fmul_rn(p0, x);
     case FSUAE_ACT_PRELU: return fmaf(p0 - 1.f, fminf(x, 0.f), x);     // x + (slope - 1) * min(x, 0)
     case FSUAE_ACT_SCALED_TANH: return fmaf(tanh_fast(x), 0.5f, 0.5f);
-    case FSUAE_ACT_TELU: return x * tanh_fast(__expf(x));
-    case FSUAE_ACT_SINLU: return sigmoid_fast(x) * fmaf(p0, __sinf(p1 * x), x);
+    case FSUAE_ACT_TELU: return __fmul_rn(x, tanh_fast(__expf(x)));
+    case FSUAE_ACT_SINLU: return __fmul_rn(sigmoid_fast(x), fmaf(p0, __sinf(p1 * x), x));
     case FSUAE_ACT_BIASED_RELU: return fmaxf(x - p0, 0.f);
     case FSUAE_ACT_BIASED_PRELU: {   // p1 holds (slope - 1), prepared on the host: y + (slope - 1) * min(y, 0)
       float y = x - p0;
