@@ -328,12 +328,16 @@ def main():
     barrier()
     # (b) the streaming form of the same call: every step is submitted (upload + forward + download of its 64 host
     # frames), consecutive steps overlap, one wait at the end -- all copies of all steps are inside the timed region
+    sampler_e2e = ClockSampler(local)        # the legs before this one have warmed the GPU up: is the SM clock still at its maximum?
+    if rank == 0:
+        sampler_e2e.start()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         eng.submit_host(host[i & 1], h_out[i & 1], BATCH, _lib.FMT_U8_NHWC4, _lib.FMT_U8_NHWC4, flags)
     eng.wait_host()
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
+    e2e_clocks = sampler_e2e.stop() if rank == 0 else None
     barrier()
     # (c) what the box's host<->device path can carry at this rank count: the same bytes, same 16-frame pieces, H2D and D2H
     # on two streams at once, all ranks concurrently, no kernel in between -- the ceiling of any end-to-end number here
@@ -376,12 +380,16 @@ def main():
                 s_host[f0:f0 + k].copy_(synth.synth_rgb444_frames(k, FRAME_H, FRAME_W, seed=5000, first_frame=lo + f0, device=dev))
             torch.cuda.synchronize(dev)
             barrier()
+            sampler5 = ClockSampler(local)
+            if rank == 0:
+                sampler5.start()
             t0 = time.perf_counter()
             for f0 in range(0, n5, BATCH):
                 k = min(BATCH, n5 - f0)
                 eng.submit_host(s_host[f0:f0 + k], s_out[f0:f0 + k], k, _lib.FMT_U8_NHWC4, _lib.FMT_U8_NHWC4, flags)
             eng.wait_host()
             stream_s = time.perf_counter() - t0
+            clocks5 = sampler5.stop() if rank == 0 else None
             barrier()
             # latency of a piece in the stream: blocking 64-frame calls, submit -> all 64 frames back in host memory
             piece_ms = []
@@ -394,7 +402,8 @@ def main():
             stream5 = {"frames": args.stream_frames, "frames_per_gpu": n5, "sharding": "contiguous ranges (sharding.frame_range)",
                        "value": args.stream_frames / stream_s, "unit": "frames/s", "seconds": stream_s,
                        "piece_frames": BATCH, "piece_latency_p50_ms": pctl(piece_ms, 0.5), "piece_latency_p99_ms": pctl(piece_ms, 0.99),
-                       "api": "fsuae_engine_submit_host per 64-frame piece of the rank's range + one fsuae_engine_wait_host"}
+                       "api": "fsuae_engine_submit_host per 64-frame piece of the rank's range + one fsuae_engine_wait_host",
+                       "clocks": clocks5}
         del s_host, s_out
 
     # sustained leg: the same device-resident step back to back for >= args.sustain seconds (the burst number above is
@@ -463,7 +472,8 @@ def main():
                     "sync_call_api": "one blocking fsuae_engine_run_host per step",
                     "copy_ceiling_fps": BATCH * world * e2e_steps / copy_s,
                     "frac_of_copy_ceiling": (BATCH * world * e2e_steps / e2e_s) / (BATCH * world * e2e_steps / copy_s),
-                    "copy_ceiling_note": "the same H2D + D2H bytes in the same 16-frame pieces on two streams, all ranks at once, no kernel"},
+                    "copy_ceiling_note": "the same H2D + D2H bytes in the same 16-frame pieces on two streams, all ranks at once, no kernel",
+                    "clocks": e2e_clocks},
             "gpu_launches": int(launches_per_step * args.steps),
             "roofline": {"bound": "tensor", "achieved": dom_line["achieved"] if dom_line else achieved_tf, "peak": tf_peak,
                          "unit": "TFLOP/s", "frac": (dom_line["achieved"] if dom_line else achieved_tf) / tf_peak,
