@@ -1975,8 +1975,9 @@ int TC_FN(enqueue_chunk)(fsuae_engine* e, const void* in, void* out, int n, int 
   {
     const int teams = plan->mega_ok ? plan->mega_groups / S : 0;
     // Default: framebuffer (uint8 RGBA) passes of 8 frames or more.  Float / planar frames run correctly through the fused pass
-    // (FSUAE_MEGA_MIN_FRAMES=n sends them there) but its head reads them with plain loads, row by row, and the layer kernels
-    // are faster for those formats at every batch size (64 frames: 38 vs 62 us/frame).
+    // (FSUAE_MEGA_MIN_FRAMES=n sends them there) but its head reads them through registers, one row ahead, instead of the
+    // framebuffer path's cp.async staging two rows ahead, and the layer kernels are faster for those formats at every batch
+    // size (float in -> float out, 64 frames: 42.9 vs 45.5 us/frame).
     const int min_frames = e->tuning.mega_min_frames >= 0 ? e->tuning.mega_min_frames : (in_fmt == FSUAE_FMT_U8_NHWC4 ? 8 : INT_MAX);
     if (teams >= 1 && S <= MG_SMAX && n >= std::max(2, min_frames) &&
         (size_t)teams * 2 * mega_block_bytes(PW) <= plan->mega_scratch_bytes) {

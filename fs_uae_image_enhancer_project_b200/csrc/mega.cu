@@ -94,8 +94,15 @@ __device__ unsigned long long g_mega_t[8][16];     // row 7: the head producer i
 #define MG_T(var)
 #define MG_ACC(cond, L, i, v)
 #endif
-#ifdef MG_DBG_FINISH      // timing experiment: cycles every CTA took from entry to its last engine's last row (per-stage run time)
-__device__ long long g_mega_finish[160];
+#ifdef MG_DBG_FINISH      // timing experiment: cycles every CTA took from entry to its last engine's last row (per-stage run time),
+__device__ long long g_mega_finish[160];            // and its entry / exit on the global timer for the last four launches
+__device__ unsigned long long g_mega_gt[4][2][160];
+__device__ unsigned int g_mega_launch;
+__device__ __forceinline__ unsigned long long mg_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 #endif
 __device__ __forceinline__ unsigned int* mg_cons(unsigned int* fl, int ch, int consumer) {
   return fl + MG_NCH * MG_DMAX + (ch * 2 + consumer) * MG_SMAX;
@@ -450,6 +457,23 @@ __device__ void mg_head_worker(const MegaK& M, const MCtx& c, const float* s_lut
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
+  const bool f32 = M.in_fmt == FSUAE_FMT_F32_NCHW3;
+  float cv[2][12];                               // float frames: the current row's values of my two slots
+  auto ldrow_f32 = [&](int rf, int ry, float (&v)[2][12]) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (!okx[k]) continue;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const float* ip = (const float*)M.frame_in + (size_t)rf * 3 * fpl + (size_t)(2 * ry + dy) * M.W + 2 * xx[k] + M.xoff;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          const float2 t2 = __ldg(reinterpret_cast<const float2*>(ip + ch * fpl));
+          v[k][ch * 4 + dy * 2] = t2.x; v[k][ch * 4 + dy * 2 + 1] = t2.y;
+        }
+      }
+    }
+  };
   int fC, yC, fN = 0, yN = 0, fP = 0, yP = 0;
   bool haveC = next_row(fC, yC), haveN = false;
   uint32_t q = 0, cons_seen = 0, qtotal = 0;
@@ -464,6 +488,7 @@ __device__ void mg_head_worker(const MegaK& M, const MCtx& c, const float* s_lut
     if (haveN) prefetch(fN, yN, stage + MROWS);
   } else if (haveC) {
     haveN = next_row(fN, yN);
+    if (f32) ldrow_f32(fC, yC, cv);
   }
   MG_T(th_begin);
   while (haveC) {
@@ -512,8 +537,25 @@ __device__ void mg_head_worker(const MegaK& M, const MCtx& c, const float* s_lut
           *reinterpret_cast<uint4*>(d + plane_pitch) = make_uint4(pack_op2(v[8], v[9]), pack_op2(v[10], v[11]), 0u, 0u);
         }
       }
+    } else if (f32) {
+      // float frames: the NEXT row's 24 values per lane are requested before this row is stored (registers, one row = ~1.4 us
+      // ahead: about one DRAM round trip), so the loads are in flight under the stores, the barrier and the release
+      float nv[2][12];
+      if (haveN) ldrow_f32(fN, yN, nv);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (okx[k]) {
+          unsigned char* d = dp + (size_t)(xx[k] + BORDER) * 16;
+          *reinterpret_cast<uint4*>(d) = make_uint4(pack_op2(cv[k][0], cv[k][1]), pack_op2(cv[k][2], cv[k][3]), pack_op2(cv[k][4], cv[k][5]), pack_op2(cv[k][6], cv[k][7]));
+          *reinterpret_cast<uint4*>(d + plane_pitch) = make_uint4(pack_op2(cv[k][8], cv[k][9]), pack_op2(cv[k][10], cv[k][11]), 0u, 0u);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int i = 0; i < 12; ++i) cv[k][i] = nv[k][i];
     } else {
-      // float / planar uint8 frames (not the streaming format): this path only has to be correct
+      // planar uint8 frames (not a streaming format): this path only has to be correct
 #pragma unroll 1
       for (int k = 0; k < 2; ++k) {
         if (!okx[k]) continue;
@@ -521,18 +563,9 @@ __device__ void mg_head_worker(const MegaK& M, const MCtx& c, const float* s_lut
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy) {
           const size_t p0 = (size_t)(2 * yC + dy) * M.W + 2 * xx[k] + M.xoff;
-          if (M.in_fmt == FSUAE_FMT_F32_NCHW3) {
-            const float* ip = (const float*)M.frame_in + (size_t)fC * 3 * fpl + p0;
+          const unsigned char* ip = (const unsigned char*)M.frame_in + (size_t)fC * 4 * fpl + p0;
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-              const float2 t2 = __ldg(reinterpret_cast<const float2*>(ip + ch * fpl));
-              v[ch * 4 + dy * 2] = t2.x; v[ch * 4 + dy * 2 + 1] = t2.y;
-            }
-          } else {
-            const unsigned char* ip = (const unsigned char*)M.frame_in + (size_t)fC * 4 * fpl + p0;
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) { v[ch * 4 + dy * 2] = s_lut[__ldg(ip + ch * fpl)]; v[ch * 4 + dy * 2 + 1] = s_lut[__ldg(ip + ch * fpl + 1)]; }
-          }
+          for (int ch = 0; ch < 3; ++ch) { v[ch * 4 + dy * 2] = s_lut[__ldg(ip + ch * fpl)]; v[ch * 4 + dy * 2 + 1] = s_lut[__ldg(ip + ch * fpl + 1)]; }
         }
         unsigned char* d = dp + (size_t)(xx[k] + BORDER) * 16;
         *reinterpret_cast<uint4*>(d) = make_uint4(pack_op2(v[0], v[1]), pack_op2(v[2], v[3]), pack_op2(v[4], v[5]), pack_op2(v[6], v[7]));
@@ -1123,6 +1156,8 @@ template <class ST, class E0, class E1>
 __device__ __forceinline__ void mg_run_stage(const MegaK& M, MCtx& c, uint8_t* smem, float* s_lut, uint4* s_raw, int warp, int lane) {
 #ifdef MG_DBG_FINISH
   const long long t_start = clock64();
+  const unsigned int dbg_slot = g_mega_launch & 3u;            // bumped by the host-side launcher between launches
+  if (threadIdx.x == 0) g_mega_gt[dbg_slot][0][blockIdx.x] = mg_globaltimer();
 #endif
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MG_SMEM - MG_BAR_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 120);
@@ -1188,7 +1223,7 @@ __device__ __forceinline__ void mg_run_stage(const MegaK& M, MCtx& c, uint8_t* s
   tc_fence_before();
   __syncthreads();
 #ifdef MG_DBG_FINISH
-  if (threadIdx.x == 0) g_mega_finish[blockIdx.x] = clock64() - t_start;
+  if (threadIdx.x == 0) { g_mega_finish[blockIdx.x] = clock64() - t_start; g_mega_gt[dbg_slot][1][blockIdx.x] = mg_globaltimer(); }
 #endif
   cluster_sync_all();
   if (warp == 1) tmem_dealloc_2cta(tmem_base, 512);
@@ -1235,6 +1270,12 @@ extern "C" __attribute__((visibility("default"))) int fsuae_debug_mega_finish(lo
   cudaDeviceSynchronize();
   return cudaMemcpyFromSymbol(out, g_mega_finish, sizeof(g_mega_finish)) == cudaSuccess ? 0 : -1;
 }
+extern "C" __attribute__((visibility("default"))) int fsuae_debug_mega_globaltimer(unsigned long long* out, unsigned int* launches) {   // [4][2][160] ns
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(launches, g_mega_launch, sizeof(unsigned int)) != cudaSuccess) return -1;
+  return cudaMemcpyFromSymbol(out, g_mega_gt, sizeof(g_mega_gt)) == cudaSuccess ? 0 : -1;
+}
+__global__ void mg_dbg_next_launch() { g_mega_launch++; }
 #endif
 
 int TC_FN(mega_prepare)() {
@@ -1252,7 +1293,13 @@ int TC_FN(mega_launch)(const MegaK& k, int grid, cudaStream_t st) {
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+#if defined(MG_DBG_FINISH) && !defined(FSUAE_OPERAND_FP16)
+  const cudaError_t ce = cudaLaunchKernelEx(&cfg, fused_pass_kernel, k);
+  mg_dbg_next_launch<<<1, 1, 0, st>>>();
+  return (int)ce;
+#else
   return (int)cudaLaunchKernelEx(&cfg, fused_pass_kernel, k);
+#endif
 }
 
 }  // namespace fsuae

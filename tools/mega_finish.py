@@ -30,3 +30,21 @@ names = ["A conv5+conv2", "B conv4+head", "C conv3+conv7", "D conv6+conv1"]
 for st in range(4):
     v = [out[blk] for blk in range(144) if (blk >> 1) & 3 == st]
     print(f"stage {names[st]}: cycles per row min {min(v) / rows:7.0f}  mean {sum(v) / len(v) / rows:7.0f}  max {max(v) / rows:7.0f}")
+
+# entry / exit of every CTA on the global timer, last four back-to-back launches: how far apart the CTAs of a launch start,
+# how long the launch lives, and the gap to the next one
+for _ in range(8):
+    m.forward_framebuffer(x)
+gt = (C.c_ulonglong * (4 * 2 * 160))()
+nl = C.c_uint(0)
+lib.fsuae_debug_mega_globaltimer(gt, C.byref(nl))
+n = nl.value
+prev_end = None
+for k in range(n - 4, n):
+    sl = k & 3
+    st = [gt[(sl * 2 + 0) * 160 + i] for i in range(144)]
+    en = [gt[(sl * 2 + 1) * 160 + i] for i in range(144)]
+    gap = f"  gap after the previous launch {(min(st) - prev_end) / 1e3:7.1f} us" if prev_end else ""
+    print(f"launch {k}: CTA entries spread over {(max(st) - min(st)) / 1e3:6.1f} us, first entry -> last exit {(max(en) - min(st)) / 1e3:8.1f} us, "
+          f"exits spread over {(max(en) - min(en)) / 1e3:6.1f} us{gap}")
+    prev_end = max(en)
