@@ -958,9 +958,13 @@ __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, ui
           o[0] = __uint_as_float(v[0]) + b0.x; o[1] = __uint_as_float(v[1]) + b0.y; o[2] = __uint_as_float(v[2]) + b0.z;
           o[3] = __uint_as_float(v[3]) + b0.w; o[4] = __uint_as_float(v[4]) + b1.x; o[5] = __uint_as_float(v[5]) + b1.y;
           o[6] = __uint_as_float(v[6]) + b1.z; o[7] = __uint_as_float(v[7]) + b1.w;
+          // A chain that ends in ReLU / ReLU6 gets it on the packed words behind the rounding (one HMNMX2 per two channels instead
+          // of an FMNMX each): rounding is monotone and 0 and 6 are exact in both operand types, so the bits are the same.
+          constexpr bool kTailRelu = EPI::kOp3 == FSUAE_ACT_RELU;
+          constexpr bool kTailRelu6 = !EPI::kSkip && EPI::kOp2 == 0 && EPI::kOp3 == 0 && EPI::kOp1 == FSUAE_ACT_RELU6;
 #ifndef MG_DBG_NOACT      // timing experiment (garbage results): what the pass costs without any activation math
           mg_slot8<EPI::kOp0>(0, prm, o);
-          mg_slot8<EPI::kOp1>(1, prm, o);
+          mg_slot8<kTailRelu6 ? 0 : EPI::kOp1>(1, prm, o);
 #endif
           if constexpr (EPI::kSkip) {
 #pragma unroll
@@ -971,7 +975,7 @@ __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, ui
           }
 #ifndef MG_DBG_NOACT
           mg_slot8<EPI::kOp2>(2, prm, o);
-          mg_slot8<EPI::kOp3>(3, prm, o);
+          mg_slot8<kTailRelu ? 0 : EPI::kOp3>(3, prm, o);
 #endif
           if constexpr (E::COUT % 8 != 0) {
             if (cc == E::OUT_PLANES - 1) {       // padding channels stay exactly zero
@@ -979,8 +983,11 @@ __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, ui
               for (int i = E::COUT % 8; i < 8; ++i) o[i] = 0.f;
             }
           }
-          if (valid)
-            *reinterpret_cast<uint4*>(dpc) = make_uint4(pack_op2(o[0], o[1]), pack_op2(o[2], o[3]), pack_op2(o[4], o[5]), pack_op2(o[6], o[7]));
+          uint4 pk = make_uint4(pack_op2(o[0], o[1]), pack_op2(o[2], o[3]), pack_op2(o[4], o[5]), pack_op2(o[6], o[7]));
+#ifndef MG_DBG_NOACT
+          if constexpr (kTailRelu || kTailRelu6) { pk.x = op2_relu<kTailRelu6>(pk.x); pk.y = op2_relu<kTailRelu6>(pk.y); pk.z = op2_relu<kTailRelu6>(pk.z); pk.w = op2_relu<kTailRelu6>(pk.w); }
+#endif
+          if (valid) *reinterpret_cast<uint4*>(dpc) = pk;
           prm += 8;
           spc += PLANE_ROW;
           dpc += plane_pitch;

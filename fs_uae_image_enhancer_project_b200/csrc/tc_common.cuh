@@ -160,6 +160,22 @@ __device__ __forceinline__ float op_lo(uint32_t w) { return __uint_as_float(w <<
 __device__ __forceinline__ float op_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 #endif
 
+// ReLU (SIX: ReLU6) on a packed pair of operand-type values
+template <bool SIX>
+__device__ __forceinline__ uint32_t op2_relu(uint32_t w) {
+#ifdef FSUAE_OPERAND_FP16
+  __half2 h = *reinterpret_cast<__half2*>(&w);
+  h = __hmax2(h, __float2half2_rn(0.f));
+  if constexpr (SIX) h = __hmin2(h, __float2half2_rn(6.f));
+  return *reinterpret_cast<uint32_t*>(&h);
+#else
+  __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&w);
+  h = __hmax2(h, __float2bfloat162_rn(0.f));
+  if constexpr (SIX) h = __hmin2(h, __float2bfloat162_rn(6.f));
+  return *reinterpret_cast<uint32_t*>(&h);
+#endif
+}
+
 __device__ __forceinline__ uint8_t to_u8_fast(float v, int gamma_out) {
   if (gamma_out) v = __powf(fmaxf(v, 0.f), 1.0f / 2.2f);
   v = fminf(fmaxf(v, 0.f), 1.f) * 255.0f;
