@@ -723,6 +723,23 @@ def test_fused_pass_framebuffer_contract_full_size(crop16):
     assert torch.equal(m.run_host(fb.pin_memory(), crop16=crop16), got)
 
 
+def test_fused_pass_is_the_default_for_framebuffers_only():
+    """From 8 frames on a uint8 RGBA pass is ONE launch; float frames keep the layer kernels (faster for that format) unless
+    FSUAE_MEGA_MIN_FRAMES sends them to the fused pass; both give the same bytes."""
+    spec = O.pix_shuffle_preset("lightweight")
+    sd = O.make_pix_shuffle_state_dict(spec, 12)
+    m = _tc_model(spec, sd, "bf16")
+    fb = O.synth_framebuffers(8, seed=3, h=64, w=96).to(dev())
+    out = m.forward_framebuffer(fb)
+    eng = m.engine_for(dev(), 64, 96)
+    assert eng.last_launch_count == 1, eng.last_launch_count
+    small = m.forward_framebuffer(fb[:7])                                   # below the threshold: layer by layer
+    assert eng.last_launch_count >= 6 and torch.equal(small, out[:7])
+    x = torch.rand(8, 3, 64, 96, generator=torch.Generator().manual_seed(4)).to(dev())
+    m(x)
+    assert eng.last_launch_count >= 6, eng.last_launch_count
+
+
 def test_fused_pass_is_reproducible_under_load():
     """The inter-layer rings are re-used every few microseconds and guarded only by flags: 10 runs of a 64-frame pass must
     give identical bytes, and equal the layer-by-layer result within one rounding step."""
