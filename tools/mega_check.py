@@ -29,6 +29,7 @@ def build(no_mega):
         os.environ["FSUAE_NO_MEGA"] = "1"
     else:
         os.environ.pop("FSUAE_NO_MEGA", None)
+        os.environ.setdefault("FSUAE_MEGA_MIN_FRAMES", "2")      # float frames too (by default they stay on the layer kernels)
     m = model_pix_shuffle.get_model("lightweight")
     m.load_state_dict(sd)
     m = m.to(dev).set_precision("bf16")
