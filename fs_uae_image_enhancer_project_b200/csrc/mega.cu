@@ -97,6 +97,7 @@ __device__ unsigned long long g_mega_t[8][16];     // row 7: the head producer i
 #ifdef MG_DBG_FINISH      // timing experiment: cycles every CTA took from entry to its last engine's last row (per-stage run time),
 __device__ long long g_mega_finish[160];            // and its entry / exit on the global timer for the last four launches
 __device__ unsigned long long g_mega_gt[4][2][160];
+__device__ unsigned long long g_mega_rows[2][8];    // probe CTA: global timer when the head / conv1..7 finished their first and last row
 __device__ unsigned int g_mega_launch;
 __device__ __forceinline__ unsigned long long mg_globaltimer() {
   unsigned long long t;
@@ -582,6 +583,12 @@ __device__ void mg_head_worker(const MegaK& M, const MCtx& c, const float* s_lut
       for (uint32_t qq = q & ~3u; qq <= q; ++qq) red_relaxed_gpu_add(prod + qq % D, 1u);
     }
     MG_T(th3);
+#ifdef MG_DBG_FINISH
+    if (c.probe && w == 0 && lane == 0) {
+      if (q == 0) g_mega_rows[0][0] = mg_globaltimer();
+      if (q + 1u == qtotal) g_mega_rows[1][0] = mg_globaltimer();
+    }
+#endif
     if (haveP && fb) prefetch(fP, yP, stage + ((q + 2u) % 3u) * MROWS);
     MG_T(th4);
     MG_ACC(tprobe, 8, 0, th4 - th3); MG_ACC(tprobe, 8, 1, th1 - th0); MG_ACC(tprobe, 8, 2, th2 - th1); MG_ACC(tprobe, 8, 3, th3 - th2); MG_ACC(tprobe, 8, 4, 1);
@@ -1086,6 +1093,12 @@ __device__ void mg_epilogue(const MegaK& M, const MCtx& c, const MEngSmem& s, ui
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(&s.tempty[stage], 0);
       }
+#ifdef MG_DBG_FINISH
+      if (c.probe && q4 == 0 && lane == 0) {
+        if (q == 0) g_mega_rows[0][E::L] = mg_globaltimer();
+        if (q + (uint32_t)E::NG >= qtotal) g_mega_rows[1][E::L] = mg_globaltimer();       // this warpgroup's last row
+      }
+#endif
       MG_T(te3);
       MG_ACC(tprobe, E::L, 7, te1 - te0); MG_ACC(tprobe, E::L, 8, te2 - te1); MG_ACC(tprobe, E::L, 9, te3 - te2); MG_ACC(tprobe, E::L, 11, 1);
     }
@@ -1281,6 +1294,10 @@ extern "C" __attribute__((visibility("default"))) int fsuae_debug_mega_globaltim
   cudaDeviceSynchronize();
   if (cudaMemcpyFromSymbol(launches, g_mega_launch, sizeof(unsigned int)) != cudaSuccess) return -1;
   return cudaMemcpyFromSymbol(out, g_mega_gt, sizeof(g_mega_gt)) == cudaSuccess ? 0 : -1;
+}
+extern "C" __attribute__((visibility("default"))) int fsuae_debug_mega_rows(unsigned long long* out) {   // [2][8] ns: first / last row of head, conv1..7
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out, g_mega_rows, sizeof(g_mega_rows)) == cudaSuccess ? 0 : -1;
 }
 __global__ void mg_dbg_next_launch() { g_mega_launch++; }
 #endif

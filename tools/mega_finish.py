@@ -48,3 +48,15 @@ for k in range(n - 4, n):
     print(f"launch {k}: CTA entries spread over {(max(st) - min(st)) / 1e3:6.1f} us, first entry -> last exit {(max(en) - min(st)) / 1e3:8.1f} us, "
           f"exits spread over {(max(en) - min(en)) / 1e3:6.1f} us{gap}")
     prev_end = max(en)
+
+# the probe CTAs (team 0, middle strip, leader) of the last launch: when each engine finished its first and its last row,
+# relative to the launch's first CTA entry -- the fill and the drain of the pipeline, hop by hop
+rows_t = (C.c_ulonglong * 16)()
+lib.fsuae_debug_mega_rows(rows_t)
+sl = (n - 1) & 3
+t0 = min(gt[(sl * 2 + 0) * 160 + i] for i in range(144))
+t1 = max(gt[(sl * 2 + 1) * 160 + i] for i in range(144))
+names = ["head"] + [f"conv{i}" for i in range(1, 8)]
+print("engine : first row done at / last row done before the end of the launch (us)")
+for i, nm in enumerate(names):
+    print(f"{nm:6s} : {(rows_t[i] - t0) / 1e3:8.1f}   {(t1 - rows_t[8 + i]) / 1e3:8.1f}")
